@@ -1,0 +1,372 @@
+// bf16 x bf16 -> fp32-accumulate GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   for every batch z = (zo, zi):   C[z] = epilogue( alpha * A[z] (M x K)  *  B[z'] (N x K)^T )
+//
+// Both operands are K-major (the natural layout of torch.nn.Linear: activations [rows, K],
+// weights [out, K]); the same kernel serves every Linear on the hot path (ViT qkv / out_proj /
+// MLP, projector, the mu2-tokenizer wq/wk/wv/dense, decoder q/k/v/o/gate/up/down, lm_head) and,
+// through the 4-D batch coordinates, the QK^T and PV contractions of the attention blocks.
+//
+// Structure (persistent, warp specialised, 1 CTA per SM):
+//   warp 0   : TMA producer   - 4-D tiled loads of A/B k-blocks into a kStages-deep smem ring
+//   warp 1   : MMA issuer     - one thread issues tcgen05.mma (128 x BLOCK_N x 16), accumulators
+//                               live in TMEM, double buffered so the epilogue overlaps the next tile
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue       - tcgen05.ld TMEM -> registers, alpha/bias/activation/residual, store
+//
+// Reference call sites this replaces: every nn.Linear / torch.matmul on the path, e.g.
+// src/model/u2tokenizer/rma.py:52-58,60-73 and tta.py:42-69 (reference repo paths).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+#include "u2b200.h"
+
+namespace u2 {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int kBlockN>
+struct GemmCfg {
+  static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = kBlockN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;  // double-buffered accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmDev {
+  int M, N, K;
+  int zi, zo, b_zi_div;
+  long long ldc, c_stride_zi, c_stride_zo;
+  int c_dtype;
+  float alpha;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  int res_row_mod;
+  int row_div, row_stride, row_off;
+  void* C;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == U2_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (act == U2_ACT_SILU) return x / (1.0f + __expf(-x));
+  return x;
+}
+
+template <int kBlockN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
+  using Cfg = GemmCfg<kBlockN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + kStages;            // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n_blocks = (p.N + kBlockN - 1) / kBlockN;
+  const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int tiles_per_batch = num_m_blocks * num_n_blocks;
+  const int num_tiles = tiles_per_batch * p.zi * p.zo;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_batch;
+        const int t = tile - z * tiles_per_batch;
+        const int n_blk = t / num_m_blocks;
+        const int m_blk = t - n_blk * num_m_blocks;
+        const int zo_i = z / p.zi;
+        const int zi_i = z - zo_i * p.zi;
+        const int zi_b = zi_i / p.b_zi_div;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBlockK,
+                      m_blk * kBlockM, zi_i, zo_i);
+          tma_load_4d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK,
+                      n_blk * kBlockN, zi_b, zo_i);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance the start address by k * 16 elements * 2 B = 32 B (>>4 -> +2) inside the swizzle row
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx >= kEpiWarp0) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp_idx - kEpiWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_batch;
+      const int t = tile - z * tiles_per_batch;
+      const int n_blk = t / num_m_blocks;
+      const int m_blk = t - n_blk * num_m_blocks;
+      const int zo_i = z / p.zi;
+      const int zi_i = z - zo_i * p.zi;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int row = m_blk * kBlockM + q * 32 + lane;  // row of the logical (M x N) output
+      const bool row_ok = row < p.M;
+      long long out_row = row;
+      if (p.row_div > 0) out_row = (long long)(row / p.row_div) * p.row_stride + p.row_off + row % p.row_div;
+      const long long zoff = (long long)zo_i * p.c_stride_zo + (long long)zi_i * p.c_stride_zi;
+      const long long c_off = zoff + out_row * p.ldc;
+      const long long res_row = p.res_row_mod > 0 ? (long long)(row % p.res_row_mod) : out_row;
+      const __nv_bfloat16* res_ptr =
+          p.residual ? p.residual + (p.res_row_mod > 0 ? 0 : zoff) + res_row * p.ldr : nullptr;
+
+      const uint32_t taddr = tmem_base + acc * kBlockN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+        const int col0 = n_blk * kBlockN + c0;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          const bool full = (col0 + 32 <= p.N);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.act != U2_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          }
+          if (res_ptr) {
+            if (full && ((p.ldr & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + col0 + j);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rf = __bfloat1622float2(r2[e]);
+                  f[j + 2 * e] += rf.x;
+                  f[j + 2 * e + 1] += rf.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
+            }
+          }
+          if (p.c_dtype == U2_DT_BF16) {
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + col0;
+            if (full && ((p.ldc & 7) == 0) && ((c_off & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(c + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) c[j] = __float2bfloat16(f[j]);
+            }
+          } else {
+            float* c = reinterpret_cast<float*>(p.C) + c_off + col0;
+            if (full && ((p.ldc & 3) == 0) && ((c_off & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) c[j] = f[j];
+            }
+          }
+        }
+      }
+      // hand the accumulator buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int kBlockN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int num_sms,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<kBlockN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kBlockN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + kBlockN - 1) / kBlockN;
+  const long long tiles = (long long)num_m * num_n * p.zi * p.zo;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  gemm_bf16_tcgen05_kernel<kBlockN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  return U2_OK;
+}
+
+}  // namespace u2
+
+extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const u2_gemm_desc* d, void* stream) {
+  using namespace u2;
+  if (!A || !B || !C || !d) return set_error(U2_ERR_ARG, "gemm: null pointer");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return set_error(U2_ERR_ARG, "gemm: M,N,K must be > 0");
+  const int zi = d->zi > 0 ? d->zi : 1, zo = d->zo > 0 ? d->zo : 1;
+  const int bdiv = d->b_zi_div > 0 ? d->b_zi_div : 1;
+  if ((d->lda & 7) || (d->ldb & 7)) return set_error(U2_ERR_ARG, "gemm: lda/ldb must be multiples of 8 elements (16 B, TMA)");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return set_error(U2_ERR_ARG, "gemm: A/B must be 16-byte aligned");
+  if (zi > 1 && ((d->a_stride_zi & 7) || (d->b_stride_zi & 7))) return set_error(U2_ERR_ARG, "gemm: inner batch strides must be multiples of 8 elements");
+  if (zo > 1 && ((d->a_stride_zo & 7) || (d->b_stride_zo & 7))) return set_error(U2_ERR_ARG, "gemm: outer batch strides must be multiples of 8 elements");
+
+  int block_n = d->block_n;
+  if (block_n == 0) {
+    // pick the widest tile that still fills the machine reasonably
+    const long long m_tiles = (d->M + 127) / 128;
+    const long long z = (long long)zi * zo;
+    if (d->N <= 64) block_n = 64;
+    else if (d->N <= 128) block_n = 128;
+    else {
+      const long long t256 = m_tiles * ((d->N + 255) / 256) * z;
+      block_n = (t256 >= 2LL * num_sms()) || (d->N % 256 == 0 && t256 >= num_sms()) ? 256 : 128;
+    }
+  }
+  if (block_n != 64 && block_n != 128 && block_n != 256) return set_error(U2_ERR_ARG, "gemm: block_n must be 0/64/128/256");
+
+  CUtensorMap ta, tb;
+  const int zi_b = (zi + bdiv - 1) / bdiv;
+  int rc = make_tmap_bf16_4d(&ta, A, d->K, d->M, zi, zo, d->lda, zi > 1 ? d->a_stride_zi : 0, zo > 1 ? d->a_stride_zo : 0, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_4d(&tb, B, d->K, d->N, zi_b, zo, d->ldb, zi_b > 1 ? d->b_stride_zi : 0, zo > 1 ? d->b_stride_zo : 0, kBlockK, block_n);
+  if (rc) return rc;
+
+  GemmDev p;
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.zi = zi; p.zo = zo; p.b_zi_div = bdiv;
+  p.ldc = d->ldc; p.c_stride_zi = d->c_stride_zi; p.c_stride_zo = d->c_stride_zo;
+  p.c_dtype = d->c_dtype;
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.act = d->act;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p.ldr = d->ldr;
+  p.res_row_mod = d->res_row_mod;
+  p.row_div = d->row_div; p.row_stride = d->row_stride; p.row_off = d->row_off;
+  p.C = C;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 64: return launch_gemm<64>(ta, tb, p, num_sms(), s);
+    case 128: return launch_gemm<128>(ta, tb, p, num_sms(), s);
+    default: return launch_gemm<256>(ta, tb, p, num_sms(), s);
+  }
+}
