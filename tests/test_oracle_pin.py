@@ -1,0 +1,149 @@
+"""Pin the oracle (oracle/u2_oracle.py) against the REFERENCE modules imported unmodified from
+/root/reference, and the decoder restatement against the installed HF transformers models.
+
+Runs only where the reference tree is mounted (the authoring container); elsewhere the committed
+golden fixtures (tests/test_golden.py) carry the same pin."""
+import math
+
+import pytest
+import torch
+
+from common import fp32_sd, rel_err, tiny_geometry
+from oracle import u2_oracle as O
+import refshim
+
+needs_ref = pytest.mark.skipif(not refshim.have_reference(), reason="reference tree not mounted")
+TOL = 2e-5
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@needs_ref
+@pytest.mark.parametrize("attn_type", ["rma", "rope"])
+@pytest.mark.parametrize("diffts,dmtp,multi", [(True, True, True), (False, False, True), (True, False, False)])
+def test_u2tokenizer_matches_reference(attn_type, diffts, dmtp, multi):
+    refshim.install()
+    from src.model.u2tokenizer.u2Tokenizer import u2Tokenizer
+    g = tiny_geometry(attn_type=attn_type, enable_diffts=diffts, enable_dmtp=dmtp, use_multi_scale=multi)
+    sd = fp32_sd(g, seed=3)
+    ref = u2Tokenizer(embed_size=g.hidden_size, num_heads=g.u2t_num_heads, num_layers=g.u2t_num_layers,
+                      top_k=g.u2t_top_k, use_multi_scale=multi, num_3d_query_token=g.num_3d_query_token,
+                      hidden_size=g.hidden_size, attn_type=attn_type, enable_diffts=diffts, enable_dmtp=dmtp)
+    missing, unexpected = ref.load_state_dict(_sub(sd, "model.u2tokenizer."), strict=True)
+    torch.manual_seed(0)
+    v = torch.randn(2, 3, g.tokens_per_frame, g.hidden_size)
+    t = torch.randn(2, 5, g.hidden_size)
+    with torch.no_grad():
+        want = ref(v_token=v, t_token=t)
+        got = O.u2tokenizer(sd, "model.u2tokenizer.", v, t, g)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL
+
+
+@needs_ref
+@pytest.mark.parametrize("ptype", ["spatial", "sequence"])
+def test_projector_matches_reference(ptype):
+    refshim.install()
+    from src.model.multimodal_projector.spatial_pooling_projector import SpatialPoolingProjector
+    g = tiny_geometry(proj_pooling_type=ptype)
+    sd = fp32_sd(g, seed=4)
+    ref = SpatialPoolingProjector(image_size=g.image_size, patch_size=g.patch_size, in_dim=g.vit_hidden,
+                                  out_dim=g.hidden_size, layer_type=g.proj_layer_type, layer_num=g.proj_layer_num,
+                                  pooling_type=ptype, pooling_size=g.proj_pooling_size)
+    ref.load_state_dict(_sub(sd, "model.mm_projector."), strict=True)
+    x = torch.randn(3, g.n_patches, g.vit_hidden)
+    with torch.no_grad():
+        want = ref(x)
+        got = O.spatial_pooling_projector(sd, "model.mm_projector.", x, g)
+    assert ref.proj_out_num == g.tokens_per_frame or ptype == "sequence"
+    assert rel_err(got, want) < TOL
+
+
+def _hf_cfg_kwargs(g):
+    return dict(hidden_size=g.hidden_size, intermediate_size=g.intermediate_size,
+                num_hidden_layers=g.num_hidden_layers, num_attention_heads=g.num_attention_heads,
+                num_key_value_heads=g.num_key_value_heads, head_dim=g.head_dim, vocab_size=g.vocab_size,
+                rms_norm_eps=g.rms_norm_eps, max_position_embeddings=4096,
+                tie_word_embeddings=g.tie_word_embeddings, attention_bias=False)
+
+
+@needs_ref
+def test_full_model_matches_reference_llama():
+    """forward() logits and greedy generate() ids of the reference u2LlamaForCausalLM (with the
+    MONAI stand-in) equal the oracle's: pins the splice, the generate contract and the wiring."""
+    refshim.install()
+    from src.model.language_model.u2llama import u2Config, u2LlamaForCausalLM
+    from u2tokenizer_b200.configuration import MM_DEFAULTS
+    rs = dict(factor=32.0, high_freq_factor=4.0, low_freq_factor=1.0,
+              original_max_position_embeddings=64, rope_type="llama3")
+    g = tiny_geometry(qk_norm=False, rope_theta=500000.0, rope_scaling=rs, rms_norm_eps=1e-5)
+    cfg = u2Config(**_hf_cfg_kwargs(g), rope_parameters=dict(rope_theta=g.rope_theta, **rs))
+    for k, v in MM_DEFAULTS.items():
+        setattr(cfg, k, v)
+    cfg.image_size, cfg.patch_size = g.image_size, g.patch_size
+    cfg.u2t_num_layers, cfg.u2t_top_k, cfg.num_3d_query_token = g.u2t_num_layers, g.u2t_top_k, g.num_3d_query_token
+    cfg.mm_hidden_size = g.vit_hidden
+    cfg.pretraining_tp = 1
+    torch.manual_seed(0)
+    import src.model.multimodal_encoder.vit as refvit
+    # the reference builds ViT-B/12 from MONAI defaults; shrink it through the same constructor args
+    orig = refvit.ViT.__init__
+
+    def small_init(self, *a, **kw):
+        kw.update(hidden_size=g.vit_hidden, mlp_dim=g.vit_mlp, num_layers=g.vit_layers, num_heads=g.vit_heads)
+        orig(self, *a, **kw)
+    refvit.ViT.__init__ = small_init
+    try:
+        model = u2LlamaForCausalLM(cfg)
+        from src.model.u2tokenizer.builder import build_u2tokenizer_tower
+        model.get_model().u2tokenizer = build_u2tokenizer_tower(cfg)
+    finally:
+        refvit.ViT.__init__ = orig
+    sd = fp32_sd(g, seed=5)
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all("rotary" in k or "inv_freq" in k for k in res.missing_keys), res.missing_keys
+    model.eval().float()
+    from u2tokenizer_b200.synthetic import synthetic_inputs
+    images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12, im_patch_id=g.vocab_size - 2)
+    with torch.no_grad():
+        want = model(images=images, input_ids=ids, question_ids=qids).logits
+        got = O.forward_logits(sd, ids, images, qids, g)
+        assert rel_err(got, want) < 1e-4
+        want_ids = model.generate(images, ids, question_ids=qids, max_new_tokens=6, do_sample=False)
+        got_ids, margins = O.greedy_generate(sd, ids, images, qids, g, max_new_tokens=6)
+    assert torch.equal(got_ids, want_ids[:, -6:]) or bool((margins.min() < 1e-4))
+    assert torch.equal(got_ids, want_ids[:, -6:])
+
+
+@pytest.mark.parametrize("family", ["qwen3", "llama"])
+def test_decoder_matches_hf(family):
+    """The decoder restatement equals the installed HF implementation (prefill + cached decode)."""
+    from transformers import LlamaConfig, LlamaForCausalLM, Qwen3Config, Qwen3ForCausalLM
+    if family == "qwen3":
+        g = tiny_geometry()
+        hf = Qwen3ForCausalLM(Qwen3Config(**_hf_cfg_kwargs(g), rope_parameters=dict(rope_theta=g.rope_theta, rope_type="default")))
+    else:
+        rs = dict(factor=8.0, high_freq_factor=4.0, low_freq_factor=1.0, original_max_position_embeddings=16,
+                  rope_type="llama3")
+        g = tiny_geometry(qk_norm=False, rope_theta=500000.0, rope_scaling=rs, tie_word_embeddings=True)
+        hf = LlamaForCausalLM(LlamaConfig(**_hf_cfg_kwargs(g), rope_parameters=dict(rope_theta=g.rope_theta, **rs)))
+    sd = fp32_sd(g, seed=6)
+    dec = {k: v for k, v in sd.items() if k.startswith("model.layers") or k in
+           ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight")}
+    res = hf.load_state_dict(dec, strict=False)
+    assert not res.unexpected_keys
+    hf.eval().float()
+    if g.tie_word_embeddings:
+        hf.tie_weights()
+    emb = torch.randn(2, 40, g.hidden_size)
+    with torch.no_grad():
+        want = hf(inputs_embeds=emb, use_cache=True)
+        got, past = O.decoder_forward(sd, emb, g)
+        assert rel_err(got, want.logits) < 1e-4
+        nxt = torch.randn(2, 1, g.hidden_size)
+        want2 = hf(inputs_embeds=nxt, past_key_values=want.past_key_values, use_cache=True).logits
+        got2, _ = O.decoder_forward(sd, nxt, g, past)
+        assert rel_err(got2, want2) < 1e-4
