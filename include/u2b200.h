@@ -80,6 +80,123 @@ typedef struct u2_gemm_desc {
 
 U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const u2_gemm_desc* desc, void* stream);
 
+/* Row-wise normalisation ----------------------------------------------------------------------------
+ * y = LayerNorm(x [+ residual]) * gamma + beta   (fp32 statistics, eps inside the sqrt)
+ * y = RMSNorm (x [+ residual]) * gamma
+ * x, residual, y, sum_out: bf16 rows of E elements (row strides ldx/ldr/ldy, multiples of 8);
+ * gamma/beta fp32 [E]. When residual and sum_out are given, sum_out receives x + residual (the new
+ * residual stream, row stride ldy). Replaces nn.LayerNorm (MONAI TransformerBlock norm1/norm2, ViT
+ * final norm vit.py:123; tta.py:95,99,103) and HF Qwen3RMSNorm / LlamaRMSNorm.
+ */
+U2_API int u2_layernorm_bf16(const void* x, const void* residual, const float* gamma, const float* beta,
+                             void* y, void* sum_out, int64_t rows, int32_t E, int64_t ldx, int64_t ldr,
+                             int64_t ldy, float eps, void* stream);
+U2_API int u2_rmsnorm_bf16(const void* x, const void* residual, const float* gamma, void* y, void* sum_out,
+                           int64_t rows, int32_t E, int64_t ldx, int64_t ldr, int64_t ldy, float eps,
+                           void* stream);
+
+/* Softmax over fp32 score rows -> bf16 probabilities ---------------------------------------------------
+ * Rows are indexed (i0 batch, i1 head in [0,H), i2 query in [0,S)); element strides given for input
+ * and output. p[j] = softmax_j(in[j] * scale + rel_bias[(j - i2 + rel_max - 1) * H + i1]) over the
+ * visible keys j < n (and j <= i2 + causal_off when causal). Columns [n, zero_pad_to) are written 0.
+ * Replaces F.softmax in rma.py:60-73 (relative bias gather included), tta.py:55-57, the MONAI
+ * SABlock softmax and the HF eager attention softmax + causal mask.
+ */
+typedef struct u2_softmax_desc {
+  int64_t in_s0, in_s1, in_s2;
+  int64_t out_s0, out_s1, out_s2;
+  int32_t n0, H, S, n;
+  float scale;
+  const float* rel_bias;
+  int32_t rel_max;
+  int32_t causal, causal_off;
+  int32_t zero_pad_to;
+} u2_softmax_desc;
+U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_softmax_desc* desc, void* stream);
+
+/* out[r, i] = silu(gate_up[r, i]) * gate_up[r, I + i]  (HF Qwen3MLP / LlamaMLP act_fn(gate) * up) */
+U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t rows, int32_t I, int64_t ldg,
+                            int64_t ldo, void* stream);
+
+/* Vision-front data movement ----------------------------------------------------------------------------
+ * patchify: fp32 volume [frames, d0, d1, d2] -> bf16 patch rows [frames * n_patches, p0*p1*p2] in the
+ * MONAI "perceptron" order "b c (h p1) (w p2) (d p3) -> b (h w d) (p1 p2 p3 c)", c == 1
+ * (reference vit.py:90-99 -> MONAI PatchEmbeddingBlock).
+ */
+U2_API int u2_patchify_f32_bf16(const float* vol, void* rows, int64_t frames, int32_t d0, int32_t d1,
+                                int32_t d2, int32_t p0, int32_t p1, int32_t p2, void* stream);
+/* dst[(r * row_stride + row_off), :] = vec for r in [0, n_rows)   (cls token rows, vit.py:116-118) */
+U2_API int u2_set_rows_bf16(void* dst, const void* vec, int64_t n_rows, int64_t row_stride, int64_t row_off,
+                            int32_t E, void* stream);
+/* in[b][s][h][d] (element strides in_sb, in_ss, in_sh; d contiguous) -> out[b][h][d][s] with the s axis
+ * padded to ld_out (zeros): the K-major V^T operand of the PV contraction. */
+U2_API int u2_transpose_heads_bf16(const void* in, void* out, int32_t B, int32_t S, int32_t H, int32_t Dh,
+                                   int64_t in_sb, int64_t in_ss, int64_t in_sh, int64_t out_sb,
+                                   int64_t out_sh, int64_t ld_out, void* stream);
+/* SpatialPoolingProjector pooling (spatial_pooling_projector.py:38-46): token (a0,a1,a2) of frame f lives
+ * at row f*in_frame_stride + in_off + (a0*g1+a1)*g2+a2 (row stride ldx); out [frames, n_out, E] dense.
+ * sequence != 0 selects the avg_pool1d(ps^3) variant. */
+U2_API int u2_spp_pool_bf16(const void* x, void* out, int64_t frames, int32_t g0, int32_t g1, int32_t g2,
+                            int32_t ps, int32_t E, int64_t in_frame_stride, int64_t in_off, int64_t ldx,
+                            int32_t sequence, void* stream);
+/* Multi-scale token pooling, scales (1,2,4) over the token dim of x [B, K, E] -> out [B, K+K/2+K/4, E];
+ * dynamic != 0: DynamicMultiScalePooling gate (svr.py:126-151) with gate_w [E] fp32, gate_bias scalar and a
+ * [B,3] fp32 workspace; dynamic == 0: the plain concat (svr.py:175-184). */
+U2_API int u2_multiscale_pool_bf16(const void* x, void* out, const float* gate_w, float gate_bias,
+                                   float* logits_ws, int32_t B, int32_t K, int32_t E, int32_t dynamic,
+                                   void* stream);
+/* out[b][l] = vis[b][l-1] for 1 <= l <= n_vis (when vis != NULL) else table[ids[b][l]]
+ * (u2_arch.py:118-121: embed_tokens gather + cat splice). ids int64. */
+U2_API int u2_embed_splice_bf16(const int64_t* ids, const void* table, const void* vis, void* out, int32_t B,
+                                int32_t L, int32_t E, int32_t n_vis, int64_t vocab, void* stream);
+
+/* Small attention pieces ----------------------------------------------------------------------------------
+ * temporal attention of the SVR layer (svr.py:33-36 with rma.py:60-73): qkv rows ordered (b, c, n),
+ * columns [q|k|v] (E each); attends across the C <= 32 frames of each (b, n, head). rel_bias as above. */
+U2_API int u2_temporal_attention_bf16(const void* qkv, void* out, int32_t B, int32_t C, int32_t N, int32_t H,
+                                      int32_t dh, int64_t ld_qkv, int64_t ld_out, float scale,
+                                      const float* rel_bias, int32_t rel_max, void* stream);
+
+/* In-place rotate-half RoPE on the first n_q_heads + n_k_heads heads of every row (optionally preceded by
+ * the per-head RMSNorm of Qwen3, HF modeling_qwen3.py:263-268), and optional KV-cache append
+ * (caches [B, n_k_heads, Tmax, dh]). position(row) = pos0 + (row / pos_div) % pos_mod; pos0 may be read
+ * from the device (pos0_dev). Also used for attn_type == "rope" of the tokenizer (rope.py:77-80). */
+typedef struct u2_rope_desc {
+  int64_t rows, ld;
+  int32_t dh, n_q_heads, n_k_heads, n_v_heads;
+  const float* q_norm_w;
+  const float* k_norm_w;
+  float eps;
+  const float* inv_freq; /* [dh/2] fp32 */
+  int32_t pos0, pos_div, pos_mod;
+  const int32_t* pos0_dev;
+  void* k_cache;
+  void* v_cache;
+  int32_t Tmax, rows_per_batch;
+} u2_rope_desc;
+U2_API int u2_rope_bf16(void* x, const u2_rope_desc* desc, void* stream);
+
+/* One query token per sequence against the KV cache (GQA). q [B, Hq*dh] (row stride ldq), caches
+ * [B, Hkv, Tmax, dh]; T valid keys (or *T_dev when T_dev != NULL). */
+U2_API int u2_decode_attention_bf16(const void* q, const void* k_cache, const void* v_cache, void* out,
+                                    int32_t B, int32_t Hq, int32_t Hkv, int32_t dh, int32_t Tmax, int32_t T,
+                                    const int32_t* T_dev, int64_t ldq, int64_t ldo, float scale, void* stream);
+
+/* Decode-step linear (weight streaming, HBM-bound): y[b, n] = sum_k norm(x)[b, k] * w[n, k] (+ residual).
+ * B <= 8. norm_gamma != NULL fuses the input RMSNorm; silu_pair != 0 treats w as [gate; up] halves and
+ * writes silu(gate) * up (N/2 outputs). */
+typedef struct u2_gemv_desc {
+  int32_t B, N, K;
+  int64_t ldx, ldw, ldy, ldr;
+  int32_t y_dtype;
+  const void* residual;
+  const float* norm_gamma;
+  float norm_eps;
+  int32_t silu_pair;
+} u2_gemv_desc;
+U2_API int u2_gemv_bf16(const void* x, const void* w, void* y, const u2_gemv_desc* desc, void* stream);
+U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,265 @@
+"""Each CUDA op (C ABI) against the same arithmetic in fp32 torch on identical bf16 inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gen(seed):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def close(out, ref, tol=1e-2):
+    err = (out.float() - ref.float()).abs().max().item()
+    scale = ref.float().abs().max().item() + 1e-6
+    assert err / scale < tol, f"max abs err {err:.4g} vs scale {scale:.4g}"
+
+
+@pytest.mark.parametrize("E", [96, 768, 2048, 4096])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layernorm_rmsnorm(E, with_res):
+    from u2tokenizer_b200 import ops
+    g = gen(E)
+    x = torch.randn(37, E, device=DEV, generator=g).bfloat16()
+    r = torch.randn(37, E, device=DEV, generator=g).bfloat16() if with_res else None
+    gamma = 1 + 0.1 * torch.randn(E, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(E, device=DEV, generator=g)
+    xs = x.float() + (r.float() if with_res else 0)
+    y = ops.layernorm(x, gamma, beta, 1e-5, residual=r)
+    close(y, F.layer_norm(xs, (E,), gamma, beta, 1e-5))
+    so = torch.empty_like(x) if with_res else None
+    y = ops.rmsnorm(x, gamma, 1e-6, residual=r, sum_out=so)
+    if with_res:
+        close(so, xs, 5e-3)
+        xs = so.float()
+    close(y, gamma * xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + 1e-6))
+
+
+@pytest.mark.parametrize("S,n", [(7, 7), (256, 256), (40, 1792), (33, 2049), (64, 300)])
+@pytest.mark.parametrize("mode", ["plain", "rel", "causal"])
+def test_softmax(S, n, mode):
+    from u2tokenizer_b200 import ops
+    if mode == "rel" and (S != n or n > 512):
+        pytest.skip("relative bias needs square S<=512")
+    if mode == "causal" and S > n:
+        pytest.skip()
+    B, H = 2, 3
+    g = gen(S * 31 + n)
+    ld = (n + 7) // 8 * 8
+    sc = torch.randn(B, H, S, ld, device=DEV, generator=g) * 3
+    out = torch.full((B, H, S, ld), 7.0, device=DEV, dtype=torch.bfloat16)
+    rel = torch.randn(1023, H, device=DEV, generator=g) if mode == "rel" else None
+    off = n - S
+    ops.softmax(sc, out, n0=B, H=H, S=S, n=n, in_strides=(H * S * ld, S * ld, ld), out_strides=(H * S * ld, S * ld, ld),
+                scale=0.5, rel_bias=rel, rel_max=512, causal=(mode == "causal"), causal_off=off, zero_pad_to=ld)
+    ref = sc[..., :n] * 0.5
+    if rel is not None:
+        pos = torch.arange(n, device=DEV)
+        ref = ref + rel[pos[None, :] - pos[:, None] + 511].permute(2, 0, 1)[None]
+    if mode == "causal":
+        i = torch.arange(S, device=DEV)[:, None]
+        j = torch.arange(n, device=DEV)[None, :]
+        ref = ref.masked_fill(j > i + off, float("-inf"))
+    close(out[..., :n], torch.softmax(ref, -1), 1e-2)
+    assert out[..., n:].abs().max().item() == 0 if ld > n else True
+
+
+def test_silu_mul():
+    from u2tokenizer_b200 import ops
+    gu = torch.randn(50, 2 * 768, device=DEV, generator=gen(1)).bfloat16()
+    close(ops.silu_mul(gu), F.silu(gu[:, :768].float()) * gu[:, 768:].float())
+
+
+def test_patchify():
+    from u2tokenizer_b200 import ops
+    vol = torch.rand(3, 8, 32, 48, device=DEV, generator=gen(2))
+    p = (4, 16, 16)
+    out = ops.patchify(vol, p)
+    x = vol.view(3, 1, 2, 4, 2, 16, 3, 16).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(3 * 12, 1024)
+    assert torch.equal(out, x.bfloat16())
+
+
+def test_set_rows_transpose():
+    from u2tokenizer_b200 import ops
+    g = gen(3)
+    x = torch.zeros(4, 10, 64, device=DEV, dtype=torch.bfloat16)
+    v = torch.randn(64, device=DEV, generator=g).bfloat16()
+    ops.set_rows(x, v, 4, 10, 0)
+    assert torch.equal(x[:, 0], v.expand(4, 64)) and x[:, 1:].abs().max().item() == 0
+    B, S, H, Dh = 2, 45, 3, 40
+    t = torch.randn(B, S, 3 * H * Dh, device=DEV, generator=g).bfloat16()  # fused qkv; take the V part
+    ld = 48
+    out = torch.full((B, H, Dh, ld), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.transpose_heads(t[:, :, 2 * H * Dh:], out, B=B, S=S, H=H, Dh=Dh, in_strides=(S * 3 * H * Dh, 3 * H * Dh, Dh),
+                        out_strides=(H * Dh * ld, Dh * ld), ld_out=ld)
+    ref = t[:, :, 2 * H * Dh:].view(B, S, H, Dh).permute(0, 2, 3, 1)
+    assert torch.equal(out[..., :S], ref) and out[..., S:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("sequence", [False, True])
+def test_spp_pool(sequence):
+    from u2tokenizer_b200 import ops
+    Fr, g0, g1, g2, E, S_pad = 3, 4, 6, 8, 96, 200
+    x = torch.randn(Fr, S_pad, E, device=DEV, generator=gen(4)).bfloat16()
+    n_out = (g0 // 2) * (g1 // 2) * (g2 // 2)
+    out = torch.empty(Fr, n_out, E, device=DEV, dtype=torch.bfloat16)
+    ops.spp_pool(x, out, frames=Fr, grid=(g0, g1, g2), ps=2, E=E, in_frame_stride=S_pad, in_off=1, ldx=E, sequence=sequence)
+    tok = x[:, 1:1 + g0 * g1 * g2].float()
+    if sequence:
+        ref = F.avg_pool1d(tok.permute(0, 2, 1), 8, 8).permute(0, 2, 1)
+    else:
+        ref = F.avg_pool3d(tok.view(Fr, g0, g1, g2, E).permute(0, 4, 1, 2, 3), 2, 2).permute(0, 2, 3, 4, 1).reshape(Fr, -1, E)
+    close(out, ref, 5e-3)
+
+
+@pytest.mark.parametrize("K", [1024, 8, 7, 3, 1])
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_multiscale_pool(K, dynamic):
+    from u2tokenizer_b200 import ops
+    B, E = 2, 256
+    g = gen(K)
+    x = torch.randn(B, K, E, device=DEV, generator=g).bfloat16()
+    w = torch.randn(E, device=DEV, generator=g) * 0.3
+    bias = 0.1
+    out = ops.multiscale_pool(x, w, bias, dynamic)
+    xf = x.float()
+    pooled, gates = [], []
+    for s in (1, 2, 4):
+        if K >= s:
+            p = F.avg_pool1d(xf.permute(0, 2, 1), s, s).permute(0, 2, 1)
+            pooled.append(p)
+            gates.append(p.mean(1) @ w[:, None] + bias)
+    if dynamic:
+        wts = torch.softmax(torch.cat(gates, 1), 1)
+        ref = torch.cat([p * wts[:, i].view(-1, 1, 1) for i, p in enumerate(pooled)], 1)
+    else:
+        ref = torch.cat(pooled, 1)
+    assert out.shape == ref.shape
+    close(out, ref, 1e-2)
+
+
+def test_embed_splice():
+    from u2tokenizer_b200 import ops
+    g = gen(6)
+    table = torch.randn(100, 64, device=DEV, generator=g).bfloat16()
+    ids = torch.randint(0, 100, (2, 12), device=DEV, generator=g)
+    vis = torch.randn(2, 5, 64, device=DEV, generator=g).bfloat16()
+    out = ops.embed_splice(ids, table, vis)
+    emb = table[ids]
+    ref = torch.cat((emb[:, :1], vis, emb[:, 6:]), 1)
+    assert torch.equal(out, ref)
+    assert torch.equal(ops.embed_splice(ids, table, None), emb)
+
+
+@pytest.mark.parametrize("C_,dh", [(8, 512), (3, 32), (1, 64), (16, 256)])
+@pytest.mark.parametrize("rel", [True, False])
+def test_temporal_attention(C_, dh, rel):
+    from u2tokenizer_b200 import ops
+    B, N, H = 2, 5, 4
+    E = H * dh
+    g = gen(C_ * dh)
+    qkv = torch.randn(B * C_ * N, 3 * E, device=DEV, generator=g).bfloat16()
+    bias = torch.randn(1023, H, device=DEV, generator=g) if rel else None
+    out = torch.empty(B * C_ * N, E, device=DEV, dtype=torch.bfloat16)
+    ops.temporal_attention(qkv, out, B=B, C_=C_, N=N, H=H, dh=dh, scale=1 / math.sqrt(dh), rel_bias=bias)
+    t = qkv.float().view(B, C_, N, 3, H, dh)
+    q, k, v = (t[:, :, :, i].permute(0, 2, 3, 1, 4) for i in range(3))  # [B, N, H, C, dh]
+    sc = q @ k.transpose(-1, -2) / math.sqrt(dh)
+    if rel:
+        pos = torch.arange(C_, device=DEV)
+        sc = sc + bias[pos[None, :] - pos[:, None] + 511].permute(2, 0, 1)[None, None]
+    ref = (torch.softmax(sc, -1) @ v).permute(0, 3, 1, 2, 4).reshape(B * C_ * N, E)
+    close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("dh", [32, 64, 128])
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_rope_and_cache(dh, qk_norm):
+    from u2tokenizer_b200 import ops
+    B, S, Hq, Hkv, Tmax, pos0 = 2, 9, 4, 2, 32, 5
+    g = gen(dh)
+    ld = (Hq + 2 * Hkv) * dh
+    x = torch.randn(B * S, ld, device=DEV, generator=g).bfloat16()
+    x0 = x.clone()
+    inv = 1.0 / (10000 ** (torch.arange(0, dh, 2, device=DEV).float() / dh))
+    qw = 1 + 0.1 * torch.randn(dh, device=DEV, generator=g) if qk_norm else None
+    kw = 1 + 0.1 * torch.randn(dh, device=DEV, generator=g) if qk_norm else None
+    kc = torch.zeros(B, Hkv, Tmax, dh, device=DEV, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    ops.rope(x, rows=B * S, ld=ld, dh=dh, n_q=Hq, n_k=Hkv, n_v=Hkv, inv_freq=inv, q_norm_w=qw, k_norm_w=kw, eps=1e-6,
+             pos0=pos0, pos_div=1, pos_mod=S, k_cache=kc, v_cache=vc, Tmax=Tmax, rows_per_batch=S)
+    t = x0.float().view(B, S, Hq + 2 * Hkv, dh)
+    q, k, v = t[:, :, :Hq], t[:, :, Hq:Hq + Hkv], t[:, :, Hq + Hkv:]
+    if qk_norm:
+        q = qw * q * torch.rsqrt(q.pow(2).mean(-1, keepdim=True) + 1e-6)
+        k = kw * k * torch.rsqrt(k.pow(2).mean(-1, keepdim=True) + 1e-6)
+    pos = torch.arange(pos0, pos0 + S, device=DEV).float()
+    fr = torch.outer(pos, inv)
+    emb = torch.cat((fr, fr), -1)
+    cos, sin = emb.cos()[None, :, None], emb.sin()[None, :, None]
+    rot = lambda u: torch.cat((-u[..., dh // 2:], u[..., :dh // 2]), -1)
+    qr, kr = q * cos + rot(q) * sin, k * cos + rot(k) * sin
+    got = x.float().view(B, S, Hq + 2 * Hkv, dh)
+    close(got[:, :, :Hq], qr, 1e-2)
+    close(got[:, :, Hq:Hq + Hkv], kr, 1e-2)
+    assert torch.equal(got[:, :, Hq + Hkv:], v)
+    close(kc[:, :, pos0:pos0 + S].permute(0, 2, 1, 3), kr, 1e-2)
+    assert torch.equal(vc[:, :, pos0:pos0 + S].permute(0, 2, 1, 3).float(), v)
+    assert kc[:, :, :pos0].abs().max().item() == 0 and kc[:, :, pos0 + S:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dh,T", [(128, 545), (64, 17), (32, 3), (128, 1)])
+def test_decode_attention(dh, T):
+    from u2tokenizer_b200 import ops
+    B, Hq, Hkv, Tmax = 3, 8, 2, 600
+    g = gen(T)
+    q = torch.randn(B, Hq * dh, device=DEV, generator=g).bfloat16()
+    kc = torch.randn(B, Hkv, Tmax, dh, device=DEV, generator=g).bfloat16()
+    vc = torch.randn(B, Hkv, Tmax, dh, device=DEV, generator=g).bfloat16()
+    out = torch.empty(B, Hq * dh, device=DEV, dtype=torch.bfloat16)
+    Td = torch.tensor([T], device=DEV, dtype=torch.int32)
+    for kw in (dict(T=T), dict(T_dev=Td)):
+        out.zero_()
+        ops.decode_attention(q, kc, vc, out, B=B, Hq=Hq, Hkv=Hkv, dh=dh, Tmax=Tmax, ldq=Hq * dh, ldo=Hq * dh,
+                             scale=1 / math.sqrt(dh), **kw)
+        qq = q.float().view(B, Hq, 1, dh)
+        kk = kc[:, :, :T].float().repeat_interleave(Hq // Hkv, 1)
+        vv = vc[:, :, :T].float().repeat_interleave(Hq // Hkv, 1)
+        ref = (torch.softmax(qq @ kk.transpose(-1, -2) / math.sqrt(dh), -1) @ vv).reshape(B, Hq * dh)
+        close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("B", [1, 4, 8])
+@pytest.mark.parametrize("N,K", [(4096, 2048), (1000, 328), (24576, 4096), (151936, 1024)])
+def test_gemv(B, N, K):
+    from u2tokenizer_b200 import ops
+    g = gen(B * N + K)
+    x = torch.randn(B, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * K ** -0.5).bfloat16()
+    res = torch.randn(B, N, device=DEV, generator=g).bfloat16()
+    out = torch.empty(B, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemv(x, w, out, residual=res)
+    close(out, x.float() @ w.float().t() + res.float())
+    outf = torch.empty(B, N, device=DEV, dtype=torch.float32)
+    gamma = 1 + 0.1 * torch.randn(K, device=DEV, generator=g)
+    ops.gemv(x, w, outf, norm_gamma=gamma, norm_eps=1e-6)
+    xn = (gamma * x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6))
+    close(outf, xn @ w.float().t(), 1e-2)
+    if N % 2 == 0:
+        o2 = torch.empty(B, N // 2, device=DEV, dtype=torch.bfloat16)
+        ops.gemv(x, w, o2, silu_pair=True)
+        y = x.float() @ w.float().t()
+        close(o2, F.silu(y[:, :N // 2]) * y[:, N // 2:], 2e-2)
+
+
+def test_argmax():
+    from u2tokenizer_b200 import ops
+    lg = torch.randn(4, 151936, device=DEV, generator=gen(9))
+    lg[1, 77] = 100.0
+    lg[1, 5000] = 100.0  # tie -> first index
+    assert torch.equal(ops.argmax(lg), lg.argmax(-1))
+    assert ops.argmax(lg)[1].item() == 77

@@ -31,6 +31,48 @@ class GemmDesc(C.Structure):
     ]
 
 
+class SoftmaxDesc(C.Structure):
+    """Mirror of ``u2_softmax_desc``."""
+    _fields_ = [
+        ("in_s0", C.c_int64), ("in_s1", C.c_int64), ("in_s2", C.c_int64),
+        ("out_s0", C.c_int64), ("out_s1", C.c_int64), ("out_s2", C.c_int64),
+        ("n0", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("n", C.c_int32),
+        ("scale", C.c_float),
+        ("rel_bias", C.c_void_p),
+        ("rel_max", C.c_int32),
+        ("causal", C.c_int32), ("causal_off", C.c_int32),
+        ("zero_pad_to", C.c_int32),
+    ]
+
+
+class RopeDesc(C.Structure):
+    """Mirror of ``u2_rope_desc``."""
+    _fields_ = [
+        ("rows", C.c_int64), ("ld", C.c_int64),
+        ("dh", C.c_int32), ("n_q_heads", C.c_int32), ("n_k_heads", C.c_int32), ("n_v_heads", C.c_int32),
+        ("q_norm_w", C.c_void_p), ("k_norm_w", C.c_void_p),
+        ("eps", C.c_float),
+        ("inv_freq", C.c_void_p),
+        ("pos0", C.c_int32), ("pos_div", C.c_int32), ("pos_mod", C.c_int32),
+        ("pos0_dev", C.c_void_p),
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("Tmax", C.c_int32), ("rows_per_batch", C.c_int32),
+    ]
+
+
+class GemvDesc(C.Structure):
+    """Mirror of ``u2_gemv_desc``."""
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldy", C.c_int64), ("ldr", C.c_int64),
+        ("y_dtype", C.c_int32),
+        ("residual", C.c_void_p),
+        ("norm_gamma", C.c_void_p),
+        ("norm_eps", C.c_float),
+        ("silu_pair", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -39,6 +81,21 @@ SIGNATURES = {
     "u2_last_error": (C.c_char_p, []),
     "u2_device_sm_count": (C.c_int, []),
     "u2_gemm_bf16": (C.c_int, [_P, _P, _P, C.POINTER(GemmDesc), _P]),
+    "u2_layernorm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _F, _P]),
+    "u2_rmsnorm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _F, _P]),
+    "u2_softmax_f32_bf16": (C.c_int, [_P, _P, C.POINTER(SoftmaxDesc), _P]),
+    "u2_silu_mul_bf16": (C.c_int, [_P, _P, _L, _I, _L, _L, _P]),
+    "u2_patchify_f32_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "u2_set_rows_bf16": (C.c_int, [_P, _P, _L, _L, _L, _I, _P]),
+    "u2_transpose_heads_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
+    "u2_spp_pool_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _L, _L, _L, _I, _P]),
+    "u2_multiscale_pool_bf16": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _I, _I, _P]),
+    "u2_embed_splice_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _L, _P]),
+    "u2_temporal_attention_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _L, _L, _F, _P, _I, _P]),
+    "u2_rope_bf16": (C.c_int, [_P, C.POINTER(RopeDesc), _P]),
+    "u2_decode_attention_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _F, _P]),
+    "u2_gemv_bf16": (C.c_int, [_P, _P, _P, C.POINTER(GemvDesc), _P]),
+    "u2_argmax_f32": (C.c_int, [_P, _P, _I, _I, _L, _P]),
 }
 
 

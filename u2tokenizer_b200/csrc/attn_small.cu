@@ -1,0 +1,315 @@
+// Small-sequence attention pieces that do not belong on the tensor cores:
+//   temporal_attention  RMA / RoPE attention across the <= 32 frames of one spatial token
+//                       (reference svr.py:33-36 + rma.py:60-73); one CTA per (batch, token, head)
+//   rope / qk_norm_rope rotate-half RoPE (optionally per-head RMSNorm first: Qwen3) applied in place
+//                       on a fused QKV buffer, and the KV-cache append of the decoder
+//   decode_attention    one query token against the KV cache (HBM-bound, GQA)
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "host_util.h"
+#include "u2b200.h"
+
+namespace u2 {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// temporal attention. qkv rows are (b, c, n) -> row = (b*C + c)*N + n, columns [q | k | v] each E wide.
+// out[(b*C + c)*N + n][h*dh + d] = sum_c' softmax_c'(q_c . k_c' * scale + bias[c'-c+rel_max-1][h]) v_c'[d]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+temporal_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int C, int N,
+                          int H, int dh, long long ld_qkv, long long ld_out, float scale,
+                          const float* __restrict__ rel_bias, int rel_max) {
+  extern __shared__ __nv_bfloat16 sm[];  // K [C][dh] then V [C][dh]
+  __nv_bfloat16* sK = sm;
+  __nv_bfloat16* sV = sm + (size_t)C * dh;
+  const int h = blockIdx.x, n = blockIdx.y, b = blockIdx.z;
+  const int E = H * dh;
+  const int nvec = dh >> 3;
+  for (int i = threadIdx.x; i < C * nvec; i += blockDim.x) {
+    const int c = i / nvec, v = i - c * nvec;
+    const long long row = ((long long)b * C + c) * N + n;
+    const __nv_bfloat16* base = qkv + row * ld_qkv + h * dh;
+    reinterpret_cast<uint4*>(sK + (size_t)c * dh)[v] = reinterpret_cast<const uint4*>(base + E)[v];
+    reinterpret_cast<uint4*>(sV + (size_t)c * dh)[v] = reinterpret_cast<const uint4*>(base + 2 * E)[v];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += (blockDim.x >> 5)) {
+    const long long row = ((long long)b * C + c) * N + n;
+    const __nv_bfloat16* q = qkv + row * ld_qkv + h * dh;
+    // scores: lane j keeps the score of key frame j
+    float my = -INFINITY;
+    for (int j = 0; j < C; ++j) {
+      float d = 0.f;
+      for (int e = lane * 2; e < dh; e += 64) {
+        const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + e));
+        const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * dh + e));
+        d += qq.x * kk.x + qq.y * kk.y;
+      }
+      d = wsum(d) * scale;
+      if (rel_bias) d += __ldg(rel_bias + (long long)(j - c + rel_max - 1) * H + h);
+      if (lane == j) my = d;
+    }
+    const float m = wmax(my);
+    const float e = (lane < C) ? __expf(my - m) : 0.f;
+    const float s = wsum(e);
+    const float p = e / s;
+    __nv_bfloat16* o = out + row * ld_out + h * dh;
+    for (int e0 = lane * 2; e0 < dh; e0 += 64) {
+      float ax = 0.f, ay = 0.f;
+      for (int j = 0; j < C; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j);
+        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)j * dh + e0));
+        ax += pj * vv.x;
+        ay += pj * vv.y;
+      }
+      *reinterpret_cast<__nv_bfloat162*>(o + e0) = __floats2bfloat162_rn(ax, ay);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (optional per-head RMSNorm) + rotate-half RoPE, in place on `n_rot_heads` heads of every row of a
+// fused buffer; optional KV-cache append. One warp per (row, head).
+//   position(row) = pos0 + (row / pos_div) % pos_mod
+// ------------------------------------------------------------------------------------------------
+struct RopeArgs {
+  __nv_bfloat16* x;          // [rows, ld]
+  long long rows, ld;
+  int dh;
+  int n_q_heads;             // heads [0, n_q_heads) use q_norm_w
+  int n_k_heads;             // heads [n_q_heads, n_q_heads + n_k_heads) use k_norm_w
+  int n_v_heads;             // heads after that are V (no rope): only copied to the cache
+  const float* q_norm_w;     // [dh] or null
+  const float* k_norm_w;     // [dh] or null
+  float eps;
+  const float* inv_freq;     // [dh/2]
+  int pos0, pos_div, pos_mod;
+  const int* pos0_dev;       // when set, pos0 is read from the device (CUDA-graph friendly decode)
+  __nv_bfloat16* k_cache;    // [B, n_k_heads, Tmax, dh] or null
+  __nv_bfloat16* v_cache;
+  int Tmax, rows_per_batch;  // batch index = row / rows_per_batch, cache position = position(row)
+};
+
+__global__ void __launch_bounds__(256)
+rope_kernel(const RopeArgs a) {
+  const int heads = a.n_q_heads + a.n_k_heads + a.n_v_heads;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= a.rows * heads) return;
+  const int lane = threadIdx.x & 31;
+  const long long row = item / heads;
+  const int head = (int)(item - row * heads);
+  __nv_bfloat16* p = a.x + row * a.ld + (long long)head * a.dh;
+  const int pos = (a.pos0_dev ? *a.pos0_dev : a.pos0) + (int)((row / a.pos_div) % a.pos_mod);
+  const int half = a.dh >> 1;
+  const bool is_q = head < a.n_q_heads;
+  const bool is_k = !is_q && head < a.n_q_heads + a.n_k_heads;
+  const int b = (int)(row / a.rows_per_batch);
+  if (!is_q && !is_k) {
+    if (a.v_cache) {
+      const int hv = head - a.n_q_heads - a.n_k_heads;
+      __nv_bfloat16* dst = a.v_cache + (((long long)b * a.n_v_heads + hv) * a.Tmax + pos) * a.dh;
+      for (int e = lane * 2; e < a.dh; e += 64)
+        *reinterpret_cast<uint32_t*>(dst + e) = *reinterpret_cast<const uint32_t*>(p + e);
+    }
+    return;
+  }
+  const float* nw = is_q ? a.q_norm_w : a.k_norm_w;
+  float rstd = 1.f;
+  if (nw) {
+    float ss = 0.f;
+    for (int e = lane; e < a.dh; e += 32) {
+      const float v = __bfloat162float(p[e]);
+      ss += v * v;
+    }
+    ss = wsum(ss);
+    rstd = rsqrtf(ss / a.dh + a.eps);
+  }
+  __nv_bfloat16* kdst = nullptr;
+  if (is_k && a.k_cache)
+    kdst = a.k_cache + (((long long)b * a.n_k_heads + (head - a.n_q_heads)) * a.Tmax + pos) * a.dh;
+  for (int i = lane; i < half; i += 32) {
+    float x1 = __bfloat162float(p[i]), x2 = __bfloat162float(p[i + half]);
+    if (nw) {
+      x1 = x1 * rstd * nw[i];
+      x2 = x2 * rstd * nw[i + half];
+    }
+    float sn, cs;
+    sincosf((float)pos * a.inv_freq[i], &sn, &cs);
+    const __nv_bfloat16 o1 = __float2bfloat16(x1 * cs - x2 * sn);
+    const __nv_bfloat16 o2 = __float2bfloat16(x2 * cs + x1 * sn);
+    p[i] = o1;
+    p[i + half] = o2;
+    if (kdst) {
+      kdst[i] = o1;
+      kdst[i + half] = o2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention: one query token per sequence against the KV cache.
+//   q   [B, Hq, dh] (row stride ldq), caches [B, Hkv, Tmax, dh], T valid keys, out [B, Hq*dh]
+// grid (Hq, B), 8 warps split the keys; online softmax per warp, merged through smem.
+// ------------------------------------------------------------------------------------------------
+template <int kEpl>
+__device__ __forceinline__ void load_epl(const __nv_bfloat16* p, float (&f)[kEpl]) {
+  if constexpr (kEpl == 1) {
+    f[0] = __bfloat162float(p[0]);
+  } else if constexpr (kEpl == 2) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    f[0] = t.x; f[1] = t.y;
+  } else {
+    static_assert(kEpl == 4, "kEpl in {1,2,4}");
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+}
+
+template <int kEpl>  // dh = kEpl * 32: lane owns elements [lane*kEpl, lane*kEpl + kEpl)
+__global__ void __launch_bounds__(256)
+decode_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                        const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int Hq, int Hkv,
+                        int Tmax, int T_host, const int* __restrict__ T_dev, long long ldq, long long ldo,
+                        float scale) {
+  constexpr int dh = kEpl * 32;
+  const int T = T_dev ? min(*T_dev, Tmax) : T_host;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int hk = h / (Hq / Hkv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* qp = q + (long long)b * ldq + (long long)h * dh + lane * kEpl;
+  const __nv_bfloat16* kp = kc + ((long long)b * Hkv + hk) * Tmax * dh + lane * kEpl;
+  const __nv_bfloat16* vp = vc + ((long long)b * Hkv + hk) * Tmax * dh + lane * kEpl;
+  float qv[kEpl];
+  load_epl<kEpl>(qp, qv);
+#pragma unroll
+  for (int i = 0; i < kEpl; ++i) qv[i] *= scale;
+  float m = -INFINITY, l = 0.f;
+  float acc[kEpl];
+#pragma unroll
+  for (int i = 0; i < kEpl; ++i) acc[i] = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    float kk[kEpl], vv[kEpl];
+    load_epl<kEpl>(kp + (long long)t * dh, kk);
+    load_epl<kEpl>(vp + (long long)t * dh, vv);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) d += qv[i] * kk[i];
+    d = wsum(d);
+    const float mn = fmaxf(m, d);
+    const float corr = __expf(m - mn);
+    const float pe = __expf(d - mn);
+    l = l * corr + pe;
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) acc[i] = acc[i] * corr + pe * vv[i];
+    m = mn;
+  }
+  __shared__ float s_m[8], s_l[8];
+  __shared__ float s_acc[8][dh];
+  if (lane == 0) {
+    s_m[warp] = m;
+    s_l[warp] = l;
+  }
+#pragma unroll
+  for (int i = 0; i < kEpl; ++i) s_acc[warp][lane * kEpl + i] = acc[i];
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) gm = fmaxf(gm, s_m[w]);
+  float gl = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) gl += (s_m[w] == -INFINITY) ? 0.f : s_l[w] * __expf(s_m[w] - gm);
+  for (int e = threadIdx.x; e < dh; e += blockDim.x) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      if (s_m[w] != -INFINITY) o += s_acc[w][e] * __expf(s_m[w] - gm);
+    out[(long long)b * ldo + (long long)h * dh + e] = __float2bfloat16(o / gl);
+  }
+}
+
+}  // namespace u2
+
+using namespace u2;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" U2_API int u2_temporal_attention_bf16(const void* qkv, void* out, int32_t B, int32_t C, int32_t N,
+                                                 int32_t H, int32_t dh, int64_t ld_qkv, int64_t ld_out,
+                                                 float scale, const float* rel_bias, int32_t rel_max,
+                                                 void* stream) {
+  if (!qkv || !out) return set_error(U2_ERR_ARG, "temporal_attention: null pointer");
+  if (C <= 0 || C > 32) return set_error(U2_ERR_UNSUPPORTED, "temporal_attention: 1 <= frames <= 32 (got %d)", C);
+  if ((dh & 7) || (ld_qkv & 7) || (ld_out & 1)) return set_error(U2_ERR_ARG, "temporal_attention: dh/ld alignment");
+  if (rel_bias && C > rel_max) return set_error(U2_ERR_ARG, "temporal_attention: frames exceed relative-bias table");
+  if (B <= 0 || N <= 0) return U2_OK;
+  if (N > 65535 || B > 65535) return set_error(U2_ERR_ARG, "temporal_attention: N,B must be <= 65535");
+  const size_t smem = (size_t)2 * C * dh * sizeof(__nv_bfloat16);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "temporal_attention smem: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((unsigned)H, (unsigned)N, (unsigned)B);
+  temporal_attention_kernel<<<grid, 128, smem, ST(stream)>>>(CBF(qkv), BF(out), C, N, H, dh, ld_qkv, ld_out, scale, rel_bias, rel_max);
+  U2_CHECK_LAUNCH("temporal_attention");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_rope_bf16(void* x, const u2_rope_desc* d, void* stream) {
+  if (!x || !d || !d->inv_freq) return set_error(U2_ERR_ARG, "rope: null pointer");
+  if (d->dh <= 0 || (d->dh & 1) || (d->ld & 1)) return set_error(U2_ERR_ARG, "rope: head_dim and ld must be even");
+  if (d->rows <= 0) return U2_OK;
+  if ((d->k_cache || d->v_cache) && (d->Tmax <= 0 || d->rows_per_batch <= 0))
+    return set_error(U2_ERR_ARG, "rope: cache append needs Tmax and rows_per_batch");
+  if (d->k_cache && !d->pos0_dev && d->pos0 + d->pos_mod > d->Tmax)
+    return set_error(U2_ERR_ARG, "rope: cache overflow (pos0 %d + %d > Tmax %d)", d->pos0, d->pos_mod, d->Tmax);
+  RopeArgs a;
+  a.x = BF(x);
+  a.rows = d->rows; a.ld = d->ld; a.dh = d->dh;
+  a.n_q_heads = d->n_q_heads; a.n_k_heads = d->n_k_heads; a.n_v_heads = d->n_v_heads;
+  a.q_norm_w = d->q_norm_w; a.k_norm_w = d->k_norm_w; a.eps = d->eps;
+  a.inv_freq = d->inv_freq;
+  a.pos0_dev = d->pos0_dev;
+  a.pos0 = d->pos0; a.pos_div = d->pos_div > 0 ? d->pos_div : 1; a.pos_mod = d->pos_mod > 0 ? d->pos_mod : 1;
+  a.k_cache = BF(d->k_cache); a.v_cache = BF(d->v_cache);
+  a.Tmax = d->Tmax; a.rows_per_batch = d->rows_per_batch > 0 ? d->rows_per_batch : 1;
+  const long long items = d->rows * (long long)(a.n_q_heads + a.n_k_heads + a.n_v_heads);
+  rope_kernel<<<(unsigned)((items + 7) / 8), 256, 0, ST(stream)>>>(a);
+  U2_CHECK_LAUNCH("rope");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_decode_attention_bf16(const void* q, const void* k_cache, const void* v_cache, void* out,
+                                               int32_t B, int32_t Hq, int32_t Hkv, int32_t dh, int32_t Tmax,
+                                               int32_t T, const int32_t* T_dev, int64_t ldq, int64_t ldo,
+                                               float scale, void* stream) {
+  if (!q || !k_cache || !v_cache || !out) return set_error(U2_ERR_ARG, "decode_attention: null pointer");
+  if (Hkv <= 0 || Hq % Hkv) return set_error(U2_ERR_ARG, "decode_attention: Hq must be a multiple of Hkv");
+  if (!T_dev && (T <= 0 || T > Tmax)) return set_error(U2_ERR_ARG, "decode_attention: need 0 < T <= Tmax");
+  dim3 grid((unsigned)Hq, (unsigned)B);
+#define U2_DA(EPL) decode_attention_kernel<EPL><<<grid, 256, 0, ST(stream)>>>(CBF(q), CBF(k_cache), CBF(v_cache), BF(out), Hq, Hkv, Tmax, T, T_dev, ldq, ldo, scale)
+  switch (dh) {
+    case 32: U2_DA(1); break;
+    case 64: U2_DA(2); break;
+    case 128: U2_DA(4); break;
+    default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention: head_dim %d (supported: 32, 64, 128)", dh);
+  }
+#undef U2_DA
+  U2_CHECK_LAUNCH("decode_attention");
+  return U2_OK;
+}

@@ -100,3 +100,220 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     gemm(x2, w, o2, M=M, N=N, K=K, lda=x2.stride(0), ldb=w.stride(0), ldc=o2.stride(0),
          alpha=alpha, bias=bias, act=act, residual=r2, ldr=ldr, block_n=block_n)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# row-wise ops
+# ------------------------------------------------------------------------------------------------
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    t2 = t.reshape(-1, t.shape[-1]) if t.dim() != 2 else t
+    if t2.stride(1) != 1:
+        raise ValueError("last dim must be contiguous")
+    return t2
+
+
+def layernorm(x, gamma, beta, eps=1e-5, residual=None, out=None, sum_out=None):
+    _need_cuda(x, gamma, beta, residual)
+    x2 = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x2)
+    o2 = _rows2d(out)
+    r2 = _rows2d(residual) if residual is not None else None
+    s2 = _rows2d(sum_out) if sum_out is not None else None
+    if s2 is not None and s2.stride(0) != o2.stride(0):
+        raise ValueError("sum_out must share out's row stride")
+    _lib.check(_lib.load().u2_layernorm_bf16(x2.data_ptr(), _ptr(r2), gamma.data_ptr(), _ptr(beta), o2.data_ptr(),
+                                             _ptr(s2), x2.shape[0], x2.shape[1], x2.stride(0),
+                                             r2.stride(0) if r2 is not None else 0, o2.stride(0), eps, _stream()),
+               "u2_layernorm_bf16")
+    return out.view(x.shape) if out.numel() == x.numel() and out.is_contiguous() else out
+
+
+def rmsnorm(x, gamma, eps=1e-6, residual=None, out=None, sum_out=None):
+    _need_cuda(x, gamma, residual)
+    x2 = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x2)
+    o2 = _rows2d(out)
+    r2 = _rows2d(residual) if residual is not None else None
+    s2 = _rows2d(sum_out) if sum_out is not None else None
+    if s2 is not None and s2.stride(0) != o2.stride(0):
+        raise ValueError("sum_out must share out's row stride")
+    _lib.check(_lib.load().u2_rmsnorm_bf16(x2.data_ptr(), _ptr(r2), gamma.data_ptr(), o2.data_ptr(), _ptr(s2),
+                                           x2.shape[0], x2.shape[1], x2.stride(0),
+                                           r2.stride(0) if r2 is not None else 0, o2.stride(0), eps, _stream()),
+               "u2_rmsnorm_bf16")
+    return out.view(x.shape) if out.numel() == x.numel() and out.is_contiguous() else out
+
+
+def softmax(scores: torch.Tensor, out: torch.Tensor, *, n0: int, H: int, S: int, n: int,
+            in_strides, out_strides, scale: float = 1.0, rel_bias: Optional[torch.Tensor] = None,
+            rel_max: int = 0, causal: bool = False, causal_off: int = 0, zero_pad_to: int = 0):
+    """fp32 score rows -> bf16 probabilities (see u2_softmax_desc)."""
+    _need_cuda(scores, out, rel_bias)
+    d = _lib.SoftmaxDesc()
+    d.in_s0, d.in_s1, d.in_s2 = in_strides
+    d.out_s0, d.out_s1, d.out_s2 = out_strides
+    d.n0, d.H, d.S, d.n = n0, H, S, n
+    d.scale = scale
+    d.rel_bias = _ptr(rel_bias)
+    d.rel_max = rel_max
+    d.causal, d.causal_off = int(causal), causal_off
+    d.zero_pad_to = zero_pad_to
+    _lib.check(_lib.load().u2_softmax_f32_bf16(scores.data_ptr(), out.data_ptr(), C.byref(d), _stream()),
+               "u2_softmax_f32_bf16")
+    return out
+
+
+def silu_mul(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(gate_up)
+    g2 = _rows2d(gate_up)
+    I = g2.shape[1] // 2
+    if out is None:
+        out = torch.empty(g2.shape[0], I, device=g2.device, dtype=BF16)
+    _lib.check(_lib.load().u2_silu_mul_bf16(g2.data_ptr(), out.data_ptr(), g2.shape[0], I, g2.stride(0),
+                                            out.stride(0), _stream()), "u2_silu_mul_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# layout ops
+# ------------------------------------------------------------------------------------------------
+def patchify(vol: torch.Tensor, patch_size, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vol fp32 [F, D0, D1, D2] (single channel, contiguous) -> bf16 [F * n_patches, p0*p1*p2]."""
+    _need_cuda(vol)
+    if vol.dtype != F32 or not vol.is_contiguous():
+        raise TypeError("patchify expects a contiguous fp32 volume")
+    F_, d0, d1, d2 = vol.shape
+    p0, p1, p2 = patch_size
+    npatch = (d0 // p0) * (d1 // p1) * (d2 // p2)
+    if out is None:
+        out = torch.empty(F_ * npatch, p0 * p1 * p2, device=vol.device, dtype=BF16)
+    _lib.check(_lib.load().u2_patchify_f32_bf16(vol.data_ptr(), out.data_ptr(), F_, d0, d1, d2, p0, p1, p2,
+                                                _stream()), "u2_patchify_f32_bf16")
+    return out
+
+
+def set_rows(dst: torch.Tensor, vec: torch.Tensor, n_rows: int, row_stride: int, row_off: int):
+    _need_cuda(dst, vec)
+    E = vec.numel()
+    _lib.check(_lib.load().u2_set_rows_bf16(dst.data_ptr(), vec.data_ptr(), n_rows, row_stride, row_off, E,
+                                            _stream()), "u2_set_rows_bf16")
+    return dst
+
+
+def transpose_heads(x: torch.Tensor, out: torch.Tensor, *, B: int, S: int, H: int, Dh: int,
+                    in_strides, out_strides, ld_out: int):
+    """in[b][s][h][d] -> out[b][h][d][s(pad ld_out)]; strides in elements: in (sb, ss, sh), out (sb, sh)."""
+    _need_cuda(x, out)
+    _lib.check(_lib.load().u2_transpose_heads_bf16(x.data_ptr(), out.data_ptr(), B, S, H, Dh, in_strides[0],
+                                                   in_strides[1], in_strides[2], out_strides[0], out_strides[1],
+                                                   ld_out, _stream()), "u2_transpose_heads_bf16")
+    return out
+
+
+def spp_pool(x: torch.Tensor, out: torch.Tensor, *, frames: int, grid, ps: int, E: int,
+             in_frame_stride: int, in_off: int, ldx: int, sequence: bool = False):
+    _need_cuda(x, out)
+    _lib.check(_lib.load().u2_spp_pool_bf16(x.data_ptr(), out.data_ptr(), frames, grid[0], grid[1], grid[2], ps, E,
+                                            in_frame_stride, in_off, ldx, int(sequence), _stream()),
+               "u2_spp_pool_bf16")
+    return out
+
+
+def multiscale_pool(x: torch.Tensor, gate_w: Optional[torch.Tensor], gate_bias: float, dynamic: bool) -> torch.Tensor:
+    """x bf16 [B, K, E] -> [B, K + K//2 + K//4, E] (scales that do not fit are skipped)."""
+    _need_cuda(x, gate_w)
+    B, K, E = x.shape
+    x = x.contiguous()
+    n_out = K + (K // 2 if K >= 2 else 0) + (K // 4 if K >= 4 else 0)
+    out = torch.empty(B, n_out, E, device=x.device, dtype=BF16)
+    ws = torch.empty(B, 3, device=x.device, dtype=F32)
+    _lib.check(_lib.load().u2_multiscale_pool_bf16(x.data_ptr(), out.data_ptr(), _ptr(gate_w), gate_bias,
+                                                   ws.data_ptr(), B, K, E, int(dynamic), _stream()),
+               "u2_multiscale_pool_bf16")
+    return out
+
+
+def embed_splice(ids: torch.Tensor, table: torch.Tensor, vis: Optional[torch.Tensor]) -> torch.Tensor:
+    _need_cuda(ids, table, vis)
+    if ids.dtype != torch.int64:
+        ids = ids.long()
+    ids = ids.contiguous()
+    B, L = ids.shape
+    E = table.shape[1]
+    n_vis = 0 if vis is None else vis.shape[1]
+    if vis is not None:
+        vis = vis.contiguous()
+    out = torch.empty(B, L, E, device=table.device, dtype=BF16)
+    _lib.check(_lib.load().u2_embed_splice_bf16(ids.data_ptr(), table.data_ptr(), _ptr(vis), out.data_ptr(), B, L, E,
+                                                n_vis, table.shape[0], _stream()), "u2_embed_splice_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# small attention pieces
+# ------------------------------------------------------------------------------------------------
+def temporal_attention(qkv: torch.Tensor, out: torch.Tensor, *, B: int, C_: int, N: int, H: int, dh: int,
+                       scale: float, rel_bias: Optional[torch.Tensor], rel_max: int = 512):
+    _need_cuda(qkv, out, rel_bias)
+    _lib.check(_lib.load().u2_temporal_attention_bf16(qkv.data_ptr(), out.data_ptr(), B, C_, N, H, dh,
+                                                      qkv.stride(-2), out.stride(-2), scale, _ptr(rel_bias),
+                                                      rel_max, _stream()), "u2_temporal_attention_bf16")
+    return out
+
+
+def rope(x: torch.Tensor, *, rows: int, ld: int, dh: int, n_q: int, n_k: int, n_v: int = 0,
+         inv_freq: torch.Tensor, q_norm_w=None, k_norm_w=None, eps: float = 1e-6,
+         pos0: int = 0, pos_div: int = 1, pos_mod: int = 1, pos0_dev=None,
+         k_cache=None, v_cache=None, Tmax: int = 0, rows_per_batch: int = 1):
+    _need_cuda(x, inv_freq, q_norm_w, k_norm_w, k_cache, v_cache, pos0_dev)
+    d = _lib.RopeDesc()
+    d.rows, d.ld, d.dh = rows, ld, dh
+    d.n_q_heads, d.n_k_heads, d.n_v_heads = n_q, n_k, n_v
+    d.q_norm_w, d.k_norm_w, d.eps = _ptr(q_norm_w), _ptr(k_norm_w), eps
+    d.inv_freq = inv_freq.data_ptr()
+    d.pos0, d.pos_div, d.pos_mod = pos0, pos_div, pos_mod
+    d.pos0_dev = _ptr(pos0_dev)
+    d.k_cache, d.v_cache = _ptr(k_cache), _ptr(v_cache)
+    d.Tmax, d.rows_per_batch = Tmax, rows_per_batch
+    _lib.check(_lib.load().u2_rope_bf16(x.data_ptr(), C.byref(d), _stream()), "u2_rope_bf16")
+    return x
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, *,
+                     B: int, Hq: int, Hkv: int, dh: int, Tmax: int, T: int = 0, T_dev=None, ldq: int, ldo: int,
+                     scale: float):
+    _need_cuda(q, k_cache, v_cache, out, T_dev)
+    _lib.check(_lib.load().u2_decode_attention_bf16(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                                                    out.data_ptr(), B, Hq, Hkv, dh, Tmax, T, _ptr(T_dev), ldq, ldo,
+                                                    scale, _stream()), "u2_decode_attention_bf16")
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, residual=None, norm_gamma=None,
+         norm_eps: float = 1e-6, silu_pair: bool = False):
+    """Decode-step linear: x [B<=8, K] bf16, w [N, K] bf16 -> out [B, N or N/2] (bf16 or fp32)."""
+    _need_cuda(x, w, out, residual, norm_gamma)
+    d = _lib.GemvDesc()
+    d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
+    d.ldx, d.ldw, d.ldy = x.stride(0), w.stride(0), out.stride(0)
+    d.ldr = residual.stride(0) if residual is not None else 0
+    d.y_dtype = DT_BF16 if out.dtype == BF16 else DT_F32
+    d.residual = _ptr(residual)
+    d.norm_gamma = _ptr(norm_gamma)
+    d.norm_eps = norm_eps
+    d.silu_pair = int(silu_pair)
+    _lib.check(_lib.load().u2_gemv_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()),
+               "u2_gemv_bf16")
+    return out
+
+
+def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(logits)
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    _lib.check(_lib.load().u2_argmax_f32(logits.data_ptr(), out.data_ptr(), B, V, logits.stride(0), _stream()),
+               "u2_argmax_f32")
+    return out
