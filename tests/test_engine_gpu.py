@@ -1,0 +1,144 @@
+"""End-to-end and per-stage parity of the CUDA path (U2Engine over libu2b200.so) against the fp32
+oracle on identical seeded weights / volumes / prompts.
+
+Tolerance (stated, bf16): per stage  max|out - ref| / max|ref| <= 3e-2 and cosine >= 0.999
+(activations and weights are bf16 on the CUDA side, the oracle computes in fp32 on the same
+bf16-rounded weights). Greedy token ids must be exact wherever the oracle's top-1/top-2 logit
+margin exceeds 2e-2 * max|logit| (margin-aware)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from common import cosine, fp32_sd, rel_err, tiny_geometry
+from oracle import u2_oracle as O
+from u2tokenizer_b200.synthetic import synthetic_inputs, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+TOL, COS = 3e-2, 0.999
+
+
+def build(g, seed):
+    from u2tokenizer_b200.engine import U2Engine
+    sd16 = synthetic_state_dict(g, seed=seed, device="cpu", dtype=torch.bfloat16)
+    eng = U2Engine(g, sd16, device="cuda")
+    return eng, {k: v.float() for k, v in sd16.items()}
+
+
+def check(out, ref, tol=TOL, what=""):
+    out = out.float().cpu()
+    e, c = rel_err(out, ref), cosine(out, ref)
+    assert e < tol and c > COS, f"{what}: rel_err {e:.4g} cosine {c:.6f}"
+
+
+@pytest.mark.parametrize("ptype", ["spatial", "sequence"])
+def test_encode_images(ptype):
+    g = tiny_geometry(proj_pooling_type=ptype)
+    eng, sd = build(g, 1)
+    imgs = torch.rand(3, 1, *g.image_size, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = O.encode_images(sd, imgs, g)
+    check(eng.encode_images(imgs.cuda()), ref, what="encode_images")
+
+
+@pytest.mark.parametrize("attn_type,dmtp,multi", [("rma", True, True), ("rope", True, True), ("rma", False, True),
+                                                   ("rma", False, False)])
+def test_u2tokenizer(attn_type, dmtp, multi):
+    g = tiny_geometry(attn_type=attn_type, enable_dmtp=dmtp, use_multi_scale=multi)
+    eng, sd = build(g, 2)
+    gen = torch.Generator().manual_seed(1)
+    v = torch.randn(2, 3, g.tokens_per_frame, g.hidden_size, generator=gen).bfloat16()
+    t = torch.randn(2, 5, g.hidden_size, generator=gen).bfloat16()
+    with torch.no_grad():
+        ref = O.u2tokenizer(sd, "model.u2tokenizer.", v.float(), t.float(), g)
+    check(eng.u2tokenizer(v.cuda(), t.cuda()), ref, what="u2tokenizer")
+
+
+@pytest.mark.parametrize("attn_type", ["rma", "rope"])
+def test_u2tokenizer_vs_reference_golden(attn_type):
+    """CUDA path against the committed outputs of the REFERENCE u2Tokenizer (tests/golden)."""
+    from make_golden import golden_geometry
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "u2_reference_outputs.pt"))
+    g = golden_geometry()
+    g.attn_type = attn_type
+    eng, sd = build(g, 11)
+    gen = torch.Generator().manual_seed(21)
+    v = torch.randn(2, 3, g.tokens_per_frame, g.hidden_size, generator=gen).bfloat16()
+    t = torch.randn(2, 24, g.hidden_size, generator=gen).bfloat16()
+    check(eng.u2tokenizer(v.cuda(), t.cuda()), gold[f"u2tok_{attn_type}_11"], what="golden u2tokenizer")
+
+
+@pytest.mark.parametrize("family", ["qwen3", "llama"])
+def test_forward_logits_and_generate(family):
+    if family == "qwen3":
+        g = tiny_geometry()
+    else:
+        rs = dict(factor=8.0, high_freq_factor=4.0, low_freq_factor=1.0, original_max_position_embeddings=16,
+                  rope_type="llama3")
+        g = tiny_geometry(qk_norm=False, rope_theta=500000.0, rope_scaling=rs, tie_word_embeddings=True, head_dim=32)
+    eng, sd = build(g, 3)
+    images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12)
+    with torch.no_grad():
+        ref_emb = O.multimodal_embeds(sd, ids, images, qids, g)
+        ref_logits = O.decoder_forward(sd, ref_emb, g)[0]
+        ref_ids, margins = O.greedy_generate(sd, ids, images, qids, g, max_new_tokens=8)
+    emb = eng.multimodal_embeds(ids.cuda(), images.cuda(), qids.cuda())
+    check(emb, ref_emb, what="multimodal_embeds")
+    hidden = eng.prefill(emb)
+    logits = eng.lm_logits(hidden)
+    check(logits, ref_logits, what="prefill logits")
+    for use_graph in (False, True):
+        got = eng.generate_greedy(emb, max_new_tokens=8, use_graph=use_graph).cpu()
+        thr = 2e-2 * ref_logits.abs().max().item()
+        # compare up to (excluding) the first low-margin step of each sequence: after it the oracle's own
+        # choice is not robust to bf16 rounding and the continuations legitimately diverge
+        for b in range(got.shape[0]):
+            low = (margins[b] < thr).nonzero()
+            upto = int(low[0]) if len(low) else got.shape[1]
+            assert torch.equal(got[b, :upto], ref_ids[b, :upto]), (use_graph, b, got[b], ref_ids[b], margins[b])
+        assert got.shape == ref_ids.shape
+
+
+def test_decode_matches_prefill():
+    """KV-cached decode steps reproduce teacher-forced prefill logits (size-independent property)."""
+    g = tiny_geometry()
+    eng, sd = build(g, 4)
+    gen = torch.Generator().manual_seed(5)
+    emb = (torch.randn(2, 20, g.hidden_size, generator=gen) * 0.5).bfloat16().cuda()
+    full = eng.lm_logits(eng.prefill(emb))
+    cache = eng.new_cache(2, 32)
+    h = eng.prefill(emb[:, :12].contiguous(), cache)
+    bufs = eng._decode_buffers(2)
+    # feed the remaining embeddings one at a time through the decode path
+    from u2tokenizer_b200 import ops
+    for t in range(12, 20):
+        # inject the embedding directly: emulate ids -> embed by writing x after the gather
+        saved = eng.embed
+        eng.embed = emb[:, t].contiguous()  # table of 2 rows; ids 0,1 select them
+        bufs["ids"].copy_(torch.arange(2, device="cuda").view(2, 1))
+        lg = eng.decode_step(cache)
+        eng.embed = saved
+        e = rel_err(lg.cpu(), full[:, t].float().cpu())
+        assert e < 3e-2, (t, e)
+
+
+def test_full_size_shapes_one_layer():
+    """Canonical widths (E=2048: head_dim 256 attention, S=2049 ViT sequence, 1024-way DiffTS, 1792-token
+    cross attention) with the depth cut to one layer per stack so the fp32 oracle finishes in seconds."""
+    g = tiny_geometry(image_size=[32, 256, 256], patch_size=[4, 16, 16], vit_hidden=768, vit_mlp=3072, vit_layers=1,
+                      vit_heads=12, u2t_num_layers=1, u2t_top_k=1024, num_3d_query_token=256, hidden_size=2048,
+                      intermediate_size=6144, num_hidden_layers=1, num_attention_heads=16, num_key_value_heads=8,
+                      head_dim=128, vocab_size=4096)
+    eng, sd = build(g, 7)
+    images, ids, qids = synthetic_inputs(g, batch=1, frames=2, n_question=16, lt=64)
+    with torch.no_grad():
+        feats = O.encode_images(sd, images.view(2, 1, *g.image_size), g)
+        ref_vis = O.u2tokenizer(sd, "model.u2tokenizer.", feats.view(1, 2, -1, g.hidden_size),
+                                torch.nn.functional.embedding(qids, sd["model.embed_tokens.weight"]), g)
+    got_feats = eng.encode_images(images.view(2, 1, *g.image_size).cuda())
+    check(got_feats, feats, what="encode_images full width")
+    vis = eng.visual_tokens(images.cuda(), qids.cuda())
+    check(vis, ref_vis, what="visual tokens full width")

@@ -1,0 +1,585 @@
+"""Host-side orchestration of the hot path over the C-ABI kernels (libu2b200.so).
+
+`U2Engine` owns the device copies of the weights in the layouts the kernels want (fused QKV /
+gate-up matrices, fp32 vectors) and sequences the kernel launches for
+
+  * the vision front   : patch embed -> ViT3D -> final LN -> spatial pooling -> projector MLP
+                         (reference src/model/u2_arch.py:96-99, multimodal_encoder/vit.py,
+                          multimodal_projector/spatial_pooling_projector.py)
+  * the mu2-tokenizer  : SVR (spatial + temporal attention, token selection, multi-scale pooling) and
+                         TTA (self / visual-cross / text-cross attention, linear aggregation)
+                         (reference src/model/u2tokenizer/{u2Tokenizer,svr,tta,rma,rope}.py)
+  * the splice         : embed_tokens gather + visual tokens at positions 1..n_vis (u2_arch.py:118-121)
+  * the decoder        : Qwen3 / Llama prefill (tensor-core GEMMs) and KV-cached greedy decode
+                         (weight-streaming GEMVs), i.e. what HF runs under super().forward()/generate()
+
+All arithmetic happens in hand-written CUDA; torch provides memory, streams and CUDA graphs only.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .geometry import Geometry
+
+BF16, F32 = torch.bfloat16, torch.float32
+REL_MAX = 512  # RelativeMultiheadAttention(max_seq_len=512), reference rma.py:6,19
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _Take:
+    """Pops tensors out of the source state dict (so fused copies do not double peak memory)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device):
+        self.sd, self.dev = sd, device
+
+    def has(self, k):
+        return k in self.sd
+
+    def bf(self, k) -> torch.Tensor:
+        return self.sd.pop(k).to(device=self.dev, dtype=BF16).contiguous()
+
+    def f32(self, k) -> torch.Tensor:
+        # parameters are bf16-valued on the reference side at inference; keep those values, fp32 storage
+        return self.sd.pop(k).to(device=self.dev, dtype=BF16).to(F32).contiguous()
+
+    def cat_bf(self, keys) -> torch.Tensor:
+        return torch.cat([self.bf(k) for k in keys], dim=0).contiguous()
+
+    def cat_f32(self, keys) -> torch.Tensor:
+        return torch.cat([self.f32(k) for k in keys], dim=0).contiguous()
+
+
+@dataclass
+class _SelfAttnW:  # RelativeMultiheadAttention / RotaryMultiheadAttention
+    wqkv: torch.Tensor
+    bqkv: torch.Tensor
+    wd: torch.Tensor
+    bd: torch.Tensor
+    rel: Optional[torch.Tensor]
+
+
+@dataclass
+class _CrossAttnW:  # MultiHeadCrossAttention
+    wq: torch.Tensor
+    bq: torch.Tensor
+    wkv: torch.Tensor   # [2E, E] (k then v); linagg: [E, E] (k only)
+    bkv: torch.Tensor
+    wd: Optional[torch.Tensor]
+    bd: Optional[torch.Tensor]
+
+
+class U2Engine:
+    def __init__(self, geom: Geometry, state_dict: Dict[str, torch.Tensor], device="cuda",
+                 attn_workspace_bytes: int = 6 << 30):
+        if not torch.cuda.is_available():
+            raise RuntimeError("U2Engine needs a CUDA device: the hot path has no CPU implementation")
+        from . import _lib
+        _lib.load()  # fail loudly when the extension is missing
+        self.g = geom
+        self.dev = torch.device(device)
+        self.attn_ws = attn_workspace_bytes
+        if geom.vision_select_feature != "patch":
+            raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
+        if geom.attn_type not in ("rma", "rope"):
+            raise NotImplementedError(f"attn_type={geom.attn_type!r}: 'rma' and 'rope' are implemented")
+        t = _Take(dict(state_dict), self.dev)
+        self._prep_vit(t)
+        self._prep_projector(t)
+        if geom.enable_u2tokenizer:
+            self._prep_tokenizer(t)
+        self._prep_decoder(t)
+        self._graph = None
+
+    # =========================================================================================
+    # weight preparation
+    # =========================================================================================
+    def _prep_vit(self, t: _Take):
+        g = self.g
+        v = "model.vision_tower.vision_tower."
+        self.pe_w = t.bf(v + "patch_embedding.patch_embeddings.1.weight")
+        self.pe_b = t.f32(v + "patch_embedding.patch_embeddings.1.bias")
+        self.pos = t.bf(v + "patch_embedding.position_embeddings").view(g.n_patches, g.vit_hidden)
+        self.cls = t.bf(v + "cls_token").view(g.vit_hidden)
+        self.vit = []
+        for i in range(g.vit_layers):
+            b = f"{v}blocks.{i}."
+            self.vit.append(dict(
+                ln1g=t.f32(b + "norm1.weight"), ln1b=t.f32(b + "norm1.bias"),
+                wqkv=t.bf(b + "attn.qkv.weight"),
+                bqkv=t.f32(b + "attn.qkv.bias") if t.has(b + "attn.qkv.bias") else None,
+                wo=t.bf(b + "attn.out_proj.weight"), bo=t.f32(b + "attn.out_proj.bias"),
+                ln2g=t.f32(b + "norm2.weight"), ln2b=t.f32(b + "norm2.bias"),
+                w1=t.bf(b + "mlp.linear1.weight"), b1=t.f32(b + "mlp.linear1.bias"),
+                w2=t.bf(b + "mlp.linear2.weight"), b2=t.f32(b + "mlp.linear2.bias")))
+        self.vit_ng = t.f32(v + "norm.weight")
+        self.vit_nb = t.f32(v + "norm.bias")
+
+    def _prep_projector(self, t: _Take):
+        g = self.g
+        p = "model.mm_projector.projector."
+        self.proj = [(t.bf(p + "0.weight"), t.f32(p + "0.bias"))]
+        for i in range(1, int(g.proj_layer_num)):
+            idx = 2 * i if g.proj_layer_type == "mlp" else i
+            self.proj.append((t.bf(p + f"{idx}.weight"), t.f32(p + f"{idx}.bias")))
+
+    def _self_attn_w(self, t: _Take, pre: str) -> _SelfAttnW:
+        rel = t.f32(pre + "relative_bias") if self.g.attn_type == "rma" else None
+        return _SelfAttnW(
+            wqkv=t.cat_bf([pre + "wq.weight", pre + "wk.weight", pre + "wv.weight"]),
+            bqkv=t.cat_f32([pre + "wq.bias", pre + "wk.bias", pre + "wv.bias"]),
+            wd=t.bf(pre + "dense.weight"), bd=t.f32(pre + "dense.bias"), rel=rel)
+
+    def _cross_attn_w(self, t: _Take, pre: str, compress: bool = False) -> _CrossAttnW:
+        if compress:
+            # LinearAggregation never runs wv / dense (reference tta.py:47-48,62-65): drop them
+            for k in ("wv.weight", "wv.bias", "dense.weight", "dense.bias"):
+                t.sd.pop(pre + k, None)
+            return _CrossAttnW(wq=t.bf(pre + "wq.weight"), bq=t.f32(pre + "wq.bias"),
+                               wkv=t.bf(pre + "wk.weight"), bkv=t.f32(pre + "wk.bias"), wd=None, bd=None)
+        return _CrossAttnW(wq=t.bf(pre + "wq.weight"), bq=t.f32(pre + "wq.bias"),
+                           wkv=t.cat_bf([pre + "wk.weight", pre + "wv.weight"]),
+                           bkv=t.cat_f32([pre + "wk.bias", pre + "wv.bias"]),
+                           wd=t.bf(pre + "dense.weight"), bd=t.f32(pre + "dense.bias"))
+
+    def _prep_tokenizer(self, t: _Take):
+        g = self.g
+        u = "model.u2tokenizer."
+        self.queries = t.bf(u + "query_tokens").view(g.num_3d_query_token, g.hidden_size)
+        self.svr = []
+        for i in range(g.u2t_num_layers):
+            l = f"{u}svt_module.attention_network.layers.{i}."
+            self.svr.append((self._self_attn_w(t, l + "spatial_attention."),
+                             self._self_attn_w(t, l + "temporal_attention.")))
+        self.score_w = t.bf(u + "svt_module.token_selection.score_net.weight")
+        self.score_b = t.f32(u + "svt_module.token_selection.score_net.bias")
+        self.gate_w, self.gate_b = None, 0.0
+        if g.enable_dmtp:
+            self.gate_w = t.f32(u + "svt_module.dynamic_pool.gate_fc.weight").view(-1)
+            self.gate_b = float(t.f32(u + "svt_module.dynamic_pool.gate_fc.bias").item())
+        self.tta = []
+        for i in range(g.u2t_num_layers):
+            l = f"{u}tta_module.layers_vt.{i}."
+            self.tta.append(dict(
+                self_attn=self._self_attn_w(t, l + "self_attention."),
+                vis=self._cross_attn_w(t, l + "visual_cross_attention."),
+                txt=self._cross_attn_w(t, l + "text_cross_attention."),
+                ns=(t.f32(l + "norm_self.weight"), t.f32(l + "norm_self.bias")),
+                nv=(t.f32(l + "norm_cross_v.weight"), t.f32(l + "norm_cross_v.bias")),
+                nt=(t.f32(l + "norm_cross_t.weight"), t.f32(l + "norm_cross_t.bias"))))
+        self.linagg = self._cross_attn_w(t, u + "tta_module.layer_linagg.linear_aggregator.", compress=True)
+        dh = g.hidden_size // g.u2t_num_heads
+        self.u2t_inv_freq = (1.0 / (10000 ** (torch.arange(0, dh, 2, dtype=F32) / dh))).to(self.dev)
+
+    def _prep_decoder(self, t: _Take):
+        g = self.g
+        self.embed = t.bf("model.embed_tokens.weight")
+        self.layers = []
+        for i in range(g.num_hidden_layers):
+            l = f"model.layers.{i}."
+            self.layers.append(dict(
+                ln1=t.f32(l + "input_layernorm.weight"),
+                wqkv=t.cat_bf([l + "self_attn.q_proj.weight", l + "self_attn.k_proj.weight",
+                               l + "self_attn.v_proj.weight"]),
+                qn=t.f32(l + "self_attn.q_norm.weight") if g.qk_norm else None,
+                kn=t.f32(l + "self_attn.k_norm.weight") if g.qk_norm else None,
+                wo=t.bf(l + "self_attn.o_proj.weight"),
+                ln2=t.f32(l + "post_attention_layernorm.weight"),
+                wgu=t.cat_bf([l + "mlp.gate_proj.weight", l + "mlp.up_proj.weight"]),
+                wdown=t.bf(l + "mlp.down_proj.weight")))
+        self.final_norm = t.f32("model.norm.weight")
+        self.lm_head = self.embed if (g.tie_word_embeddings or not t.has("lm_head.weight")) else t.bf("lm_head.weight")
+        self.inv_freq = self._decoder_inv_freq().to(self.dev)
+
+    def _decoder_inv_freq(self) -> torch.Tensor:
+        """Default RoPE or the llama3 rescaling (HF modeling_rope_utils; reference config.json:49-56)."""
+        g = self.g
+        dh = g.head_dim
+        inv = 1.0 / (g.rope_theta ** (torch.arange(0, dh, 2, dtype=F32) / dh))
+        rs = g.rope_scaling
+        if rs and rs.get("rope_type", rs.get("type")) == "llama3":
+            factor, lo, hi = rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
+            old = rs["original_max_position_embeddings"]
+            wavelen = 2 * math.pi / inv
+            inv_l = torch.where(wavelen > old / lo, inv / factor, inv)
+            smooth = (old / wavelen - lo) / (hi - lo)
+            smoothed = (1 - smooth) * inv_l / factor + smooth * inv_l
+            is_med = ~(wavelen < old / hi) & ~(wavelen > old / lo)
+            inv = torch.where(is_med, smoothed, inv_l)
+        elif rs:
+            raise NotImplementedError(f"rope_scaling {rs} not supported")
+        return inv
+
+    # =========================================================================================
+    # attention through the GEMM kernel (scores materialised in fp32, probabilities in bf16)
+    # =========================================================================================
+    def _attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
+                   rel_bias: Optional[torch.Tensor] = None, causal: bool = False):
+        """q [b, Sq, h, dh], k/v [b, Sk, hk, dh] (strided views, dh contiguous), out [b, Sq, h*dh] view.
+        softmax(q k^T * scale (+ rel bias) (+ causal mask)) v, batched over (b, h) on the tensor cores."""
+        b, Sq, h, dh = q.shape
+        Sk, hk = k.shape[1], k.shape[2]
+        Skp = _pad8(Sk)
+        per_b = h * Sq * Skp * 6 + hk * dh * Skp * 2
+        chunk = max(1, min(b, self.attn_ws // max(per_b, 1)))
+        dev = q.device
+        sc = torch.empty(chunk, h, Sq, Skp, device=dev, dtype=F32)
+        pr = torch.empty(chunk, h, Sq, Skp, device=dev, dtype=BF16)
+        vt = torch.empty(chunk, hk, dh, Skp, device=dev, dtype=BF16)
+        for b0 in range(0, b, chunk):
+            nb = min(chunk, b - b0)
+            qq, kk, vv, oo = q[b0:b0 + nb], k[b0:b0 + nb], v[b0:b0 + nb], out[b0:b0 + nb]
+            ops.transpose_heads(vv, vt, B=nb, S=Sk, H=hk, Dh=dh, in_strides=(vv.stride(0), vv.stride(1), vv.stride(2)),
+                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
+            ops.gemm(qq, kk, sc, M=Sq, N=Sk, K=dh, lda=qq.stride(1), ldb=kk.stride(1), ldc=Skp, zi=h, zo=nb,
+                     b_zi_div=h // hk, a_strides=(qq.stride(2), qq.stride(0)), b_strides=(kk.stride(2), kk.stride(0)),
+                     c_strides=(Sq * Skp, h * Sq * Skp), alpha=scale)
+            ops.softmax(sc, pr, n0=nb, H=h, S=Sq, n=Sk, in_strides=(h * Sq * Skp, Sq * Skp, Skp),
+                        out_strides=(h * Sq * Skp, Sq * Skp, Skp), rel_bias=rel_bias, rel_max=REL_MAX, causal=causal,
+                        causal_off=Sk - Sq)
+            ops.gemm(pr, vt, oo, M=Sq, N=dh, K=Sk, lda=Skp, ldb=Skp, ldc=oo.stride(1), zi=h, zo=nb, b_zi_div=h // hk,
+                     a_strides=(Sq * Skp, h * Sq * Skp), b_strides=(dh * Skp, hk * dh * Skp),
+                     c_strides=(dh, oo.stride(0)))
+        return out
+
+    # =========================================================================================
+    # vision front
+    # =========================================================================================
+    def encode_images(self, frames: torch.Tensor) -> torch.Tensor:
+        """frames fp32 [F, 1, D, H, W] -> projected tokens bf16 [F, tokens_per_frame, E]
+        (u2MetaForCausalLM.encode_images, reference u2_arch.py:96-99)."""
+        g = self.g
+        if frames.dim() != 5 or frames.shape[1] != 1 or g.image_channel != 1:
+            raise NotImplementedError("single-channel volumes [F, 1, D, H, W] only")
+        if list(frames.shape[2:]) != list(g.image_size):
+            raise ValueError(f"frame size {list(frames.shape[2:])} != config.image_size {g.image_size}")
+        Fr = frames.shape[0]
+        Hd, P = g.vit_hidden, g.n_patches
+        S = P + 1
+        Sp = _pad8(S)
+        vol = frames.to(device=self.dev, dtype=F32).contiguous().view(Fr, *g.image_size)
+        # --- patch embedding: brick gather -> GEMM (+bias +position table, rows scattered behind the cls row)
+        rows = ops.patchify(vol, g.patch_size)
+        x = torch.zeros(Fr, Sp, Hd, device=self.dev, dtype=BF16)
+        ops.gemm(rows, self.pe_w, x, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd,
+                 bias=self.pe_b, residual=self.pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
+        ops.set_rows(x, self.cls, Fr, Sp, 0)
+        del rows
+        # --- transformer blocks
+        nh = g.vit_heads
+        dh = Hd // nh
+        x2 = x.view(Fr * Sp, Hd)
+        y = torch.empty_like(x2)
+        qkv = torch.empty(Fr * Sp, 3 * Hd, device=self.dev, dtype=BF16)
+        ctx = torch.zeros(Fr, Sp, Hd, device=self.dev, dtype=BF16)
+        hmid = torch.empty(Fr * Sp, g.vit_mlp, device=self.dev, dtype=BF16)
+        qkv5 = qkv.view(Fr, Sp, 3, nh, dh)
+        for w in self.vit:
+            ops.layernorm(x2, w["ln1g"], w["ln1b"], 1e-5, out=y)
+            ops.linear(y, w["wqkv"], w["bqkv"], out=qkv)
+            self._attention(qkv5[:, :S, 0], qkv5[:, :S, 1], qkv5[:, :S, 2], ctx[:, :S], dh ** -0.5)
+            ops.linear(ctx.view(Fr * Sp, Hd), w["wo"], w["bo"], residual=x2, out=x2)
+            ops.layernorm(x2, w["ln2g"], w["ln2b"], 1e-5, out=y)
+            ops.linear(y, w["w1"], w["b1"], act=ops.ACT_GELU, out=hmid)
+            ops.linear(hmid, w["w2"], w["b2"], residual=x2, out=x2)
+        ops.layernorm(x2, self.vit_ng, self.vit_nb, 1e-5, out=y)
+        # --- drop cls + pooling + projector MLP
+        npf = g.tokens_per_frame
+        pooled = torch.empty(Fr, npf, Hd, device=self.dev, dtype=BF16)
+        ops.spp_pool(y, pooled, frames=Fr, grid=g.grid, ps=g.proj_pooling_size, E=Hd, in_frame_stride=Sp, in_off=1,
+                     ldx=Hd, sequence=(g.proj_pooling_type == "sequence"))
+        z = pooled.view(Fr * npf, Hd)
+        n = len(self.proj)
+        for i, (w, b) in enumerate(self.proj):
+            act = ops.ACT_GELU if (g.proj_layer_type == "mlp" and i < n - 1) else ops.ACT_NONE
+            z = ops.linear(z, w, b, act=act)
+        return z.view(Fr, npf, g.hidden_size)
+
+    # =========================================================================================
+    # mu2-tokenizer
+    # =========================================================================================
+    def _u2t_self_attention(self, x2: torch.Tensor, nb: int, S: int, w: _SelfAttnW,
+                            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RMA / RoPE self-attention over sequences of length S (reference rma.py:46-82, rope.py:62-91)."""
+        g = self.g
+        E, H = g.hidden_size, g.u2t_num_heads
+        dh = E // H
+        qkv = ops.linear(x2, w.wqkv, w.bqkv)
+        if g.attn_type == "rope":
+            ops.rope(qkv, rows=nb * S, ld=3 * E, dh=dh, n_q=H, n_k=H, inv_freq=self.u2t_inv_freq, pos_div=1, pos_mod=S)
+        q5 = qkv.view(nb, S, 3, H, dh)
+        ctx = torch.empty(nb, S, E, device=self.dev, dtype=BF16)
+        self._attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], ctx, 1.0 / math.sqrt(dh), rel_bias=w.rel)
+        return ops.linear(ctx.view(nb * S, E), w.wd, w.bd, residual=residual)
+
+    def _u2t_temporal_attention(self, x2: torch.Tensor, B: int, C: int, N: int, w: _SelfAttnW) -> torch.Tensor:
+        """Attention across the C frames of every (batch, token); rows stay in (b, c, n) order so the two
+        permute+contiguous copies of the reference (svr.py:33,36) disappear."""
+        g = self.g
+        E, H = g.hidden_size, g.u2t_num_heads
+        dh = E // H
+        qkv = ops.linear(x2, w.wqkv, w.bqkv)
+        if g.attn_type == "rope":
+            ops.rope(qkv, rows=B * C * N, ld=3 * E, dh=dh, n_q=H, n_k=H, inv_freq=self.u2t_inv_freq, pos_div=N, pos_mod=C)
+        ctx = torch.empty(B * C * N, E, device=self.dev, dtype=BF16)
+        ops.temporal_attention(qkv, ctx, B=B, C_=C, N=N, H=H, dh=dh, scale=1.0 / math.sqrt(dh), rel_bias=w.rel,
+                               rel_max=REL_MAX)
+        return ops.linear(ctx, w.wd, w.bd)
+
+    def _cross_attention(self, q_in: torch.Tensor, kv_in: torch.Tensor, B: int, Sq: int, Sk: int, w: _CrossAttnW,
+                         residual: Optional[torch.Tensor]) -> torch.Tensor:
+        """MultiHeadCrossAttention (reference tta.py:42-69), no mask; linagg when w.wd is None."""
+        g = self.g
+        E, H = g.hidden_size, g.u2t_num_heads
+        dh = E // H
+        q = ops.linear(q_in, w.wq, w.bq).view(B, Sq, H, dh)
+        ctx = torch.empty(B, Sq, E, device=self.dev, dtype=BF16)
+        if w.wd is None:
+            k = ops.linear(kv_in, w.wkv, w.bkv).view(B, Sk, H, dh)
+            v = kv_in.view(B, Sk, H, dh)
+            self._attention(q, k, v, ctx, 1.0 / math.sqrt(dh))
+            return ctx.view(B * Sq, E)
+        kv = ops.linear(kv_in, w.wkv, w.bkv).view(B, Sk, 2, H, dh)
+        self._attention(q, kv[:, :, 0], kv[:, :, 1], ctx, 1.0 / math.sqrt(dh))
+        return ops.linear(ctx.view(B * Sq, E), w.wd, w.bd, residual=residual)
+
+    def _token_selection_diff(self, x2: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """DifferentiableTokenSelection (reference svr.py:101-117) without the 1024-iteration Python loop:
+        scores^T = W_s X^T, softmax over the TOKEN axis, selected = softmax^T-weights @ X.
+        (score_net.bias is constant along the softmax axis and cancels exactly.)"""
+        g = self.g
+        E, K = g.hidden_size, self.score_w.shape[0]
+        Tp = _pad8(T)
+        scT = torch.empty(K, B * T, device=self.dev, dtype=F32)
+        ops.gemm(self.score_w, x2, scT, M=K, N=B * T, K=E, lda=E, ldb=E, ldc=B * T)
+        pT = torch.empty(B, K, Tp, device=self.dev, dtype=BF16)
+        ops.softmax(scT, pT, n0=B, H=1, S=K, n=T, in_strides=(T, 0, B * T), out_strides=(K * Tp, 0, Tp))
+        xT = torch.empty(B, E, Tp, device=self.dev, dtype=BF16)
+        ops.transpose_heads(x2, xT, B=B, S=T, H=1, Dh=E, in_strides=(T * E, E, 0), out_strides=(E * Tp, 0), ld_out=Tp)
+        sel = torch.empty(B, K, E, device=self.dev, dtype=BF16)
+        ops.gemm(pT, xT, sel, M=K, N=E, K=T, lda=Tp, ldb=Tp, ldc=E, zo=B, a_strides=(0, K * Tp), b_strides=(0, E * Tp),
+                 c_strides=(0, K * E))
+        return sel
+
+    def u2tokenizer(self, v_tokens: torch.Tensor, t_tokens: torch.Tensor) -> torch.Tensor:
+        """u2Tokenizer.forward (reference u2Tokenizer.py:40-47): v_tokens [B, C, N, E], t_tokens [B, Lt, E]
+        -> [B, num_3d_query_token, E]."""
+        g = self.g
+        B, C, N, E = v_tokens.shape
+        Lt = t_tokens.shape[1]
+        x = v_tokens.reshape(B * C * N, E)
+        for sp, tp in self.svr:
+            x = self._u2t_self_attention(x, B * C, N, sp)
+            x = self._u2t_temporal_attention(x, B, C, N, tp)
+        if g.enable_diffts:
+            sel = self._token_selection_diff(x, B, C * N)
+        else:
+            raise NotImplementedError("hard TokenSelection (enable_diffts=False) is not implemented yet")
+        vis = ops.multiscale_pool(sel, self.gate_w, self.gate_b, g.enable_dmtp) if g.use_multi_scale else sel
+        Mv = vis.shape[1]
+        vis2 = vis.view(B * Mv, E)
+        txt2 = t_tokens.reshape(B * Lt, E)
+        Q = g.num_3d_query_token
+        q = self.queries.unsqueeze(0).expand(B, Q, E).contiguous().view(B * Q, E)
+        for w in self.tta:
+            s = self._u2t_self_attention(q, B, Q, w["self_attn"], residual=q)
+            s = ops.layernorm(s, w["ns"][0], w["ns"][1], 1e-5)
+            v = self._cross_attention(s, vis2, B, Q, Mv, w["vis"], residual=s)
+            v = ops.layernorm(v, w["nv"][0], w["nv"][1], 1e-5)
+            t = self._cross_attention(v, txt2, B, Q, Lt, w["txt"], residual=v)
+            q = ops.layernorm(t, w["nt"][0], w["nt"][1], 1e-5)
+        out = self._cross_attention(q, vis2, B, Q, Mv, self.linagg, residual=None)
+        return out.view(B, Q, E)
+
+    # =========================================================================================
+    # multimodal front (prepare_inputs_for_multimodal, reference u2_arch.py:101-122)
+    # =========================================================================================
+    def visual_tokens(self, images: torch.Tensor, question_ids: Optional[torch.Tensor]) -> torch.Tensor:
+        g = self.g
+        if g.enable_u2tokenizer:
+            B, C = images.shape[0], images.shape[1]
+            feats = self.encode_images(images.reshape(B * C, 1, *images.shape[2:]))
+            v_tokens = feats.view(B, C, feats.shape[-2], feats.shape[-1])
+            if question_ids is None:
+                raise ValueError("question_ids is required when the mu2-tokenizer is enabled")
+            t_tokens = ops.embed_splice(question_ids.to(self.dev), self.embed, None)
+            return self.u2tokenizer(v_tokens, t_tokens)
+        return self.encode_images(images)
+
+    def multimodal_embeds(self, input_ids: torch.Tensor, images: torch.Tensor,
+                          question_ids: Optional[torch.Tensor]) -> torch.Tensor:
+        vis = self.visual_tokens(images, question_ids)
+        return ops.embed_splice(input_ids.to(self.dev), self.embed, vis)
+
+    def embed_tokens(self, input_ids: torch.Tensor) -> torch.Tensor:
+        return ops.embed_splice(input_ids.to(self.dev), self.embed, None)
+
+    # =========================================================================================
+    # decoder: prefill
+    # =========================================================================================
+    def new_cache(self, batch: int, max_len: int) -> "KVCache":
+        return KVCache(self.g, batch, max_len, self.dev)
+
+    def prefill(self, embeds: torch.Tensor, cache: Optional["KVCache"] = None) -> torch.Tensor:
+        """Decoder stack over a full prompt [B, L, E] (causal, positions 0..L-1); fills `cache` when given.
+        Returns the final-norm hidden states [B, L, E]."""
+        g = self.g
+        B, L, E = embeds.shape
+        hq, hkv, dh, I = g.num_attention_heads, g.num_key_value_heads, g.head_dim, g.intermediate_size
+        if cache is not None and (cache.batch != B or cache.max_len < L or cache.length != 0):
+            raise ValueError("prefill needs an empty cache with matching batch and max_len >= prompt length")
+        x = embeds.reshape(B * L, E).clone()
+        y = torch.empty_like(x)
+        nqkv = (hq + 2 * hkv) * dh
+        qkv = torch.empty(B * L, nqkv, device=self.dev, dtype=BF16)
+        ctx = torch.empty(B, L, hq * dh, device=self.dev, dtype=BF16)
+        gu = torch.empty(B * L, 2 * I, device=self.dev, dtype=BF16)
+        act = torch.empty(B * L, I, device=self.dev, dtype=BF16)
+        q4 = qkv.view(B, L, hq + 2 * hkv, dh)
+        for li, w in enumerate(self.layers):
+            ops.rmsnorm(x, w["ln1"], g.rms_norm_eps, out=y)
+            ops.linear(y, w["wqkv"], out=qkv)
+            kc, vc = (cache.k[li], cache.v[li]) if cache is not None else (None, None)
+            ops.rope(qkv, rows=B * L, ld=nqkv, dh=dh, n_q=hq, n_k=hkv, n_v=hkv if cache is not None else 0,
+                     inv_freq=self.inv_freq, q_norm_w=w["qn"], k_norm_w=w["kn"], eps=g.rms_norm_eps, pos0=0, pos_div=1,
+                     pos_mod=L, k_cache=kc, v_cache=vc, Tmax=cache.max_len if cache is not None else 0, rows_per_batch=L)
+            self._attention(q4[:, :, :hq], q4[:, :, hq:hq + hkv], q4[:, :, hq + hkv:], ctx, 1.0 / math.sqrt(dh), causal=True)
+            ops.linear(ctx.view(B * L, hq * dh), w["wo"], residual=x, out=x)
+            ops.rmsnorm(x, w["ln2"], g.rms_norm_eps, out=y)
+            ops.linear(y, w["wgu"], out=gu)
+            ops.silu_mul(gu, act)
+            ops.linear(act, w["wdown"], residual=x, out=x)
+        if cache is not None:
+            cache.set_length(L)
+        ops.rmsnorm(x, self.final_norm, g.rms_norm_eps, out=y)
+        return y.view(B, L, E)
+
+    def lm_logits(self, hidden: torch.Tensor, out_dtype=F32) -> torch.Tensor:
+        """lm_head over [.., E] hidden states -> [.., V] logits."""
+        return ops.linear(hidden, self.lm_head, out_dtype=out_dtype)
+
+    # =========================================================================================
+    # decoder: one KV-cached decode step (weight streaming)
+    # =========================================================================================
+    def _decode_buffers(self, B: int):
+        g = self.g
+        key = ("dec", B)
+        if getattr(self, "_dec_key", None) != key:
+            hq, hkv, dh, I, E = g.num_attention_heads, g.num_key_value_heads, g.head_dim, g.intermediate_size, g.hidden_size
+            d = self.dev
+            self._dec = dict(
+                x=torch.empty(B, E, device=d, dtype=BF16), qkv=torch.empty(B, (hq + 2 * hkv) * dh, device=d, dtype=BF16),
+                ctx=torch.empty(B, hq * dh, device=d, dtype=BF16), act=torch.empty(B, I, device=d, dtype=BF16),
+                logits=torch.empty(B, g.vocab_size, device=d, dtype=F32), ids=torch.zeros(B, 1, device=d, dtype=torch.int64))
+            self._dec_key = key
+        return self._dec
+
+    def decode_step(self, cache: "KVCache") -> torch.Tensor:
+        """Consumes buffers['ids'] [B,1] (the last token of every sequence), appends to the cache at
+        position cache.length (read on the device), leaves fp32 logits in buffers['logits'] and the greedy
+        next ids back in buffers['ids']. Launch sequence is CUDA-graph capturable."""
+        g = self.g
+        B = cache.batch
+        hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
+        bufs = self._decode_buffers(B)
+        x, qkv, ctx, act, logits, ids = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids"))
+        ops.embed_splice(ids, self.embed, None, out=x)  # [B, 1, E] gathered straight into x
+        nqkv = (hq + 2 * hkv) * dh
+        for li, w in enumerate(self.layers):
+            ops.gemv(x, w["wqkv"], qkv, norm_gamma=w["ln1"], norm_eps=g.rms_norm_eps)
+            ops.rope(qkv, rows=B, ld=nqkv, dh=dh, n_q=hq, n_k=hkv, n_v=hkv, inv_freq=self.inv_freq, q_norm_w=w["qn"],
+                     k_norm_w=w["kn"], eps=g.rms_norm_eps, pos0=0, pos_div=1, pos_mod=1, pos0_dev=cache.length_dev,
+                     k_cache=cache.k[li], v_cache=cache.v[li], Tmax=cache.max_len, rows_per_batch=1)
+            ops.decode_attention(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
+                                 T_dev=cache.length_plus1_dev, ldq=nqkv, ldo=hq * dh, scale=1.0 / math.sqrt(dh))
+            ops.gemv(ctx, w["wo"], x, residual=x)
+            ops.gemv(x, w["wgu"], act, norm_gamma=w["ln2"], norm_eps=g.rms_norm_eps, silu_pair=True)
+            ops.gemv(act, w["wdown"], x, residual=x)
+        ops.gemv(x, self.lm_head, logits, norm_gamma=self.final_norm, norm_eps=g.rms_norm_eps)
+        ops.argmax(logits, ids.view(B))
+        cache.advance_device()
+        return logits
+
+    # =========================================================================================
+    # greedy generation (reference u2llama.py:90-127 with do_sample=False)
+    # =========================================================================================
+    @torch.no_grad()
+    def generate_greedy(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None,
+                        use_graph: bool = True, return_margins: bool = False):
+        """Prefill on `embeds` [B, L, E], then max_new_tokens greedy steps. Returns new ids [B, n]
+        (and the per-step top-1/top-2 logit margins when asked, for margin-aware parity checks)."""
+        B, L, _ = embeds.shape
+        cache = self.new_cache(B, L + max_new_tokens)
+        hidden = self.prefill(embeds, cache)
+        bufs = self._decode_buffers(B)
+        logits0 = self.lm_logits(hidden[:, -1].contiguous())
+        out = torch.empty(B, max_new_tokens, device=self.dev, dtype=torch.int64)
+        margins = []
+        ops.argmax(logits0, bufs["ids"].view(B))
+        out[:, 0] = bufs["ids"].view(B)
+        if return_margins:
+            t2 = logits0.topk(2, dim=-1).values
+            margins.append(t2[:, 0] - t2[:, 1])
+        eos = None
+        if eos_token_id is not None:
+            eos = torch.as_tensor(eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id],
+                                  device=self.dev)
+        n_done = 1
+        graph = None
+
+        def finished() -> bool:
+            return eos is not None and bool(torch.isin(out[:, :n_done], eos).any(dim=1).all())
+
+        for step in range(1, max_new_tokens):
+            if eos is not None and (step % 16 == 1) and finished():
+                break
+            if use_graph and not return_margins and step >= 2:
+                if graph is None:
+                    # step 1 ran eagerly (warm-up + validation of the launch sequence); capture the same
+                    # sequence once - positions are read from the device, so every replay is a new step
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self.decode_step(cache)
+                graph.replay()
+            else:
+                lg = self.decode_step(cache)
+                if return_margins:
+                    t2 = lg.topk(2, dim=-1).values
+                    margins.append(t2[:, 0] - t2[:, 1])
+            out[:, step] = bufs["ids"].view(B)
+            n_done += 1
+        res = out[:, :n_done]
+        if return_margins:
+            return res, torch.stack(margins, dim=1)
+        return res
+
+
+class KVCache:
+    """Static KV cache [layers][B, Hkv, Tmax, dh] bf16 + the current length on the device (so the decode
+    step's launch parameters never change and the step can live in a CUDA graph)."""
+
+    def __init__(self, g: Geometry, batch: int, max_len: int, device):
+        self.batch, self.max_len = batch, max_len
+        shape = (g.num_hidden_layers, batch, g.num_key_value_heads, max_len, g.head_dim)
+        self.k = torch.zeros(shape, device=device, dtype=BF16)
+        self.v = torch.zeros(shape, device=device, dtype=BF16)
+        self.length = 0
+        self.length_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        self.length_plus1_dev = torch.ones(1, device=device, dtype=torch.int32)
+
+    def set_length(self, n: int):
+        self.length = n
+        self.length_dev.fill_(n)
+        self.length_plus1_dev.fill_(n + 1)
+
+    def advance_device(self):
+        self.length_dev.add_(1)
+        self.length_plus1_dev.add_(1)
+        self.length += 1

@@ -235,7 +235,8 @@ def multiscale_pool(x: torch.Tensor, gate_w: Optional[torch.Tensor], gate_bias: 
     return out
 
 
-def embed_splice(ids: torch.Tensor, table: torch.Tensor, vis: Optional[torch.Tensor]) -> torch.Tensor:
+def embed_splice(ids: torch.Tensor, table: torch.Tensor, vis: Optional[torch.Tensor],
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(ids, table, vis)
     if ids.dtype != torch.int64:
         ids = ids.long()
@@ -245,7 +246,8 @@ def embed_splice(ids: torch.Tensor, table: torch.Tensor, vis: Optional[torch.Ten
     n_vis = 0 if vis is None else vis.shape[1]
     if vis is not None:
         vis = vis.contiguous()
-    out = torch.empty(B, L, E, device=table.device, dtype=BF16)
+    if out is None:
+        out = torch.empty(B, L, E, device=table.device, dtype=BF16)
     _lib.check(_lib.load().u2_embed_splice_bf16(ids.data_ptr(), table.data_ptr(), _ptr(vis), out.data_ptr(), B, L, E,
                                                 n_vis, table.shape[0], _stream()), "u2_embed_splice_bf16")
     return out
