@@ -1,0 +1,421 @@
+"""HuggingFace-style module surface of the hot path (the drop-in boundary).
+
+Mirrors the reference classes
+
+    u2LlamaForCausalLM(u2MetaForCausalLM, LlamaForCausalLM)   src/model/language_model/u2llama.py:25-142
+    u2Qwen3ForCausalLM (Llama-style contract)    src/model/language_model/u2qwen3.py:25-145
+    u2MetaModel / u2MetaForCausalLM                            src/model/u2_arch.py:10-164
+
+with the same constructor / forward() / generate() / get_model() / initialize_vision_modules() /
+initialize_vision_tokenizer() signatures, the same state-dict keys (so reference checkpoints load with
+load_state_dict) and the same Auto* registration. The modules below only HOLD parameters; every
+forward computation is dispatched to `U2Engine` (hand-written sm_100a kernels behind the C ABI).
+Running them without CUDA / without libu2b200.so raises - there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from transformers import AutoConfig, AutoModelForCausalLM, LlamaForCausalLM, LlamaModel, Qwen3ForCausalLM, Qwen3Model
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from .configuration import U2LlamaConfig, U2Qwen3Config
+from .geometry import Geometry
+from .synthetic import param_shapes
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module / parameter names
+# ------------------------------------------------------------------------------------------------
+class ParamTree(nn.Module):
+    """A nested container of nn.Parameters addressed by dotted names (state-dict compatible with the
+    reference modules). It computes nothing: `forward` raises."""
+
+    def add_param(self, dotted: str, shape, dtype=None, device=None):
+        head, _, rest = dotted.partition(".")
+        if not rest:
+            self.register_parameter(head, nn.Parameter(torch.zeros(shape, dtype=dtype, device=device)))
+            return
+        child = self._modules.get(head)
+        if child is None:
+            child = ParamTree()
+            self.add_module(head, child)
+        child.add_param(rest, shape, dtype, device)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container: the computation runs in U2Engine (CUDA), not in this module")
+
+
+class ViT3DTowerParams(ParamTree):
+    """Stands where the reference's ViT3DTower stands (multimodal_encoder/vit.py:132-175)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.select_layer = config.vision_select_layer
+        self.select_feature = config.vision_select_feature
+        self._hidden = getattr(config, "vit_hidden_size", 768)
+
+    @property
+    def hidden_size(self):
+        return self._hidden
+
+
+class SpatialPoolingProjectorParams(ParamTree):
+    """Stands where SpatialPoolingProjector stands (multimodal_projector/spatial_pooling_projector.py:7-58)."""
+
+    def __init__(self, geom: Geometry):
+        super().__init__()
+        self._n = geom.tokens_per_frame
+
+    @property
+    def proj_out_num(self):
+        return self._n
+
+
+def _build_param_modules(config, which: str, dtype=None, device=None) -> nn.Module:
+    g = Geometry.from_hf(config)
+    shapes = param_shapes(g)
+    prefix = {"vision_tower": "model.vision_tower.", "mm_projector": "model.mm_projector.",
+              "u2tokenizer": "model.u2tokenizer."}[which]
+    if which == "vision_tower":
+        root = ViT3DTowerParams(config)
+    elif which == "mm_projector":
+        root = SpatialPoolingProjectorParams(g)
+    else:
+        root = ParamTree()
+    for name, shape in shapes.items():
+        if name.startswith(prefix):
+            root.add_param(name[len(prefix):], shape, dtype, device)
+    return root
+
+
+def build_vision_tower(config, **kw):
+    """reference multimodal_encoder/builder.py:4-8"""
+    vt = getattr(config, "vision_tower", None)
+    if vt is not None and "vit3d" in vt.lower():
+        return _build_param_modules(config, "vision_tower", **kw)
+    raise ValueError(f"Unknown vision tower: {vt}")
+
+
+def build_mm_projector(config, **kw):
+    """reference multimodal_projector/builder.py:80-99 (only the 'spp' projector is on the hot path)"""
+    pt = getattr(config, "mm_projector_type")
+    if pt == "spp":
+        return _build_param_modules(config, "mm_projector", **kw)
+    raise ValueError(f"Unknown projector type: {pt}")
+
+
+def build_u2tokenizer_tower(config, **kw):
+    """reference u2tokenizer/builder.py:3-14"""
+    return _build_param_modules(config, "u2tokenizer", **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# mixins (reference src/model/u2_arch.py)
+# ------------------------------------------------------------------------------------------------
+class U2MetaModel:
+    def __init__(self, config):
+        super().__init__(config)
+        self.config = config
+        if getattr(config, "vision_tower", None) is not None:
+            self.vision_tower = build_vision_tower(config)
+            self.mm_projector = build_mm_projector(config)
+            # the remote-code variant builds the tokenizer from the config too
+            # (base_model_tokenizers/.../modeling_u2Llama.py:1728); src/model defers it to
+            # initialize_vision_modules - both are supported here.
+            if getattr(config, "enable_u2tokenizer", False):
+                self.u2tokenizer = build_u2tokenizer_tower(config)
+
+    def get_u2tokenizer(self):
+        return getattr(self, "u2tokenizer", None)
+
+    def get_vision_tower(self):
+        return getattr(self, "vision_tower", None)
+
+    def initialize_vision_modules(self, model_args):
+        """reference u2_arch.py:34-83"""
+        c = self.config
+        for k in ("image_channel", "image_size", "patch_size", "vision_tower", "vision_select_layer",
+                  "vision_select_feature", "mm_projector_type", "proj_layer_type", "proj_layer_num",
+                  "proj_pooling_type", "proj_pooling_size", "enable_u2tokenizer", "u2t_num_heads", "u2t_num_layers",
+                  "u2t_top_k", "use_multi_scale", "num_3d_query_token", "enable_diffts", "enable_dmtp"):
+            setattr(c, k, getattr(model_args, k))
+        c.attn_type = getattr(model_args, "attn_type", "rma")
+        if self.get_vision_tower() is None:
+            self.vision_tower = build_vision_tower(c)
+            self.vision_tower.requires_grad_(not model_args.freeze_vision_tower)
+        if self.get_u2tokenizer() is None and model_args.enable_u2tokenizer:
+            self.u2tokenizer = build_u2tokenizer_tower(c)
+        if getattr(model_args, "pretrain_vision_model", None) is not None:
+            w = torch.load(model_args.pretrain_vision_model, map_location="cpu")
+            w.pop("patch_embedding.cls_token", None)  # unused MONAI buffer in some checkpoints
+            self.vision_tower.vision_tower.load_state_dict(w, strict=True)
+        c.mm_hidden_size = self.vision_tower.hidden_size
+        if getattr(self, "mm_projector", None) is None:
+            self.mm_projector = build_mm_projector(c)
+        if getattr(model_args, "pretrain_mm_mlp_adapter", None) is not None:
+            w = torch.load(model_args.pretrain_mm_mlp_adapter, map_location="cpu")
+            self.mm_projector.load_state_dict({k.split("mm_projector.")[1]: v for k, v in w.items() if "mm_projector" in k},
+                                              strict=True)
+
+
+class U2MetaForCausalLM(ABC):
+    @abstractmethod
+    def get_model(self):
+        ...
+
+    def get_vision_tower(self):
+        return self.get_model().get_vision_tower()
+
+    def get_u2tokenizer(self):
+        return self.get_model().get_u2tokenizer()
+
+    # ---- engine management --------------------------------------------------------------------
+    def engine(self):
+        """Build (once) the CUDA engine from this module's current parameters."""
+        eng = self.__dict__.get("_u2_engine")
+        if eng is None:
+            from .engine import U2Engine
+            p = next(self.parameters())
+            if not p.is_cuda:
+                raise RuntimeError("the mu2 hot path runs on CUDA only: move the model to a B200 (model.cuda()); "
+                                   "there is no CPU fallback")
+            sd = {k: v for k, v in self.state_dict().items()}
+            eng = U2Engine(Geometry.from_hf(self.config), sd, device=p.device)
+            self.__dict__["_u2_engine"] = eng
+        return eng
+
+    def invalidate_engine(self):
+        self.__dict__.pop("_u2_engine", None)
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate_engine()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_engine()
+        return super()._apply(fn, *a, **k)
+
+    # ---- reference surface ----------------------------------------------------------------------
+    def encode_images(self, images):
+        """reference u2_arch.py:96-99"""
+        return self.engine().encode_images(images)
+
+    def prepare_inputs_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
+                                      images, question_ids):
+        """reference u2_arch.py:101-122 (7 arguments in, 6 values out)."""
+        if self.get_vision_tower() is None or images is None or input_ids.shape[1] == 1:
+            return input_ids, position_ids, attention_mask, past_key_values, None, labels
+        inputs_embeds = self.engine().multimodal_embeds(input_ids, images, question_ids)
+        return None, position_ids, attention_mask, past_key_values, inputs_embeds, labels
+
+    def initialize_vision_tokenizer(self, model_args, tokenizer):
+        """reference u2_arch.py:124-164"""
+        num_new_tokens = model_args.num_new_tokens
+        self.resize_token_embeddings(len(tokenizer))
+        self.invalidate_engine()
+        if num_new_tokens > 0:
+            inp = self.get_input_embeddings().weight.data
+            out = self.get_output_embeddings().weight.data
+            inp[-num_new_tokens:] = inp[:-num_new_tokens].mean(dim=0, keepdim=True)
+            out[-num_new_tokens:] = out[:-num_new_tokens].mean(dim=0, keepdim=True)
+            for p in self.get_input_embeddings().parameters():
+                p.requires_grad = True
+            for p in self.get_output_embeddings().parameters():
+                p.requires_grad = not model_args.tune_mm_mlp_adapter
+        if getattr(model_args, "pretrain_mm_mlp_adapter", None):
+            w = torch.load(model_args.pretrain_mm_mlp_adapter, map_location="cpu")
+            etw = w["model.embed_tokens.weight"]
+            inp = self.get_input_embeddings().weight.data
+            if inp.shape == etw.shape:
+                inp.copy_(etw)
+            elif etw.shape[0] == num_new_tokens:
+                inp[-num_new_tokens:] = etw
+            else:
+                raise ValueError(f"Unexpected embed_tokens_weight shape. Pretrained: {etw.shape}. Current: {inp.shape}. "
+                                 f"Numer of new tokens: {num_new_tokens}.")
+
+    # ---- forward / generate shared by the Llama and Qwen3 wrappers (reference u2llama.py:41-138) ----
+    def _u2_forward(self, images=None, input_ids=None, labels=None, attention_mask=None, question_ids=None,
+                    position_ids=None, past_key_values=None, inputs_embeds=None, use_cache=None,
+                    output_attentions=None, output_hidden_states=None, return_dict=None, **kwargs):
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention maps / hidden states are not materialised by the fused path")
+        if past_key_values is not None:
+            raise NotImplementedError("HF-driven cached decoding is not supported; call generate() "
+                                      "(greedy decode runs inside the engine with its own static KV cache)")
+        eng = self.engine()
+        if inputs_embeds is None:
+            (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels
+             ) = self.prepare_inputs_for_multimodal(input_ids, position_ids, attention_mask, past_key_values, labels,
+                                                    images, question_ids)
+            if inputs_embeds is None:
+                inputs_embeds = eng.embed_tokens(input_ids)
+        # attention_mask: right-padded batches are exact under the causal mask (real tokens never see the
+        # pads to their right); the reference itself drops the mask in generate() (u2llama.py:97-99,123-126)
+        hidden = eng.prefill(inputs_embeds.to(torch.bfloat16))
+        logits = eng.lm_logits(hidden)
+        loss = None
+        if labels is not None:
+            # HF ForCausalLMLoss: shift, mean over non-ignored positions (training head; not a hot-path kernel yet)
+            shift_logits = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
+            shift_labels = labels[:, 1:].reshape(-1).to(shift_logits.device)
+            loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
+        if return_dict is False:
+            return (loss, logits) if loss is not None else (logits,)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None)
+
+    @torch.no_grad()
+    def _u2_generate(self, images=None, inputs=None, question_ids=None, **kwargs):
+        position_ids = kwargs.pop("position_ids", None)
+        attention_mask = kwargs.pop("attention_mask", None)
+        question_ids = kwargs.pop("question_ids", question_ids)
+        if inputs is None:
+            inputs = kwargs.pop("input_ids", None)
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported")
+        eng = self.engine()
+        if images is not None:
+            (inputs, position_ids, attention_mask, _, inputs_embeds, _
+             ) = self.prepare_inputs_for_multimodal(inputs, position_ids, attention_mask, None, None, images, question_ids)
+            if inputs_embeds is None:
+                inputs_embeds = eng.embed_tokens(inputs)
+        else:
+            inputs_embeds = eng.embed_tokens(inputs)
+        if kwargs.pop("do_sample", False) or kwargs.get("num_beams", 1) != 1:
+            raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is implemented on the "
+                                      "CUDA path; sampling is listed under 'next' in DESIGN.md")
+        for k in ("top_p", "top_k", "temperature", "num_beams"):
+            kwargs.pop(k, None)
+        L = inputs_embeds.shape[1]
+        gc = getattr(self, "generation_config", None)
+        max_new = kwargs.pop("max_new_tokens", None)
+        if max_new is None:
+            max_len = kwargs.pop("max_length", None) or (gc.max_length if gc is not None else 20)
+            max_new = max(1, max_len - L)
+        eos = kwargs.pop("eos_token_id", None)
+        if eos is None and gc is not None:
+            eos = gc.eos_token_id
+        pad = kwargs.pop("pad_token_id", None)
+        if pad is None and gc is not None:
+            pad = gc.pad_token_id
+        ids = eng.generate_greedy(inputs_embeds.to(torch.bfloat16), max_new_tokens=max_new, eos_token_id=eos)
+        if eos is not None:
+            eos_t = torch.as_tensor(eos if isinstance(eos, (list, tuple)) else [eos], device=ids.device)
+            hit = torch.isin(ids, eos_t)
+            after = (hit.cumsum(dim=1) - hit.long()) > 0  # strictly after the first EOS
+            if pad is None:
+                pad = int(eos_t[0])
+            ids = ids.masked_fill(after, pad)
+            keep = int((~after).any(dim=0).sum())
+            ids = ids[:, :max(keep, 1)]
+        return ids  # new tokens only, like HF generate() on inputs_embeds (reference u2llama.py:123-127)
+
+
+# ------------------------------------------------------------------------------------------------
+# concrete classes
+# ------------------------------------------------------------------------------------------------
+class U2LlamaModel(U2MetaModel, LlamaModel):
+    config_class = U2LlamaConfig
+
+    def __init__(self, config):
+        super().__init__(config)
+
+
+class U2LlamaForCausalLM(U2MetaForCausalLM, LlamaForCausalLM):
+    config_class = U2LlamaConfig
+
+    def __init__(self, config):
+        super(LlamaForCausalLM, self).__init__(config)
+        self.model = U2LlamaModel(config)
+        self.pretraining_tp = getattr(config, "pretraining_tp", 1)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.post_init()
+
+    def get_model(self):
+        return self.model
+
+    def forward(self, images=None, input_ids=None, labels=None, attention_mask=None, question_ids=None,
+                position_ids=None, past_key_values=None, inputs_embeds=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, **kwargs) -> Union[Tuple, CausalLMOutputWithPast]:
+        return self._u2_forward(images, input_ids, labels, attention_mask, question_ids, position_ids, past_key_values,
+                                inputs_embeds, use_cache, output_attentions, output_hidden_states, return_dict, **kwargs)
+
+    @torch.no_grad()
+    def generate(self, images=None, inputs=None, question_ids=None, **kwargs):
+        return self._u2_generate(images, inputs, question_ids, **kwargs)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        images = kwargs.pop("images", None)
+        out = super().prepare_inputs_for_generation(input_ids, past_key_values=past_key_values,
+                                                    inputs_embeds=inputs_embeds, **kwargs)
+        if images is not None:
+            out["images"] = images
+        return out
+
+
+class U2Qwen3Model(U2MetaModel, Qwen3Model):
+    config_class = U2Qwen3Config
+
+    def __init__(self, config):
+        super().__init__(config)
+
+
+class U2Qwen3ForCausalLM(U2MetaForCausalLM, Qwen3ForCausalLM):
+    """Qwen3 wrapper with the working (Llama-style) contract; the shipped reference u2qwen3.py is
+    internally inconsistent and cannot serve as the surface."""
+    config_class = U2Qwen3Config
+
+    def __init__(self, config):
+        super(Qwen3ForCausalLM, self).__init__(config)
+        self.model = U2Qwen3Model(config)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.post_init()
+
+    def get_model(self):
+        return self.model
+
+    def forward(self, images=None, input_ids=None, labels=None, attention_mask=None, question_ids=None,
+                position_ids=None, past_key_values=None, inputs_embeds=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, **kwargs) -> Union[Tuple, CausalLMOutputWithPast]:
+        return self._u2_forward(images, input_ids, labels, attention_mask, question_ids, position_ids, past_key_values,
+                                inputs_embeds, use_cache, output_attentions, output_hidden_states, return_dict, **kwargs)
+
+    @torch.no_grad()
+    def generate(self, images=None, inputs=None, question_ids=None, **kwargs):
+        return self._u2_generate(images, inputs, question_ids, **kwargs)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        images = kwargs.pop("images", None)
+        out = super().prepare_inputs_for_generation(input_ids, past_key_values=past_key_values,
+                                                    inputs_embeds=inputs_embeds, **kwargs)
+        if images is not None:
+            out["images"] = images
+        return out
+
+
+# reference-compatible aliases (class names used by the reference's callers / checkpoints)
+u2LlamaForCausalLM = U2LlamaForCausalLM
+u2Qwen3ForCausalLM = U2Qwen3ForCausalLM
+
+
+def register_auto_classes():
+    """AutoConfig / AutoModelForCausalLM registration (reference u2llama.py:141-142, u2qwen3.py:144-145)."""
+    for cfg, mdl in ((U2LlamaConfig, U2LlamaForCausalLM), (U2Qwen3Config, U2Qwen3ForCausalLM)):
+        try:
+            AutoConfig.register(cfg.model_type, cfg)
+        except ValueError:
+            pass
+        try:
+            AutoModelForCausalLM.register(cfg, mdl)
+        except ValueError:
+            pass
+
+
+register_auto_classes()
