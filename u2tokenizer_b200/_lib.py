@@ -121,7 +121,25 @@ def load():
     return lib
 
 
+# kernels launched per entry point (u2_multiscale_pool_bf16: gate + write, counted at its maximum)
+KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2}
+_launches = 0
+
+
+def launches() -> int:
+    """Number of CUDA kernels this process has launched through the C ABI so far."""
+    return _launches
+
+
+def add_launches(n: int) -> None:
+    """CUDA-graph replays re-launch the captured kernels without going through check()."""
+    global _launches
+    _launches += n
+
+
 def check(rc: int, what: str) -> None:
+    global _launches
+    _launches += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = load().u2_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -544,10 +544,15 @@ class U2Engine:
                 if graph is None:
                     # step 1 ran eagerly (warm-up + validation of the launch sequence); capture the same
                     # sequence once - positions are read from the device, so every replay is a new step
+                    from . import _lib
+                    n0 = _lib.launches()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         self.decode_step(cache)
+                    n_graph = _lib.launches() - n0
+                    _lib.add_launches(-n_graph)  # capture records, it does not execute
                 graph.replay()
+                _lib.add_launches(n_graph)
             else:
                 lg = self.decode_step(cache)
                 if return_margins:
