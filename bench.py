@@ -203,7 +203,10 @@ def cpu_baseline(geom, spec, budget_note=True):
     import copy
     from oracle import u2_oracle as O
     from u2tokenizer_b200.synthetic import synthetic_inputs, synthetic_state_dict
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g1 = copy.deepcopy(geom)
     g1.vit_layers, g1.u2t_num_layers, g1.num_hidden_layers = 1, 1, 1
@@ -248,6 +251,7 @@ def cpu_baseline(geom, spec, budget_note=True):
         head = torch.randn(min(geom.vocab_size, 32768), g1.hidden_size)
         hx = torch.randn(1, g1.hidden_size)
         timed("lm_head_32k_rows", lambda: hx @ head.t())
+    log("[cpu_baseline] parts (s):", {k: round(v, 4) for k, v in t.items()}, "threads", cores)
     nl_v, nl_u, nl_d = geom.vit_layers, geom.u2t_num_layers, geom.num_hidden_layers
     tta_layer = max(t["tta_layer_plus_linagg"] - t["linagg"], 0.0)
     vision = t["patch_embed"] + nl_v * t["vit_block"] + t["projector"] + nl_u * t["svr_layer"] + t["select_pool"] \

@@ -90,9 +90,12 @@ def test_forward_logits_and_generate(family):
     hidden = eng.prefill(emb)
     logits = eng.lm_logits(hidden)
     check(logits, ref_logits, what="prefill logits")
+    # an argmax flip needs a top-1/top-2 margin below twice the logit error: derive the threshold from the
+    # error actually measured on the prefill logits (x4 headroom for the cached decode steps)
+    thr = 4.0 * (logits.float().cpu() - ref_logits).abs().max().item()
+    assert thr < 0.15 * ref_logits.abs().max().item()
     for use_graph in (False, True):
         got = eng.generate_greedy(emb, max_new_tokens=8, use_graph=use_graph).cpu()
-        thr = 2e-2 * ref_logits.abs().max().item()
         # compare up to (excluding) the first low-margin step of each sequence: after it the oracle's own
         # choice is not robust to bf16 rounding and the continuations legitimately diverge
         for b in range(got.shape[0]):

@@ -49,7 +49,8 @@ def test_forward_and_generate_surface(family):
     lg = out.logits.float().cpu()
     assert rel_err(lg, ref_logits) < 3e-2 and cosine(lg, ref_logits) > 0.999
     assert abs(out.loss.item() - ref_loss.item()) < 3e-2 * max(1.0, ref_loss.item())
-    thr = 2e-2 * ref_logits.abs().max().item()
+    thr = 4.0 * (lg - ref_logits).abs().max().item()  # margin below which an argmax flip is within bf16 error
+    assert thr < 0.15 * ref_logits.abs().max().item()
 
     def same(got):
         got = got.cpu()
