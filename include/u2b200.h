@@ -114,9 +114,10 @@ typedef struct u2_softmax_desc {
 } u2_softmax_desc;
 U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_softmax_desc* desc, void* stream);
 
-/* out[r, i] = silu(gate_up[r, i]) * gate_up[r, I + i]  (HF Qwen3MLP / LlamaMLP act_fn(gate) * up) */
+/* out[r, i] = silu(g) * u with (g, u) = gate_up[r, i], gate_up[r, I + i]  (interleaved == 0) or
+ * gate_up[r, 2i], gate_up[r, 2i + 1] (interleaved != 0)   (HF Qwen3MLP / LlamaMLP act_fn(gate) * up) */
 U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t rows, int32_t I, int64_t ldg,
-                            int64_t ldo, void* stream);
+                            int64_t ldo, int32_t interleaved, void* stream);
 
 /* Vision-front data movement ----------------------------------------------------------------------------
  * patchify: fp32 volume [frames, d0, d1, d2] -> bf16 patch rows [frames * n_patches, p0*p1*p2] in the
@@ -183,8 +184,8 @@ U2_API int u2_decode_attention_bf16(const void* q, const void* k_cache, const vo
                                     const int32_t* T_dev, int64_t ldq, int64_t ldo, float scale, void* stream);
 
 /* Decode-step linear (weight streaming, HBM-bound): y[b, n] = sum_k norm(x)[b, k] * w[n, k] (+ residual).
- * B <= 8. norm_gamma != NULL fuses the input RMSNorm; silu_pair != 0 treats w as [gate; up] halves and
- * writes silu(gate) * up (N/2 outputs). */
+ * B <= 8. norm_gamma != NULL fuses the input RMSNorm; silu_pair != 0 treats rows (2j, 2j+1) of w as
+ * (gate_j, up_j) and writes silu(gate) * up (N/2 outputs). */
 typedef struct u2_gemv_desc {
   int32_t B, N, K;
   int64_t ldx, ldw, ldy, ldr;
@@ -196,6 +197,34 @@ typedef struct u2_gemv_desc {
 } u2_gemv_desc;
 U2_API int u2_gemv_bf16(const void* x, const void* w, void* y, const u2_gemv_desc* desc, void* stream);
 U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld, void* stream);
+
+/* Decode-step linear on the tensor cores (swap-AB, stream-K over all SMs, TMA weight stream; HBM-bound):
+ *   acc[b, n] = sum_k x[b, k] * w[n, k]                       B <= 16, K % 64 == 0
+ *   v = acc * rsqrt(ssq_in[b] / K + eps)   (when ssq_in != NULL: fused RMSNorm, x must already carry gamma)
+ *   silu_pair: rows (2j, 2j+1) of w are (gate_j, up_j):  y[b, j] = silu(v_2j) * v_2j+1
+ *   else:      y[b, n] = v + residual[b, n];  optionally xg[b, n] = bf16(y * gamma_next[n]) and
+ *              ssq_out[b] += sum_n y^2 (prepares the next fused norm); ssq_zero[0..15] is reset to 0.
+ * ws: fp32 [ceil(N/128)*128*16], counters: int32 [ceil(N/128)], both zero on entry and zero again on exit.
+ * Replaces the HF decoder Linears at q_len == 1 (reference u2llama.py:123-126 -> GenerationMixin._sample). */
+typedef struct u2_dlinear_desc {
+  int32_t B, N, K;
+  int64_t ldx, ldw, ldy, ldr, ldxg;
+  int32_t y_dtype;
+  float* ws;
+  int32_t* counters;
+  const float* ssq_in;
+  float eps;
+  const void* residual;
+  int32_t silu_pair;
+  const float* gamma_next;
+  void* xg;
+  float* ssq_out;
+  float* ssq_zero;
+} u2_dlinear_desc;
+U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
+/* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0 (start of a decode step) */
+U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x, void* xg,
+                                float* ssq, float* ssq_zero, int32_t B, int32_t E, int64_t vocab, void* stream);
 
 #ifdef __cplusplus
 }

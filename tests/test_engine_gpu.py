@@ -94,7 +94,8 @@ def test_forward_logits_and_generate(family):
     # error actually measured on the prefill logits (x4 headroom for the cached decode steps)
     thr = 4.0 * (logits.float().cpu() - ref_logits).abs().max().item()
     assert thr < 0.15 * ref_logits.abs().max().item()
-    for use_graph in (False, True):
+    for use_graph, impl in ((False, "tcgen05"), (True, "tcgen05"), (False, "gemv"), (True, "gemv")):
+        eng.decode_impl = impl
         got = eng.generate_greedy(emb, max_new_tokens=8, use_graph=use_graph).cpu()
         # compare up to (excluding) the first low-margin step of each sequence: after it the oracle's own
         # choice is not robust to bf16 rounding and the continuations legitimately diverge
@@ -105,10 +106,12 @@ def test_forward_logits_and_generate(family):
         assert got.shape == ref_ids.shape
 
 
-def test_decode_matches_prefill():
+@pytest.mark.parametrize("impl", ["tcgen05", "gemv"])
+def test_decode_matches_prefill(impl):
     """KV-cached decode steps reproduce teacher-forced prefill logits (size-independent property)."""
     g = tiny_geometry()
     eng, sd = build(g, 4)
+    eng.decode_impl = impl
     gen = torch.Generator().manual_seed(5)
     emb = (torch.randn(2, 20, g.hidden_size, generator=gen) * 0.5).bfloat16().cuda()
     full = eng.lm_logits(eng.prefill(emb))

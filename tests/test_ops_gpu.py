@@ -72,6 +72,7 @@ def test_silu_mul():
     from u2tokenizer_b200 import ops
     gu = torch.randn(50, 2 * 768, device=DEV, generator=gen(1)).bfloat16()
     close(ops.silu_mul(gu), F.silu(gu[:, :768].float()) * gu[:, 768:].float())
+    close(ops.silu_mul(gu, interleaved=True), F.silu(gu[:, 0::2].float()) * gu[:, 1::2].float())
 
 
 def test_patchify():
@@ -253,7 +254,7 @@ def test_gemv(B, N, K):
         o2 = torch.empty(B, N // 2, device=DEV, dtype=torch.bfloat16)
         ops.gemv(x, w, o2, silu_pair=True)
         y = x.float() @ w.float().t()
-        close(o2, F.silu(y[:, :N // 2]) * y[:, N // 2:], 2e-2)
+        close(o2, F.silu(y[:, 0::2]) * y[:, 1::2], 2e-2)
 
 
 def test_argmax():
@@ -263,3 +264,61 @@ def test_argmax():
     lg[1, 5000] = 100.0  # tie -> first index
     assert torch.equal(ops.argmax(lg), lg.argmax(-1))
     assert ops.argmax(lg)[1].item() == 77
+
+
+@pytest.mark.parametrize("B", [1, 4, 16])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (1000, 320), (6144, 2048), (24576, 4096), (4096, 12288), (151936, 1024)])
+def test_dlinear(B, N, K):
+    """tcgen05 decode linear (swap-AB + stream-K): plain, fused-norm scale, residual + next-norm prep, silu pair."""
+    from u2tokenizer_b200 import ops
+    g = gen(B * N + K + 1)
+    x = torch.randn(B, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * K ** -0.5).bfloat16()
+    tiles = (N + 127) // 128
+    ws = torch.zeros(tiles * 128 * 16, device=DEV)
+    cnt = torch.zeros(tiles, device=DEV, dtype=torch.int32)
+    ref = x.float() @ w.float().t()
+    # (a) fp32 output, fused RMSNorm scale
+    ssq = torch.zeros(16, device=DEV)
+    ssq[:B] = torch.rand(B, device=DEV, generator=g) * K + 1.0
+    out = torch.empty(B, N, device=DEV)
+    for _ in range(2):  # twice: the workspace must come back clean
+        ops.dlinear(x, w, out, ws=ws, counters=cnt, ssq_in=ssq, eps=1e-6)
+        close(out, ref * torch.rsqrt(ssq[:B] / K + 1e-6)[:, None])
+    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+    # (b) residual (in place) + xg + ssq_out + ssq_zero
+    res = torch.randn(B, N, device=DEV, generator=g).bfloat16()
+    xres = res.clone()
+    gam = 1 + 0.1 * torch.randn(N, device=DEV, generator=g)
+    xg = torch.empty(B, N, device=DEV, dtype=torch.bfloat16)
+    sso = torch.zeros(16, device=DEV)
+    ssz = torch.ones(16, device=DEV)
+    ops.dlinear(x, w, xres, ws=ws, counters=cnt, residual=xres, gamma_next=gam, xg=xg, ssq_out=sso, ssq_zero=ssz)
+    want = (ref + res.float())
+    close(xres, want)
+    close(xg, xres.float() * gam, 1e-2)
+    close(sso[:B], xres.float().pow(2).sum(-1), 1e-3)
+    assert ssz.abs().max().item() == 0
+    # (c) silu pair on interleaved rows
+    if N % 2 == 0:
+        act = torch.empty(B, N // 2, device=DEV, dtype=torch.bfloat16)
+        ops.dlinear(x, w, act, ws=ws, counters=cnt, silu_pair=True)
+        close(act, F.silu(ref[:, 0::2]) * ref[:, 1::2], 2e-2)
+    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+
+
+def test_decode_embed():
+    from u2tokenizer_b200 import ops
+    g = gen(77)
+    table = torch.randn(50, 256, device=DEV, generator=g).bfloat16()
+    ids = torch.tensor([[3], [49], [0]], device=DEV)
+    gam = 1 + 0.1 * torch.randn(256, device=DEV, generator=g)
+    x = torch.empty(3, 256, device=DEV, dtype=torch.bfloat16)
+    xg = torch.empty_like(x)
+    ssq, ssz = torch.zeros(16, device=DEV), torch.ones(16, device=DEV)
+    ops.decode_embed(ids, table, gam, x, xg, ssq, ssz)
+    e = table[ids.view(-1)]
+    assert torch.equal(x, e)
+    close(xg, e.float() * gam, 1e-2)
+    close(ssq[:3], e.float().pow(2).sum(-1), 1e-4)
+    assert ssz[:3].abs().max().item() == 0

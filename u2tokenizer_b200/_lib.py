@@ -73,6 +73,24 @@ class GemvDesc(C.Structure):
     ]
 
 
+class DlinearDesc(C.Structure):
+    """Mirror of ``u2_dlinear_desc``."""
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldy", C.c_int64), ("ldr", C.c_int64), ("ldxg", C.c_int64),
+        ("y_dtype", C.c_int32),
+        ("ws", C.c_void_p), ("counters", C.c_void_p),
+        ("ssq_in", C.c_void_p),
+        ("eps", C.c_float),
+        ("residual", C.c_void_p),
+        ("silu_pair", C.c_int32),
+        ("gamma_next", C.c_void_p),
+        ("xg", C.c_void_p),
+        ("ssq_out", C.c_void_p),
+        ("ssq_zero", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -84,7 +102,7 @@ SIGNATURES = {
     "u2_layernorm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _F, _P]),
     "u2_rmsnorm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _F, _P]),
     "u2_softmax_f32_bf16": (C.c_int, [_P, _P, C.POINTER(SoftmaxDesc), _P]),
-    "u2_silu_mul_bf16": (C.c_int, [_P, _P, _L, _I, _L, _L, _P]),
+    "u2_silu_mul_bf16": (C.c_int, [_P, _P, _L, _I, _L, _L, _I, _P]),
     "u2_patchify_f32_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "u2_set_rows_bf16": (C.c_int, [_P, _P, _L, _L, _L, _I, _P]),
     "u2_transpose_heads_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
@@ -96,6 +114,8 @@ SIGNATURES = {
     "u2_decode_attention_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _F, _P]),
     "u2_gemv_bf16": (C.c_int, [_P, _P, _P, C.POINTER(GemvDesc), _P]),
     "u2_argmax_f32": (C.c_int, [_P, _P, _I, _I, _L, _P]),
+    "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
+    "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
 }
 
 

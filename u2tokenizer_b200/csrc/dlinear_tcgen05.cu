@@ -1,0 +1,374 @@
+// Decode-step linear layers on tcgen05 with a TMA weight stream ("skinny GEMM", swap-AB + stream-K).
+//
+//   y[b, n] = epilogue( sum_k W[n, k] * x[b, k] ),   b < B <= 16,  one generated token per sequence
+//
+// Every weight byte is read exactly once per token, so the kernel is HBM-bound; the design goal is to
+// keep >= 148 deep TMA pipelines pulling 16 KB weight tiles back to back:
+//   * swap-AB: the weight rows are the MMA M dimension (128 per tile), the <= 16 sequences are N = 16,
+//     so the tensor-core cost per 64-wide k-block is 4 tiny MMAs (128 x 16 x 16) - the tensor pipe idles,
+//     the TMA engine and HBM do the work;
+//   * stream-K: the (tile, k-block) space is cut into one equal contiguous range per CTA (grid = #SMs),
+//     so narrow layers (o_proj, down_proj: 32 row tiles) still occupy every SM;
+//   * partial sums meet in an fp32 workspace through red.global.add; the CTA that completes a tile
+//     (per-tile k-block counter) runs the fused epilogue and re-zeroes workspace + counter, so the
+//     workspace is self-cleaning and one kernel launch per linear suffices;
+//   * fused epilogues: RMSNorm scale (x is pre-multiplied by gamma, the per-sequence 1/rms is applied to
+//     the result), residual add, SiLU(gate)*up on row-interleaved [gate_j, up_j] weights, and the
+//     "prepare the next norm" outputs (x * gamma_next in bf16, sum of squares per sequence).
+//
+// Warp roles as in gemm_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue. Replaces the HF decoder Linears at q_len == 1 inside generate()
+// (reference src/model/language_model/u2llama.py:123-126 -> HF GenerationMixin._sample).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+#include "u2b200.h"
+
+namespace u2 {
+
+constexpr int kDlM = 128;      // weight rows per tile (UMMA M)
+constexpr int kDlN = 16;       // padded batch (UMMA N)
+constexpr int kDlK = 64;       // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kDlStages = 10;
+constexpr int kDlABytes = kDlM * kDlK * 2;   // 16 KB
+constexpr int kDlBBytes = kDlN * kDlK * 2;   // 2 KB
+constexpr int kDlStageBytes = kDlABytes + kDlBBytes;
+constexpr int kDlSmem = kDlStages * kDlStageBytes + 1024 + 256;
+constexpr int kDlThreads = 256;
+constexpr int kDlTmemCols = 32;  // 2 accumulator buffers x 16 columns
+
+struct DlinArgs {
+  int B, N, K;                 // sequences, output rows of W, reduction length
+  int num_tiles, kblocks;      // ceil(N/128), K/64
+  float* ws;                   // [num_tiles*128][16] fp32, zero between launches
+  int* counters;               // [num_tiles] int32, zero between launches
+  // epilogue
+  const float* ssq_in;         // [16] sum of squares of the (un-normalised) input rows, or null
+  float inv_norm_dim, eps;     // rstd = rsqrt(ssq_in[b] * inv_norm_dim + eps)
+  const __nv_bfloat16* residual;  // [B, N] (ldr) or null
+  long long ldr;
+  void* y;                     // [B, N_out] bf16 / fp32 (ldy); N_out = N/2 when silu_pair
+  long long ldy;
+  int y_dtype;
+  int silu_pair;               // rows (2j, 2j+1) = (gate_j, up_j) -> y[b, j] = silu(gate) * up
+  const float* gamma_next;     // [N] or null: also write xg[b, n] = bf16(y * gamma_next[n]) ...
+  __nv_bfloat16* xg;           // ... here (ldxg)
+  long long ldxg;
+  float* ssq_out;              // [16] += sum_n y^2 (of the bf16-rounded y), or null
+  float* ssq_zero;             // [16] buffer to reset (the one the *next* producer accumulates into), or null
+};
+
+__global__ void __launch_bounds__(kDlThreads, 1)
+dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                       const DlinArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kDlStages * kDlABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDlStages * kDlStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kDlStages;
+  uint64_t* tmem_full_bar = bars + 2 * kDlStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kDlStages + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDlStages + 4);
+  int* s_last = reinterpret_cast<int*>(tmem_base_slot + 1);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  // stream-K: equal contiguous range of (tile, k-block) units per CTA
+  const long long units = (long long)p.num_tiles * p.kblocks;
+  const long long u_begin = units * blockIdx.x / gridDim.x;
+  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kDlStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc<kDlTmemCols>(tmem_base_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int tile = (int)(u / p.kblocks);
+        const int kb = (int)(u - (long long)tile * p.kblocks);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kDlStageBytes);
+        tma_load_4d(smem_a + stage * kDlABytes, &tmap_w, &full_bar[stage], kb * kDlK, tile * kDlM, 0, 0);
+        tma_load_4d(smem_b + stage * kDlBBytes, &tmap_x, &full_bar[stage], kb * kDlK, 0, 0, 0);
+        if (++stage == kDlStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kDlM, kDlN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      long long u = u_begin;
+      while (u < u_end) {
+        const int tile = (int)(u / p.kblocks);
+        long long seg_end = (long long)(tile + 1) * p.kblocks;
+        if (seg_end > u_end) seg_end = u_end;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kDlN;
+        bool first = true;
+        for (; u < seg_end; ++u) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kDlABytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kDlBBytes));
+#pragma unroll
+          for (int k = 0; k < kDlK / 16; ++k) {
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kDlStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int q = warp_idx - 4;
+    const int et = threadIdx.x - 128;  // 0..127: row within the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long u = u_begin;
+    while (u < u_end) {
+      const int tile = (int)(u / p.kblocks);
+      long long seg_end = (long long)(tile + 1) * p.kblocks;
+      if (seg_end > u_end) seg_end = u_end;
+      const int seg_kb = (int)(seg_end - u);
+      u = seg_end;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t v[16];
+      {
+        const uint32_t taddr = tmem_base + acc * kDlN + (static_cast<uint32_t>(q * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr)
+            : "memory");
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);  // accumulator buffer is free again
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+
+      const int row = tile * kDlM + et;  // output row n of W
+      float* wsr = p.ws + (long long)row * kDlN;
+      const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
+      float f[16];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
+      bool last = whole;
+      if (!whole) {
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+          if (b < p.B) atomicAdd(wsr + b, f[b]);
+        __threadfence();
+        // all 128 epilogue threads have published their partial sums -> bump the tile counter once
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int old = atomicAdd(p.counters + tile, seg_kb);
+          *s_last = (old + seg_kb == p.kblocks) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        last = (*s_last != 0);
+        if (last) {
+          __threadfence();
+#pragma unroll
+          for (int b = 0; b < 16; ++b)
+            if (b < p.B) {
+              f[b] = __ldcg(wsr + b);
+              __stcg(wsr + b, 0.f);  // self-cleaning workspace
+            }
+          if (et == 0) p.counters[tile] = 0;
+        }
+      }
+      if (last) {
+        // ---------------- fused epilogue for the finished tile ----------------
+        if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
+        const bool row_ok = row < p.N;
+        float sq[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          sq[b] = 0.f;
+          if (b < p.B) {
+            float val = f[b];
+            if (p.ssq_in) val *= rsqrtf(p.ssq_in[b] * p.inv_norm_dim + p.eps);
+            if (p.silu_pair) {
+              // rounding points of the unfused path: gate/up are bf16 before the activation
+              const float me = __bfloat162float(__float2bfloat16(val));
+              const float other = __shfl_down_sync(0xffffffffu, me, 1);
+              if (row_ok && (et & 1) == 0) {
+                const float o = me / (1.f + __expf(-me)) * other;
+                reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
+              }
+            } else if (row_ok) {
+              if (p.residual) val += __bfloat162float(p.residual[(long long)b * p.ldr + row]);
+              if (p.y_dtype == U2_DT_BF16) {
+                const __nv_bfloat16 o = __float2bfloat16(val);
+                reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + row] = o;
+                val = __bfloat162float(o);
+              } else {
+                reinterpret_cast<float*>(p.y)[(long long)b * p.ldy + row] = val;
+              }
+              if (p.gamma_next) p.xg[(long long)b * p.ldxg + row] = __float2bfloat16(val * p.gamma_next[row]);
+              sq[b] = val * val;
+            }
+          }
+        }
+        if (p.ssq_out) {
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            if (b < p.B) {
+              float s = sq[b];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+              if (lane == 0) atomicAdd(p.ssq_out + b, s);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<kDlTmemCols>(tmem_base);
+  }
+}
+
+// embed gather for the decode step + preparation of the first layer's fused norm:
+// x[b] = table[ids[b]], xg[b] = bf16(x * gamma), ssq[b] = sum x^2 ; also resets ssq_zero.
+__global__ void __launch_bounds__(256)
+decode_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xg,
+                    float* __restrict__ ssq, float* __restrict__ ssq_zero, int E, long long vocab) {
+  const int b = blockIdx.x;
+  long long id = ids[b];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;
+  const __nv_bfloat16* src = table + id * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const __nv_bfloat16 v = src[i];
+    const float f = __bfloat162float(v);
+    x[(long long)b * E + i] = v;
+    xg[(long long)b * E + i] = __float2bfloat16(f * gamma[i]);
+    s += f * f;
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    ssq[b] = t;
+    if (ssq_zero) ssq_zero[b] = 0.f;
+  }
+}
+
+}  // namespace u2
+
+using namespace u2;
+
+extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* d, void* stream) {
+  if (!x || !w || !y || !d || !d->ws || !d->counters) return set_error(U2_ERR_ARG, "dlinear: null pointer");
+  if (d->B < 1 || d->B > kDlN) return set_error(U2_ERR_UNSUPPORTED, "dlinear: 1 <= B <= 16 (got %d)", d->B);
+  if (d->N <= 0 || d->K <= 0 || (d->K % kDlK)) return set_error(U2_ERR_ARG, "dlinear: K must be a positive multiple of 64");
+  if ((d->ldx & 7) || (d->ldw & 7)) return set_error(U2_ERR_ARG, "dlinear: ldx/ldw must be multiples of 8");
+  if (d->silu_pair && (d->N & 1)) return set_error(U2_ERR_ARG, "dlinear: silu_pair needs an even N");
+  if (d->gamma_next && !d->xg) return set_error(U2_ERR_ARG, "dlinear: gamma_next needs xg");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dlinear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem);
+    if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  DlinArgs p;
+  p.B = d->B; p.N = d->N; p.K = d->K;
+  p.num_tiles = (d->N + kDlM - 1) / kDlM;
+  p.kblocks = d->K / kDlK;
+  p.ws = d->ws; p.counters = d->counters;
+  p.ssq_in = d->ssq_in;
+  p.inv_norm_dim = 1.0f / (float)d->K;
+  p.eps = d->eps;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p.ldr = d->ldr;
+  p.y = y; p.ldy = d->ldy; p.y_dtype = d->y_dtype;
+  p.silu_pair = d->silu_pair;
+  p.gamma_next = d->gamma_next;
+  p.xg = reinterpret_cast<__nv_bfloat16*>(d->xg);
+  p.ldxg = d->ldxg;
+  p.ssq_out = d->ssq_out;
+  p.ssq_zero = d->ssq_zero;
+  CUtensorMap tw, tx;
+  int rc = make_tmap_bf16_4d(&tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kDlM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_4d(&tx, x, d->K, d->B, 1, 1, d->ldx, 0, 0, kDlK, kDlN);
+  if (rc) return rc;
+  const long long units = (long long)p.num_tiles * p.kblocks;
+  int grid = num_sms();
+  if (grid <= 0) return set_error(U2_ERR_CUDA, "dlinear: cannot query SM count");
+  if (units < grid) grid = (int)units;
+  dlinear_tcgen05_kernel<<<grid, kDlThreads, kDlSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tw, tx, p);
+  U2_CHECK_LAUNCH("dlinear");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x,
+                                           void* xg, float* ssq, float* ssq_zero, int32_t B, int32_t E,
+                                           int64_t vocab, void* stream) {
+  if (!ids || !table || !gamma || !x || !xg || !ssq) return set_error(U2_ERR_ARG, "decode_embed: null pointer");
+  if (B < 1 || B > kDlN) return set_error(U2_ERR_UNSUPPORTED, "decode_embed: 1 <= B <= 16");
+  decode_embed_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), reinterpret_cast<const __nv_bfloat16*>(table), gamma,
+      reinterpret_cast<__nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(xg), ssq, ssq_zero, E, vocab);
+  U2_CHECK_LAUNCH("decode_embed");
+  return U2_OK;
+}

@@ -48,7 +48,7 @@ struct GemvArgs {
   int B, N, K;
   long long ldx, ldw, ldy, ldr;
   int y_dtype;
-  int silu_pair;            // rows [0, N/2) are "gate", rows [N/2, N) "up": y[b, n] = silu(g_n) * u_n, N/2 outputs
+  int silu_pair;            // rows (2j, 2j+1) are (gate_j, up_j): y[b, j] = silu(g_j) * u_j, N/2 outputs
 };
 
 template <int kB, int kRows>
@@ -126,8 +126,9 @@ gemv_kernel(const GemvArgs a) {
         uint4 wv[kW];
 #pragma unroll
         for (int r = 0; r < kW; ++r) {
-          const int row = row0 + r + s * n_out;
-          const int rr = (row0 + r < n_out) ? row : (s * n_out + n_out - 1);
+          // silu_pair: weight rows are interleaved (gate_j, up_j) = rows (2j, 2j+1)
+          const int rb = (row0 + r < n_out) ? (row0 + r) : (n_out - 1);
+          const int rr = a.silu_pair ? 2 * rb + s : rb;
           wv[r] = ldg_stream(reinterpret_cast<const uint4*>(a.w + (long long)rr * a.ldw) + v);
         }
 #pragma unroll

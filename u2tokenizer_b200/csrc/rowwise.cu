@@ -238,7 +238,7 @@ softmax_rows_kernel(const SoftmaxArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, long long rows,
-                int I, long long ldg, long long ldo) {
+                int I, long long ldg, long long ldo, int interleaved) {
   const int nvec = I >> 3;
   const long long total = rows * nvec;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -246,8 +246,19 @@ silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict_
     const long long r = idx / nvec;
     const int c = (int)(idx - r * nvec);
     float g[8], u[8], o[8];
-    unpack8(reinterpret_cast<const uint4*>(gu + r * ldg)[c], g);
-    unpack8(reinterpret_cast<const uint4*>(gu + r * ldg + I)[c], u);
+    if (interleaved) {
+      float a[8], b[8];
+      unpack8(reinterpret_cast<const uint4*>(gu + r * ldg)[2 * c], a);
+      unpack8(reinterpret_cast<const uint4*>(gu + r * ldg)[2 * c + 1], b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g[j] = a[2 * j]; u[j] = a[2 * j + 1];
+        g[4 + j] = b[2 * j]; u[4 + j] = b[2 * j + 1];
+      }
+    } else {
+      unpack8(reinterpret_cast<const uint4*>(gu + r * ldg)[c], g);
+      unpack8(reinterpret_cast<const uint4*>(gu + r * ldg + I)[c], u);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
     reinterpret_cast<uint4*>(out + r * ldo)[c] = pack8(o);
@@ -311,7 +322,7 @@ extern "C" U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_s
 }
 
 extern "C" U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t rows, int32_t I, int64_t ldg,
-                                       int64_t ldo, void* stream) {
+                                       int64_t ldo, int32_t interleaved, void* stream) {
   if (!gate_up || !out) return set_error(U2_ERR_ARG, "silu_mul: null pointer");
   if (I <= 0 || (I & 7) || (ldg & 7) || (ldo & 7)) return set_error(U2_ERR_ARG, "silu_mul: I/ld must be multiples of 8");
   if (rows <= 0) return U2_OK;
@@ -319,7 +330,7 @@ extern "C" U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t r
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   silu_mul_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(gate_up), reinterpret_cast<__nv_bfloat16*>(out), rows, I, ldg, ldo);
+      reinterpret_cast<const __nv_bfloat16*>(gate_up), reinterpret_cast<__nv_bfloat16*>(out), rows, I, ldg, ldo, interleaved);
   U2_CHECK_LAUNCH("silu_mul");
   return U2_OK;
 }

@@ -78,7 +78,7 @@ class _CrossAttnW:  # MultiHeadCrossAttention
 
 class U2Engine:
     def __init__(self, geom: Geometry, state_dict: Dict[str, torch.Tensor], device="cuda",
-                 attn_workspace_bytes: int = 6 << 30):
+                 attn_workspace_bytes: int = 6 << 30, decode_impl: str = "tcgen05"):
         if not torch.cuda.is_available():
             raise RuntimeError("U2Engine needs a CUDA device: the hot path has no CPU implementation")
         from . import _lib
@@ -86,6 +86,7 @@ class U2Engine:
         self.g = geom
         self.dev = torch.device(device)
         self.attn_ws = attn_workspace_bytes
+        self.decode_impl = decode_impl  # "tcgen05" (stream-K tensor-core linears) or "gemv" (CUDA-core GEMV)
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
         if geom.attn_type not in ("rma", "rope"):
@@ -192,7 +193,10 @@ class U2Engine:
                 kn=t.f32(l + "self_attn.k_norm.weight") if g.qk_norm else None,
                 wo=t.bf(l + "self_attn.o_proj.weight"),
                 ln2=t.f32(l + "post_attention_layernorm.weight"),
-                wgu=t.cat_bf([l + "mlp.gate_proj.weight", l + "mlp.up_proj.weight"]),
+                # gate/up rows interleaved (gate_j, up_j) = rows (2j, 2j+1): one copy serves the prefill GEMM
+                # (+ interleaved SiLU*mul) and the decode linear's in-epilogue pairing
+                wgu=torch.stack([t.bf(l + "mlp.gate_proj.weight"), t.bf(l + "mlp.up_proj.weight")], dim=1)
+                .view(2 * g.intermediate_size, g.hidden_size).contiguous(),
                 wdown=t.bf(l + "mlp.down_proj.weight")))
         self.final_norm = t.f32("model.norm.weight")
         self.lm_head = self.embed if (g.tie_word_embeddings or not t.has("lm_head.weight")) else t.bf("lm_head.weight")
@@ -454,7 +458,7 @@ class U2Engine:
             ops.linear(ctx.view(B * L, hq * dh), w["wo"], residual=x, out=x)
             ops.rmsnorm(x, w["ln2"], g.rms_norm_eps, out=y)
             ops.linear(y, w["wgu"], out=gu)
-            ops.silu_mul(gu, act)
+            ops.silu_mul(gu, act, interleaved=True)
             ops.linear(act, w["wdown"], residual=x, out=x)
         if cache is not None:
             cache.set_length(L)
@@ -477,9 +481,51 @@ class U2Engine:
             self._dec = dict(
                 x=torch.empty(B, E, device=d, dtype=BF16), qkv=torch.empty(B, (hq + 2 * hkv) * dh, device=d, dtype=BF16),
                 ctx=torch.empty(B, hq * dh, device=d, dtype=BF16), act=torch.empty(B, I, device=d, dtype=BF16),
-                logits=torch.empty(B, g.vocab_size, device=d, dtype=F32), ids=torch.zeros(B, 1, device=d, dtype=torch.int64))
+                logits=torch.empty(B, g.vocab_size, device=d, dtype=F32), ids=torch.zeros(B, 1, device=d, dtype=torch.int64),
+                xg=torch.empty(B, E, device=d, dtype=BF16), ssq_a=torch.zeros(16, device=d, dtype=F32),
+                ssq_b=torch.zeros(16, device=d, dtype=F32))
+            max_n = max(g.vocab_size, 2 * I, (hq + 2 * hkv) * dh, E)
+            tiles = (max_n + 127) // 128
+            self._dec["ws"] = torch.zeros(tiles * 128 * 16, device=d, dtype=F32)
+            self._dec["counters"] = torch.zeros(tiles, device=d, dtype=torch.int32)
             self._dec_key = key
         return self._dec
+
+    def _use_tc_decode(self, B: int) -> bool:
+        g = self.g
+        dims = (g.hidden_size, g.intermediate_size, g.num_attention_heads * g.head_dim)
+        return self.decode_impl == "tcgen05" and B <= 16 and all(k % 64 == 0 for k in dims)
+
+    def decode_step_tc(self, cache: "KVCache") -> torch.Tensor:
+        """Decode step with every linear on the tcgen05 stream-K kernel (u2_dlinear_bf16) and the RMSNorms
+        folded into its epilogues: 6 launches per layer."""
+        g = self.g
+        B = cache.batch
+        hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
+        bufs = self._decode_buffers(B)
+        x, qkv, ctx, act, logits, ids, xg = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids", "xg"))
+        ssq_a, ssq_b, ws, cnt = bufs["ssq_a"], bufs["ssq_b"], bufs["ws"], bufs["counters"]
+        eps = g.rms_norm_eps
+        nqkv = (hq + 2 * hkv) * dh
+        nl = len(self.layers)
+        ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a)
+        for li, w in enumerate(self.layers):
+            ops.dlinear(xg, w["wqkv"], qkv, ws=ws, counters=cnt, ssq_in=ssq_b, eps=eps)
+            ops.rope(qkv, rows=B, ld=nqkv, dh=dh, n_q=hq, n_k=hkv, n_v=hkv, inv_freq=self.inv_freq, q_norm_w=w["qn"],
+                     k_norm_w=w["kn"], eps=eps, pos0=0, pos_div=1, pos_mod=1, pos0_dev=cache.length_dev,
+                     k_cache=cache.k[li], v_cache=cache.v[li], Tmax=cache.max_len, rows_per_batch=1)
+            ops.decode_attention(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
+                                 T_dev=cache.length_plus1_dev, ldq=nqkv, ldo=hq * dh, scale=1.0 / math.sqrt(dh))
+            ops.dlinear(ctx, w["wo"], x, ws=ws, counters=cnt, residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a,
+                        ssq_zero=ssq_b)
+            ops.dlinear(xg, w["wgu"], act, ws=ws, counters=cnt, ssq_in=ssq_a, eps=eps, silu_pair=True)
+            g_next = self.layers[li + 1]["ln1"] if li + 1 < nl else self.final_norm
+            ops.dlinear(act, w["wdown"], x, ws=ws, counters=cnt, residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b,
+                        ssq_zero=ssq_a)
+        ops.dlinear(xg, self.lm_head, logits, ws=ws, counters=cnt, ssq_in=ssq_b, eps=eps)
+        ops.argmax(logits, ids.view(B))
+        cache.advance_device()
+        return logits
 
     def decode_step(self, cache: "KVCache") -> torch.Tensor:
         """Consumes buffers['ids'] [B,1] (the last token of every sequence), appends to the cache at
@@ -487,6 +533,8 @@ class U2Engine:
         next ids back in buffers['ids']. Launch sequence is CUDA-graph capturable."""
         g = self.g
         B = cache.batch
+        if self._use_tc_decode(B):
+            return self.decode_step_tc(cache)
         hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
         bufs = self._decode_buffers(B)
         x, qkv, ctx, act, logits, ids = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids"))

@@ -165,14 +165,14 @@ def softmax(scores: torch.Tensor, out: torch.Tensor, *, n0: int, H: int, S: int,
     return out
 
 
-def silu_mul(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def silu_mul(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None, interleaved: bool = False) -> torch.Tensor:
     _need_cuda(gate_up)
     g2 = _rows2d(gate_up)
     I = g2.shape[1] // 2
     if out is None:
         out = torch.empty(g2.shape[0], I, device=g2.device, dtype=BF16)
     _lib.check(_lib.load().u2_silu_mul_bf16(g2.data_ptr(), out.data_ptr(), g2.shape[0], I, g2.stride(0),
-                                            out.stride(0), _stream()), "u2_silu_mul_bf16")
+                                            out.stride(0), int(interleaved), _stream()), "u2_silu_mul_bf16")
     return out
 
 
@@ -319,3 +319,40 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     _lib.check(_lib.load().u2_argmax_f32(logits.data_ptr(), out.data_ptr(), B, V, logits.stride(0), _stream()),
                "u2_argmax_f32")
     return out
+
+
+def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, ws: torch.Tensor, counters: torch.Tensor,
+            ssq_in=None, eps: float = 1e-6, residual=None, silu_pair: bool = False, gamma_next=None, xg=None,
+            ssq_out=None, ssq_zero=None):
+    """Decode-step linear on tcgen05 (see u2_dlinear_desc): x [B<=16, K] bf16, w [N, K] bf16."""
+    _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
+    d = _lib.DlinearDesc()
+    d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
+    tiles = (d.N + 127) // 128
+    if ws.numel() < tiles * 128 * 16 or counters.numel() < tiles:
+        raise ValueError("dlinear workspace too small")
+    d.ldx, d.ldw, d.ldy = x.stride(0), w.stride(0), out.stride(0)
+    d.ldr = residual.stride(0) if residual is not None else 0
+    d.ldxg = xg.stride(0) if xg is not None else 0
+    d.y_dtype = DT_BF16 if out.dtype == BF16 else DT_F32
+    d.ws, d.counters = ws.data_ptr(), counters.data_ptr()
+    d.ssq_in = _ptr(ssq_in)
+    d.eps = eps
+    d.residual = _ptr(residual)
+    d.silu_pair = int(silu_pair)
+    d.gamma_next = _ptr(gamma_next)
+    d.xg = _ptr(xg)
+    d.ssq_out = _ptr(ssq_out)
+    d.ssq_zero = _ptr(ssq_zero)
+    _lib.check(_lib.load().u2_dlinear_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()),
+               "u2_dlinear_bf16")
+    return out
+
+
+def decode_embed(ids: torch.Tensor, table: torch.Tensor, gamma: torch.Tensor, x: torch.Tensor, xg: torch.Tensor,
+                 ssq: torch.Tensor, ssq_zero: Optional[torch.Tensor]):
+    _need_cuda(ids, table, gamma, x, xg, ssq, ssq_zero)
+    _lib.check(_lib.load().u2_decode_embed_bf16(ids.data_ptr(), table.data_ptr(), gamma.data_ptr(), x.data_ptr(),
+                                                xg.data_ptr(), ssq.data_ptr(), _ptr(ssq_zero), ids.numel(),
+                                                table.shape[1], table.shape[0], _stream()), "u2_decode_embed_bf16")
+    return x
