@@ -220,11 +220,29 @@ typedef struct u2_dlinear_desc {
   void* xg;
   float* ssq_out;
   float* ssq_zero;
+  int32_t pdl; /* != 0: launch with programmatic stream serialization (weight prefetch overlaps the previous kernel) */
 } u2_dlinear_desc;
 U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
 /* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0 (start of a decode step) */
 U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x, void* xg,
                                 float* ssq, float* ssq_zero, int32_t B, int32_t E, int64_t vocab, void* stream);
+
+/* Fused decode-step attention (one launch per layer): per-head RMSNorm (optional) + RoPE of the new q/k,
+ * KV-cache append at position pos (or *pos_dev) and GQA attention over the pos + 1 cached keys.
+ * qkv [B, (Hq + 2 Hkv) * dh] raw projections; caches [B, Hkv, Tmax, dh]; out [B, Hq * dh].
+ * Replaces HF modeling_qwen3.py:263-288 at q_len == 1. */
+typedef struct u2_fused_decode_desc {
+  int32_t B, Hq, Hkv, dh, Tmax, pos;
+  const int32_t* pos_dev;
+  int64_t ldq, ldo;
+  const float* q_norm_w;
+  const float* k_norm_w;
+  float eps;
+  const float* inv_freq;
+  float scale;
+} u2_fused_decode_desc;
+U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_cache, void* v_cache, void* out,
+                                          const u2_fused_decode_desc* desc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ def make(family):
     res = model.load_state_dict(sd16, strict=False)
     assert not res.unexpected_keys and all("rotary" in k or "inv_freq" in k for k in res.missing_keys)
     model = model.to(torch.bfloat16).cuda().eval()
+    model.generation_config.eos_token_id = None  # the oracle's greedy loop has no EOS; tested separately below
     return model, g, {k: v.float() for k, v in sd16.items()}
 
 

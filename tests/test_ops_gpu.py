@@ -322,3 +322,44 @@ def test_decode_embed():
     close(xg, e.float() * gam, 1e-2)
     close(ssq[:3], e.float().pow(2).sum(-1), 1e-4)
     assert ssz[:3].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dh,Hq,Hkv", [(128, 32, 8), (128, 16, 8), (64, 32, 8), (32, 4, 2), (64, 8, 8)])
+@pytest.mark.parametrize("pos", [0, 5, 290, 543])
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
+    """Fused q/k-norm + RoPE + cache append + attention vs the unfused kernels' arithmetic in fp32 torch."""
+    from u2tokenizer_b200 import ops
+    B, Tmax = 3, 600
+    g = gen(dh * 7 + pos + Hq)
+    ld = (Hq + 2 * Hkv) * dh
+    qkv = torch.randn(B, ld, device=DEV, generator=g).bfloat16()
+    kc = torch.randn(B, Hkv, Tmax, dh, device=DEV, generator=g).bfloat16()
+    vc = torch.randn(B, Hkv, Tmax, dh, device=DEV, generator=g).bfloat16()
+    kc0, vc0 = kc.clone(), vc.clone()
+    inv = 1.0 / (1e6 ** (torch.arange(0, dh, 2, device=DEV).float() / dh))
+    qw = 1 + 0.1 * torch.randn(dh, device=DEV, generator=g) if qk_norm else None
+    kw = 1 + 0.1 * torch.randn(dh, device=DEV, generator=g) if qk_norm else None
+    out = torch.empty(B, Hq * dh, device=DEV, dtype=torch.bfloat16)
+    pd = torch.tensor([pos], device=DEV, dtype=torch.int32)
+    ops.decode_attention_fused(qkv, kc, vc, out, B=B, Hq=Hq, Hkv=Hkv, dh=dh, Tmax=Tmax, inv_freq=inv,
+                               scale=1 / math.sqrt(dh), pos_dev=pd, q_norm_w=qw, k_norm_w=kw, eps=1e-6)
+    t = qkv.float().view(B, Hq + 2 * Hkv, dh)
+    q, k, v = t[:, :Hq], t[:, Hq:Hq + Hkv], t[:, Hq + Hkv:]
+    if qk_norm:
+        q = qw * q * torch.rsqrt(q.pow(2).mean(-1, keepdim=True) + 1e-6)
+        k = kw * k * torch.rsqrt(k.pow(2).mean(-1, keepdim=True) + 1e-6)
+    fr = pos * inv
+    emb = torch.cat((fr, fr))
+    rot = lambda u: torch.cat((-u[..., dh // 2:], u[..., :dh // 2]), -1)
+    q = (q * emb.cos() + rot(q) * emb.sin()).bfloat16().float()
+    k = (k * emb.cos() + rot(k) * emb.sin()).bfloat16().float()
+    close(kc[:, :, pos], k, 1e-2)
+    assert torch.equal(vc[:, :, pos].float(), v)
+    keep = torch.ones(Tmax, dtype=torch.bool, device=DEV)
+    keep[pos] = False
+    assert torch.equal(kc[:, :, keep], kc0[:, :, keep]) and torch.equal(vc[:, :, keep], vc0[:, :, keep])
+    K = kc[:, :, :pos + 1].float().repeat_interleave(Hq // Hkv, 1)
+    V = vc[:, :, :pos + 1].float().repeat_interleave(Hq // Hkv, 1)
+    ref = (torch.softmax(q[:, :, None] @ K.transpose(-1, -2) / math.sqrt(dh), -1) @ V).reshape(B, Hq * dh)
+    close(out, ref, 1e-2)

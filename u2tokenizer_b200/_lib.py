@@ -88,6 +88,21 @@ class DlinearDesc(C.Structure):
         ("xg", C.c_void_p),
         ("ssq_out", C.c_void_p),
         ("ssq_zero", C.c_void_p),
+        ("pdl", C.c_int32),
+    ]
+
+
+class FusedDecodeDesc(C.Structure):
+    """Mirror of ``u2_fused_decode_desc``."""
+    _fields_ = [
+        ("B", C.c_int32), ("Hq", C.c_int32), ("Hkv", C.c_int32), ("dh", C.c_int32), ("Tmax", C.c_int32),
+        ("pos", C.c_int32),
+        ("pos_dev", C.c_void_p),
+        ("ldq", C.c_int64), ("ldo", C.c_int64),
+        ("q_norm_w", C.c_void_p), ("k_norm_w", C.c_void_p),
+        ("eps", C.c_float),
+        ("inv_freq", C.c_void_p),
+        ("scale", C.c_float),
     ]
 
 
@@ -115,6 +130,7 @@ SIGNATURES = {
     "u2_gemv_bf16": (C.c_int, [_P, _P, _P, C.POINTER(GemvDesc), _P]),
     "u2_argmax_f32": (C.c_int, [_P, _P, _I, _I, _L, _P]),
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
+    "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
 }
 

@@ -313,3 +313,249 @@ extern "C" U2_API int u2_decode_attention_bf16(const void* q, const void* k_cach
   U2_CHECK_LAUNCH("decode_attention");
   return U2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused decode-step attention: per-head RMSNorm (Qwen3) + RoPE of the new q/k, KV-cache append and the
+// attention of the G = Hq/Hkv query heads of one KV head against the cache - one launch per layer.
+// One CTA per (sequence, KV head): the K/V rows are read once and shared by the G query heads.
+//   QK^T : lane == key (no shuffles; q broadcast from shared memory)
+//   PV   : lane == slice of head_dim (coalesced V rows; probabilities broadcast by shuffle)
+// ------------------------------------------------------------------------------------------------
+namespace u2 {
+
+constexpr int kFaMaxG = 8;
+
+struct FusedDecodeArgs {
+  const __nv_bfloat16* qkv;  // [B, (Hq + 2 Hkv) * dh]
+  long long ldq;
+  __nv_bfloat16* kc;         // [B, Hkv, Tmax, dh]
+  __nv_bfloat16* vc;
+  __nv_bfloat16* out;        // [B, Hq * dh]
+  long long ldo;
+  int Hq, Hkv, Tmax;
+  const int* pos_dev;        // position of the new token (device); T = pos + 1
+  int pos_host;
+  const float* q_norm_w;     // [dh] or null
+  const float* k_norm_w;
+  float eps;
+  const float* inv_freq;     // [dh/2]
+  float scale;
+};
+
+template <int kDh>
+__device__ __forceinline__ void norm_rope_head(const __nv_bfloat16* src, const float* nw, float eps,
+                                               const float* inv_freq, int pos, float mul, float* dst_f32,
+                                               __nv_bfloat16* dst_bf16, int lane) {
+  // one warp; element i pairs with i + dh/2 (rotate-half)
+  constexpr int half = kDh / 2;
+  float rstd = 1.f;
+  if (nw) {
+    float ss = 0.f;
+    for (int e = lane; e < kDh; e += 32) {
+      const float v = __bfloat162float(src[e]);
+      ss += v * v;
+    }
+    ss = wsum(ss);
+    rstd = rsqrtf(ss / kDh + eps);
+  }
+  for (int i = lane; i < half; i += 32) {
+    float x1 = __bfloat162float(src[i]), x2 = __bfloat162float(src[i + half]);
+    if (nw) {
+      x1 = x1 * rstd * nw[i];
+      x2 = x2 * rstd * nw[i + half];
+    }
+    float sn, cs;
+    sincosf((float)pos * inv_freq[i], &sn, &cs);
+    // round to bf16 exactly where the unfused path stores q / k
+    const __nv_bfloat16 o1 = __float2bfloat16(x1 * cs - x2 * sn);
+    const __nv_bfloat16 o2 = __float2bfloat16(x2 * cs + x1 * sn);
+    if (dst_bf16) {
+      dst_bf16[i] = o1;
+      dst_bf16[i + half] = o2;
+    }
+    if (dst_f32) {
+      dst_f32[i] = __bfloat162float(o1) * mul;
+      dst_f32[i + half] = __bfloat162float(o2) * mul;
+    }
+  }
+}
+
+template <int kDh, int kG>
+__global__ void __launch_bounds__(256)
+fused_decode_attention_kernel(const FusedDecodeArgs a) {
+  constexpr int kEpl = kDh / 32;  // head_dim elements per lane in the PV phase
+  constexpr int kPf = 8;          // V rows prefetched per batch (memory-level parallelism in the PV loop)
+  const int hk = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: the QKV projection must have landed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // o_proj may start prefetching its weights
+  const int pos = a.pos_dev ? *a.pos_dev : a.pos_host;
+  const int T = min(pos + 1, a.Tmax);
+  __shared__ __align__(16) float s_q[kG][kDh];
+  __shared__ float s_m[8][kG], s_l[8][kG];
+  __shared__ float s_acc[8][kG][kDh];
+
+  const __nv_bfloat16* row = a.qkv + (long long)b * a.ldq;
+  __nv_bfloat16* kbase = a.kc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
+  __nv_bfloat16* vbase = a.vc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
+  // ---- phase A: new k (norm + rope -> cache), new v (-> cache), G query heads (norm + rope -> smem)
+  for (int job = warp; job < kG + 2; job += 8) {
+    if (job == 0) {
+      norm_rope_head<kDh>(row + (long long)(a.Hq + hk) * kDh, a.k_norm_w, a.eps, a.inv_freq, pos, 1.f, nullptr,
+                          kbase + (long long)pos * kDh, lane);
+    } else if (job == 1) {
+      const __nv_bfloat16* v = row + (long long)(a.Hq + a.Hkv + hk) * kDh;
+      for (int e = lane; e < kDh; e += 32) vbase[(long long)pos * kDh + e] = v[e];
+    } else {
+      const int g = job - 2;
+      norm_rope_head<kDh>(row + (long long)(hk * kG + g) * kDh, a.q_norm_w, a.eps, a.inv_freq, pos, a.scale, s_q[g],
+                          nullptr, lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: online-softmax attention, 32 keys per warp iteration
+  float m[kG], l[kG], acc[kG][kEpl];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    m[g] = -INFINITY;
+    l[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) acc[g][i] = 0.f;
+  }
+  for (int t0 = warp * 32; t0 < T; t0 += 8 * 32) {
+    const int t = t0 + lane;
+    float s[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) s[g] = 0.f;
+    if (t < T) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)t * kDh);
+#pragma unroll
+      for (int c0 = 0; c0 < kDh / 8; c0 += 4) {
+        uint4 u[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u[c] = kr[c0 + c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[c]);
+          float kf[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f2 = __bfloat1622float2(h2[j]);
+            kf[2 * j] = f2.x;
+            kf[2 * j + 1] = f2.y;
+          }
+#pragma unroll
+          for (int g = 0; g < kG; ++g) {
+            const float4 q0 = *reinterpret_cast<const float4*>(&s_q[g][(c0 + c) * 8]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&s_q[g][(c0 + c) * 8 + 4]);
+            s[g] += kf[0] * q0.x + kf[1] * q0.y + kf[2] * q0.z + kf[3] * q0.w + kf[4] * q1.x + kf[5] * q1.y +
+                    kf[6] * q1.z + kf[7] * q1.w;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < kG; ++g) s[g] = -INFINITY;
+    }
+    float p[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const float mx = fmaxf(m[g], wmax(s[g]));
+      const float corr = __expf(m[g] - mx);
+      p[g] = (t < T) ? __expf(s[g] - mx) : 0.f;
+      l[g] = l[g] * corr + wsum(p[g]);
+#pragma unroll
+      for (int i = 0; i < kEpl; ++i) acc[g][i] *= corr;
+      m[g] = mx;
+    }
+    const int nk = min(32, T - t0);
+    for (int j0 = 0; j0 < nk; j0 += kPf) {
+      float vv[kPf][kEpl];
+#pragma unroll
+      for (int jj = 0; jj < kPf; ++jj) {
+        const int tj = min(t0 + j0 + jj, T - 1);  // clamped rows carry probability 0
+        load_epl<kEpl>(vbase + (long long)tj * kDh + lane * kEpl, vv[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < kPf; ++jj) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          const float pj = __shfl_sync(0xffffffffu, p[g], (j0 + jj) & 31);
+#pragma unroll
+          for (int i = 0; i < kEpl; ++i) acc[g][i] += pj * vv[jj][i];
+        }
+      }
+    }
+  }
+  // ---- merge the 8 warps
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    if (lane == 0) {
+      s_m[warp][g] = m[g];
+      s_l[warp][g] = l[g];
+    }
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) s_acc[warp][g][lane * kEpl + i] = acc[g][i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kG * kDh; idx += blockDim.x) {
+    const int g = idx / kDh, e = idx - g * kDh;
+    float gm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) gm = fmaxf(gm, s_m[w][g]);
+    float gl = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (s_m[w][g] != -INFINITY) {
+        const float f = __expf(s_m[w][g] - gm);
+        gl += s_l[w][g] * f;
+        o += s_acc[w][g][e] * f;
+      }
+    }
+    a.out[(long long)b * a.ldo + (long long)(hk * kG + g) * kDh + e] = __float2bfloat16(o / gl);
+  }
+}
+
+template <int kDh>
+static int launch_fused_decode(const FusedDecodeArgs& a, int G, dim3 grid, cudaStream_t st) {
+  switch (G) {
+    case 1: fused_decode_attention_kernel<kDh, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: fused_decode_attention_kernel<kDh, 2><<<grid, 256, 0, st>>>(a); break;
+    case 4: fused_decode_attention_kernel<kDh, 4><<<grid, 256, 0, st>>>(a); break;
+    case 8: fused_decode_attention_kernel<kDh, 8><<<grid, 256, 0, st>>>(a); break;
+    default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: Hq/Hkv = %d (supported 1, 2, 4, 8)", G);
+  }
+  return U2_OK;
+}
+
+}  // namespace u2
+
+extern "C" U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_cache, void* v_cache, void* out,
+                                                     const u2_fused_decode_desc* d, void* stream) {
+  using namespace u2;
+  if (!qkv || !k_cache || !v_cache || !out || !d || !d->inv_freq) return set_error(U2_ERR_ARG, "decode_attention_fused: null pointer");
+  if (d->Hkv <= 0 || d->Hq % d->Hkv || d->Hq / d->Hkv > kFaMaxG)
+    return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: Hq/Hkv must be an integer <= %d", kFaMaxG);
+  if (!d->pos_dev && (d->pos < 0 || d->pos >= d->Tmax)) return set_error(U2_ERR_ARG, "decode_attention_fused: position outside the cache");
+  FusedDecodeArgs a;
+  a.qkv = CBF(qkv); a.ldq = d->ldq;
+  a.kc = BF(k_cache); a.vc = BF(v_cache);
+  a.out = BF(out); a.ldo = d->ldo;
+  a.Hq = d->Hq; a.Hkv = d->Hkv; a.Tmax = d->Tmax;
+  a.pos_dev = d->pos_dev; a.pos_host = d->pos;
+  a.q_norm_w = d->q_norm_w; a.k_norm_w = d->k_norm_w; a.eps = d->eps;
+  a.inv_freq = d->inv_freq; a.scale = d->scale;
+  dim3 grid((unsigned)d->Hkv, (unsigned)d->B);
+  const int G = d->Hq / d->Hkv;
+  int rc;
+  switch (d->dh) {
+    case 32: rc = launch_fused_decode<32>(a, G, grid, ST(stream)); break;
+    case 64: rc = launch_fused_decode<64>(a, G, grid, ST(stream)); break;
+    case 128: rc = launch_fused_decode<128>(a, G, grid, ST(stream)); break;
+    default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: head_dim %d (supported 32/64/128)", d->dh);
+  }
+  if (rc) return rc;
+  U2_CHECK_LAUNCH("decode_attention_fused");
+  return U2_OK;
+}

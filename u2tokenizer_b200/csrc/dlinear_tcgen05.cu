@@ -103,12 +103,35 @@ dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // Programmatic dependent launch: let the next kernel in the stream start its prologue / weight prefetch
+  // as soon as SM resources free up; it still waits (griddepcontrol.wait) for this grid to complete before
+  // touching anything this grid writes.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp_idx == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u_begin; u < u_end; ++u) {
+      // Weights never depend on the previous kernel: fill the whole ring with W tiles first, ...
+      long long npre = u_end - u_begin;
+      if (npre > kDlStages) npre = kDlStages;
+      for (long long i = 0; i < npre; ++i) {
+        const long long u = u_begin + i;
+        const int tile = (int)(u / p.kblocks);
+        const int kb = (int)(u - (long long)tile * p.kblocks);
+        mbar_arrive_expect_tx(&full_bar[i], kDlStageBytes);
+        tma_load_4d(smem_a + i * kDlABytes, &tmap_w, &full_bar[i], kb * kDlK, tile * kDlM, 0, 0);
+      }
+      // ... then wait for the producer of x (previous kernel) and add the activation tiles.
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (long long i = 0; i < npre; ++i) {
+        const long long u = u_begin + i;
+        const int kb = (int)(u % p.kblocks);
+        tma_load_4d(smem_b + i * kDlBBytes, &tmap_x, &full_bar[i], kb * kDlK, 0, 0, 0);
+      }
+      stage = (int)(npre % kDlStages);
+      phase = (npre == kDlStages) ? 1u : 0u;
+      for (long long u = u_begin + npre; u < u_end; ++u) {
         const int tile = (int)(u / p.kblocks);
         const int kb = (int)(u - (long long)tile * p.kblocks);
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -163,6 +186,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   } else if (warp_idx >= 4) {
     const int q = warp_idx - 4;
     const int et = threadIdx.x - 128;  // 0..127: row within the tile
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // workspace / residual / ssq come from earlier kernels
     int acc = 0;
     uint32_t acc_phase = 0;
     long long u = u_begin;
@@ -356,8 +380,18 @@ extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, con
   int grid = num_sms();
   if (grid <= 0) return set_error(U2_ERR_CUDA, "dlinear: cannot query SM count");
   if (units < grid) grid = (int)units;
-  dlinear_tcgen05_kernel<<<grid, kDlThreads, kDlSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tw, tx, p);
-  U2_CHECK_LAUNCH("dlinear");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kDlThreads);
+  cfg.dynamicSmemBytes = kDlSmem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = d->pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dlinear_tcgen05_kernel, tw, tx, p);
+  if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear launch: %s", cudaGetErrorString(e));
   return U2_OK;
 }
 

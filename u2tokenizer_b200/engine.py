@@ -87,6 +87,8 @@ class U2Engine:
         self.dev = torch.device(device)
         self.attn_ws = attn_workspace_bytes
         self.decode_impl = decode_impl  # "tcgen05" (stream-K tensor-core linears) or "gemv" (CUDA-core GEMV)
+        import os
+        self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
         if geom.attn_type not in ("rma", "rope"):
@@ -498,7 +500,7 @@ class U2Engine:
 
     def decode_step_tc(self, cache: "KVCache") -> torch.Tensor:
         """Decode step with every linear on the tcgen05 stream-K kernel (u2_dlinear_bf16) and the RMSNorms
-        folded into its epilogues: 6 launches per layer."""
+        folded into its epilogues: 5 launches per layer."""
         g = self.g
         B = cache.batch
         hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
@@ -510,19 +512,17 @@ class U2Engine:
         nl = len(self.layers)
         ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a)
         for li, w in enumerate(self.layers):
-            ops.dlinear(xg, w["wqkv"], qkv, ws=ws, counters=cnt, ssq_in=ssq_b, eps=eps)
-            ops.rope(qkv, rows=B, ld=nqkv, dh=dh, n_q=hq, n_k=hkv, n_v=hkv, inv_freq=self.inv_freq, q_norm_w=w["qn"],
-                     k_norm_w=w["kn"], eps=eps, pos0=0, pos_div=1, pos_mod=1, pos0_dev=cache.length_dev,
-                     k_cache=cache.k[li], v_cache=cache.v[li], Tmax=cache.max_len, rows_per_batch=1)
-            ops.decode_attention(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
-                                 T_dev=cache.length_plus1_dev, ldq=nqkv, ldo=hq * dh, scale=1.0 / math.sqrt(dh))
-            ops.dlinear(ctx, w["wo"], x, ws=ws, counters=cnt, residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a,
+            ops.dlinear(xg, w["wqkv"], qkv, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_b, eps=eps)
+            ops.decode_attention_fused(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
+                                       inv_freq=self.inv_freq, scale=1.0 / math.sqrt(dh), pos_dev=cache.length_dev,
+                                       q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps)
+            ops.dlinear(ctx, w["wo"], x, ws=ws, counters=cnt, pdl=self.pdl, residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a,
                         ssq_zero=ssq_b)
-            ops.dlinear(xg, w["wgu"], act, ws=ws, counters=cnt, ssq_in=ssq_a, eps=eps, silu_pair=True)
+            ops.dlinear(xg, w["wgu"], act, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_a, eps=eps, silu_pair=True)
             g_next = self.layers[li + 1]["ln1"] if li + 1 < nl else self.final_norm
-            ops.dlinear(act, w["wdown"], x, ws=ws, counters=cnt, residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b,
+            ops.dlinear(act, w["wdown"], x, ws=ws, counters=cnt, pdl=self.pdl, residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b,
                         ssq_zero=ssq_a)
-        ops.dlinear(xg, self.lm_head, logits, ws=ws, counters=cnt, ssq_in=ssq_b, eps=eps)
+        ops.dlinear(xg, self.lm_head, logits, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_b, eps=eps)
         ops.argmax(logits, ids.view(B))
         cache.advance_device()
         return logits

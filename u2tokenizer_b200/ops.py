@@ -323,7 +323,7 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 
 def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, ws: torch.Tensor, counters: torch.Tensor,
             ssq_in=None, eps: float = 1e-6, residual=None, silu_pair: bool = False, gamma_next=None, xg=None,
-            ssq_out=None, ssq_zero=None):
+            ssq_out=None, ssq_zero=None, pdl: bool = True):
     """Decode-step linear on tcgen05 (see u2_dlinear_desc): x [B<=16, K] bf16, w [N, K] bf16."""
     _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
     d = _lib.DlinearDesc()
@@ -344,6 +344,7 @@ def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, ws: torch.Te
     d.xg = _ptr(xg)
     d.ssq_out = _ptr(ssq_out)
     d.ssq_zero = _ptr(ssq_zero)
+    d.pdl = int(pdl)
     _lib.check(_lib.load().u2_dlinear_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()),
                "u2_dlinear_bf16")
     return out
@@ -356,3 +357,21 @@ def decode_embed(ids: torch.Tensor, table: torch.Tensor, gamma: torch.Tensor, x:
                                                 xg.data_ptr(), ssq.data_ptr(), _ptr(ssq_zero), ids.numel(),
                                                 table.shape[1], table.shape[0], _stream()), "u2_decode_embed_bf16")
     return x
+
+
+def decode_attention_fused(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, *,
+                           B: int, Hq: int, Hkv: int, dh: int, Tmax: int, inv_freq: torch.Tensor, scale: float,
+                           pos: int = 0, pos_dev=None, q_norm_w=None, k_norm_w=None, eps: float = 1e-6):
+    """q/k norm + RoPE + KV-cache append + GQA attention for one new token per sequence (one launch)."""
+    _need_cuda(qkv, k_cache, v_cache, out, inv_freq, pos_dev, q_norm_w, k_norm_w)
+    d = _lib.FusedDecodeDesc()
+    d.B, d.Hq, d.Hkv, d.dh, d.Tmax, d.pos = B, Hq, Hkv, dh, Tmax, pos
+    d.pos_dev = _ptr(pos_dev)
+    d.ldq, d.ldo = qkv.stride(0), out.stride(0)
+    d.q_norm_w, d.k_norm_w, d.eps = _ptr(q_norm_w), _ptr(k_norm_w), eps
+    d.inv_freq = inv_freq.data_ptr()
+    d.scale = scale
+    _lib.check(_lib.load().u2_decode_attention_fused_bf16(qkv.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                                                          out.data_ptr(), C.byref(d), _stream()),
+               "u2_decode_attention_fused_bf16")
+    return out
