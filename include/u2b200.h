@@ -221,11 +221,21 @@ typedef struct u2_dlinear_desc {
   float* ssq_out;
   float* ssq_zero;
   int32_t pdl; /* != 0: launch with programmatic stream serialization (weight prefetch overlaps the previous kernel) */
+  void* dbg;   /* optional uint64 [grid][8] globaltimer stamps (tuning aid), normally NULL */
 } u2_dlinear_desc;
 U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
-/* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0 (start of a decode step) */
+/* Up to four DEPENDENT decode linears in one launch (o_proj -> gate|up -> down -> next qkv): software grid
+ * barriers between them (gridbar: uint32[4], monotonically increasing; target = *step_dev * #SMs, step_dev is
+ * the per-step counter u2_decode_embed_bf16 bumps), the weight stream of op i+1 is prefetched while op i
+ * drains. x[i], w[i], y[i], descs[i] as for u2_dlinear_bf16. */
+U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* const* w, void* const* y,
+                                 const u2_dlinear_desc* descs, int32_t n_ops, uint32_t* gridbar,
+                                 const int32_t* step_dev, int32_t pdl, void* stream);
+/* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0; *step_counter += 1
+ * (start of a decode step; step_counter may be NULL) */
 U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x, void* xg,
-                                float* ssq, float* ssq_zero, int32_t B, int32_t E, int64_t vocab, void* stream);
+                                float* ssq, float* ssq_zero, int32_t* step_counter, int32_t B, int32_t E,
+                                int64_t vocab, void* stream);
 
 /* Fused decode-step attention (one launch per layer): per-head RMSNorm (optional) + RoPE of the new q/k,
  * KV-cache append at position pos (or *pos_dev) and GQA attention over the pos + 1 cached keys.

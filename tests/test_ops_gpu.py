@@ -316,7 +316,9 @@ def test_decode_embed():
     x = torch.empty(3, 256, device=DEV, dtype=torch.bfloat16)
     xg = torch.empty_like(x)
     ssq, ssz = torch.zeros(16, device=DEV), torch.ones(16, device=DEV)
-    ops.decode_embed(ids, table, gam, x, xg, ssq, ssz)
+    stepc = torch.zeros(1, device=DEV, dtype=torch.int32)
+    ops.decode_embed(ids, table, gam, x, xg, ssq, ssz, stepc)
+    assert stepc.item() == 1
     e = table[ids.view(-1)]
     assert torch.equal(x, e)
     close(xg, e.float() * gam, 1e-2)
@@ -363,3 +365,63 @@ def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
     V = vc[:, :, :pos + 1].float().repeat_interleave(Hq // Hkv, 1)
     ref = (torch.softmax(q[:, :, None] @ K.transpose(-1, -2) / math.sqrt(dh), -1) @ V).reshape(B, Hq * dh)
     close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("B", [1, 4])
+@pytest.mark.parametrize("E,I,NQ", [(4096, 12288, 6144), (256, 512, 384), (2048, 6144, 4096)])
+def test_dlinear_multi_chain(B, E, I, NQ):
+    """o_proj -> gate|up -> down -> qkv in ONE launch (grid barriers inside) == the same four ops launched
+    one by one == fp32 torch. Run for several 'steps' so the barrier epochs and self-cleaning state cycle."""
+    from u2tokenizer_b200 import ops
+    g = gen(E + I + B)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, device=DEV, generator=g) * sc)
+    wo, wgu, wdn, wqkv = (rnd(E, E, sc=E ** -0.5).bfloat16(), rnd(2 * I, E, sc=E ** -0.5).bfloat16(),
+                          rnd(E, I, sc=I ** -0.5).bfloat16(), rnd(NQ, E, sc=E ** -0.5).bfloat16())
+    ln2, ln1n = 1 + 0.1 * rnd(E), 1 + 0.1 * rnd(E)
+    tiles = (max(2 * I, NQ, E) + 127) // 128
+    eps = 1e-6
+
+    def run(multi, ctx0, x0):
+        ws = torch.zeros(tiles * 128 * 16, device=DEV); cnt = torch.zeros(tiles, device=DEV, dtype=torch.int32)
+        gridbar = torch.zeros(4, device=DEV, dtype=torch.int32); step = torch.zeros(1, device=DEV, dtype=torch.int32)
+        ssq_a, ssq_b = torch.zeros(16, device=DEV), torch.zeros(16, device=DEV)
+        x, xg = x0.clone(), torch.empty(B, E, device=DEV, dtype=torch.bfloat16)
+        act = torch.empty(B, I, device=DEV, dtype=torch.bfloat16)
+        qkv = torch.empty(B, NQ, device=DEV, dtype=torch.bfloat16)
+        outs = []
+        for it in range(3):
+            step += 1
+            ssq_b.fill_(123.0)  # must be reset by op 0
+            ctx = (ctx0 * (1 + 0.1 * it)).bfloat16()
+            common = dict(ws=ws, counters=cnt)
+            chain = [(ctx, wo, x, dict(residual=x, gamma_next=ln2, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, **common)),
+                     (xg, wgu, act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, **common)),
+                     (act, wdn, x, dict(residual=x, gamma_next=ln1n, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **common)),
+                     (xg, wqkv, qkv, dict(ssq_in=ssq_b, eps=eps, **common))]
+            if multi:
+                ops.dlinear_multi(chain, gridbar=gridbar, step_dev=step)
+            else:
+                for (a, w, y, kw) in chain:
+                    ops.dlinear(a, w, y, **kw)
+            torch.cuda.synchronize()
+            outs.append((x.clone(), qkv.clone(), act.clone()))
+        assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+        return outs
+
+    ctx0 = rnd(B, E)
+    x0 = rnd(B, E).bfloat16()
+    single = run(False, ctx0, x0)
+    multi = run(True, ctx0, x0)
+    # fp32 torch reference of the chain (bf16 rounding points as in the kernels)
+    x = x0.float()
+    for it in range(3):
+        ctx = (ctx0 * (1 + 0.1 * it)).bfloat16().float()
+        x = (ctx @ wo.float().t() + x).bfloat16().float()
+        h = (x * ln2).bfloat16().float() @ wgu.float().t() * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+        a = (F.silu(h[:, 0::2].bfloat16().float()) * h[:, 1::2].bfloat16().float()).bfloat16().float()
+        x = (a @ wdn.float().t() + x).bfloat16().float()
+        q = (x * ln1n).bfloat16().float() @ wqkv.float().t() * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+        for outs in (single, multi):
+            close(outs[it][0], x, 2e-2)
+            close(outs[it][1], q, 3e-2)
+            close(outs[it][2], a, 3e-2)

@@ -89,6 +89,7 @@ class DlinearDesc(C.Structure):
         ("ssq_out", C.c_void_p),
         ("ssq_zero", C.c_void_p),
         ("pdl", C.c_int32),
+        ("dbg", C.c_void_p),
     ]
 
 
@@ -131,7 +132,8 @@ SIGNATURES = {
     "u2_argmax_f32": (C.c_int, [_P, _P, _I, _I, _L, _P]),
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
     "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
-    "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P]),
 }
 
 

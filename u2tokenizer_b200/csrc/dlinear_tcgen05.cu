@@ -21,6 +21,8 @@
 // (reference src/model/language_model/u2llama.py:123-126 -> HF GenerationMixin._sample).
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -31,7 +33,10 @@ namespace u2 {
 constexpr int kDlM = 128;      // weight rows per tile (UMMA M)
 constexpr int kDlN = 16;       // padded batch (UMMA N)
 constexpr int kDlK = 64;       // k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int kDlStages = 10;
+#ifndef U2_DL_STAGES
+#define U2_DL_STAGES 10
+#endif
+constexpr int kDlStages = U2_DL_STAGES;  // 10 x 18 KB = 180 KB of weight tiles in flight per SM
 constexpr int kDlABytes = kDlM * kDlK * 2;   // 16 KB
 constexpr int kDlBBytes = kDlN * kDlK * 2;   // 2 KB
 constexpr int kDlStageBytes = kDlABytes + kDlBBytes;
@@ -58,11 +63,36 @@ struct DlinArgs {
   long long ldxg;
   float* ssq_out;              // [16] += sum_n y^2 (of the bf16-rounded y), or null
   float* ssq_zero;             // [16] buffer to reset (the one the *next* producer accumulates into), or null
+  unsigned long long* dbg;     // optional [gridDim][8] globaltimer stamps (tuning aid)
 };
 
+constexpr int kDlMaxOps = 4;
+
+struct DlinMulti {
+  CUtensorMap tw[kDlMaxOps];
+  CUtensorMap tx[kDlMaxOps];
+  DlinArgs op[kDlMaxOps];
+  int n_ops;
+  unsigned int* gridbar;      // [kDlMaxOps] monotonically increasing arrival counters (grid barriers between ops)
+  const int* step_dev;        // barrier target = *step_dev * gridDim.x (step counter bumped once per decode step)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier_wait(const unsigned int* bar, unsigned int target) {
+  while (ld_acquire_u32(bar) < target) __nanosleep(64);
+}
+
+// One launch executes up to four dependent decode linears back to back (o_proj -> gate|up -> down -> next
+// layer's qkv): between two linears all CTAs meet at a software grid barrier, but the TMA producer keeps
+// the smem ring full with the NEXT linear's weight tiles while the current one drains and finalises, so the
+// HBM stream barely pauses at the dependency.
 __global__ void __launch_bounds__(kDlThreads, 1)
-dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                       const DlinArgs p) {
+dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -77,15 +107,13 @@ dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
-
-  // stream-K: equal contiguous range of (tile, k-block) units per CTA
-  const long long units = (long long)p.num_tiles * p.kblocks;
-  const long long u_begin = units * blockIdx.x / gridDim.x;
-  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+  const int n_ops = mp.n_ops;
 
   if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < n_ops; ++i) {
+      tma_prefetch_desc(&mp.tw[i]);
+      tma_prefetch_desc(&mp.tx[i]);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < kDlStages; ++s) {
@@ -103,196 +131,246 @@ dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  // Programmatic dependent launch: let the next kernel in the stream start its prologue / weight prefetch
-  // as soon as SM resources free up; it still waits (griddepcontrol.wait) for this grid to complete before
-  // touching anything this grid writes.
+  // Programmatic dependent launch: the next kernel may start its prologue as soon as SMs free up; it
+  // still waits (griddepcontrol.wait) for this grid to complete before touching anything we write.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp_idx == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // Weights never depend on the previous kernel: fill the whole ring with W tiles first, ...
-      long long npre = u_end - u_begin;
-      if (npre > kDlStages) npre = kDlStages;
-      for (long long i = 0; i < npre; ++i) {
-        const long long u = u_begin + i;
-        const int tile = (int)(u / p.kblocks);
-        const int kb = (int)(u - (long long)tile * p.kblocks);
-        mbar_arrive_expect_tx(&full_bar[i], kDlStageBytes);
-        tma_load_4d(smem_a + i * kDlABytes, &tmap_w, &full_bar[i], kb * kDlK, tile * kDlM, 0, 0);
-      }
-      // ... then wait for the producer of x (previous kernel) and add the activation tiles.
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (long long i = 0; i < npre; ++i) {
-        const long long u = u_begin + i;
-        const int kb = (int)(u % p.kblocks);
-        tma_load_4d(smem_b + i * kDlBBytes, &tmap_x, &full_bar[i], kb * kDlK, 0, 0, 0);
-      }
-      stage = (int)(npre % kDlStages);
-      phase = (npre == kDlStages) ? 1u : 0u;
-      for (long long u = u_begin + npre; u < u_end; ++u) {
-        const int tile = (int)(u / p.kblocks);
-        const int kb = (int)(u - (long long)tile * p.kblocks);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], kDlStageBytes);
-        tma_load_4d(smem_a + stage * kDlABytes, &tmap_w, &full_bar[stage], kb * kDlK, tile * kDlM, 0, 0);
-        tma_load_4d(smem_b + stage * kDlBBytes, &tmap_x, &full_bar[stage], kb * kDlK, 0, 0, 0);
-        if (++stage == kDlStages) {
-          stage = 0;
-          phase ^= 1;
+      unsigned int target = 0;
+      for (int oi = 0; oi < n_ops; ++oi) {
+        const DlinArgs& p = mp.op[oi];
+        const long long units = (long long)p.num_tiles * p.kblocks;
+        const long long u_begin = units * blockIdx.x / gridDim.x;
+        const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+        long long npre = u_end - u_begin;
+        if (npre > kDlStages) npre = kDlStages;
+        // (1) weights never depend on earlier kernels / ops: refill the ring with this op's W tiles as
+        //     soon as the previous op's MMAs release the slots ...
+        int st = stage;
+        uint32_t ph = phase;
+        for (long long i = 0; i < npre; ++i) {
+          const long long u = u_begin + i;
+          const int tile = (int)(u / p.kblocks);
+          const int kb = (int)(u - (long long)tile * p.kblocks);
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[st], kDlStageBytes);
+          tma_load_4d(smem_a + st * kDlABytes, &mp.tw[oi], &full_bar[st], kb * kDlK, tile * kDlM, 0, 0);
+          if (++st == kDlStages) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+        // (2) ... then wait until the activations exist (previous kernel, or previous op of this launch)
+        if (oi == 0) {
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          target = (unsigned int)(*reinterpret_cast<const volatile int*>(mp.step_dev)) * gridDim.x;
+        } else {
+          grid_barrier_wait(mp.gridbar + (oi - 1), target);
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our TMA reads
+        }
+        // (3) add the activation tiles of the prefetched stages
+        for (long long i = 0; i < npre; ++i) {
+          const long long u = u_begin + i;
+          const int kb = (int)(u % p.kblocks);
+          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
+          if (++stage == kDlStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        // (4) steady state
+        for (long long u = u_begin + npre; u < u_end; ++u) {
+          const int tile = (int)(u / p.kblocks);
+          const int kb = (int)(u - (long long)tile * p.kblocks);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kDlStageBytes);
+          tma_load_4d(smem_a + stage * kDlABytes, &mp.tw[oi], &full_bar[stage], kb * kDlK, tile * kDlM, 0, 0);
+          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
+          if (++stage == kDlStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kDlM, kDlN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      long long u = u_begin;
-      while (u < u_end) {
-        const int tile = (int)(u / p.kblocks);
-        long long seg_end = (long long)(tile + 1) * p.kblocks;
-        if (seg_end > u_end) seg_end = u_end;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kDlN;
-        bool first = true;
-        for (; u < seg_end; ++u) {
-          mbar_wait(&full_bar[stage], phase);
+      for (int oi = 0; oi < n_ops; ++oi) {
+        const DlinArgs& p = mp.op[oi];
+        const long long units = (long long)p.num_tiles * p.kblocks;
+        const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+        long long u = units * blockIdx.x / gridDim.x;
+        while (u < u_end) {
+          const int tile = (int)(u / p.kblocks);
+          long long seg_end = (long long)(tile + 1) * p.kblocks;
+          if (seg_end > u_end) seg_end = u_end;
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kDlABytes));
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kDlBBytes));
+          const uint32_t d_tmem = tmem_base + acc * kDlN;
+          bool first = true;
+          for (; u < seg_end; ++u) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kDlABytes));
+            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kDlBBytes));
 #pragma unroll
-          for (int k = 0; k < kDlK / 16; ++k) {
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < kDlK / 16; ++k) {
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kDlStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          first = false;
-          umma_commit(&empty_bar[stage]);
-          if (++stage == kDlStages) {
-            stage = 0;
-            phase ^= 1;
+          umma_commit(&tmem_full_bar[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
           }
-        }
-        umma_commit(&tmem_full_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
         }
       }
     }
   } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
     const int q = warp_idx - 4;
     const int et = threadIdx.x - 128;  // 0..127: row within the tile
     asm volatile("griddepcontrol.wait;" ::: "memory");  // workspace / residual / ssq come from earlier kernels
+    const unsigned int target = (unsigned int)(*reinterpret_cast<const volatile int*>(mp.step_dev)) * gridDim.x;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long u = u_begin;
-    while (u < u_end) {
-      const int tile = (int)(u / p.kblocks);
-      long long seg_end = (long long)(tile + 1) * p.kblocks;
-      if (seg_end > u_end) seg_end = u_end;
-      const int seg_kb = (int)(seg_end - u);
-      u = seg_end;
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const DlinArgs& p = mp.op[oi];
+      const long long units = (long long)p.num_tiles * p.kblocks;
+      const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+      long long u = units * blockIdx.x / gridDim.x;
+      if (oi > 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);  // acquire: previous op fully finalised
+      while (u < u_end) {
+        const int tile = (int)(u / p.kblocks);
+        long long seg_end = (long long)(tile + 1) * p.kblocks;
+        if (seg_end > u_end) seg_end = u_end;
+        const int seg_kb = (int)(seg_end - u);
+        u = seg_end;
 
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      uint32_t v[16];
-      {
-        const uint32_t taddr = tmem_base + acc * kDlN + (static_cast<uint32_t>(q * 32) << 16);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr)
-            : "memory");
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);  // accumulator buffer is free again
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-
-      const int row = tile * kDlM + et;  // output row n of W
-      float* wsr = p.ws + (long long)row * kDlN;
-      const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
-      float f[16];
-#pragma unroll
-      for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
-      bool last = whole;
-      if (!whole) {
-#pragma unroll
-        for (int b = 0; b < 16; ++b)
-          if (b < p.B) atomicAdd(wsr + b, f[b]);
-        __threadfence();
-        // all 128 epilogue threads have published their partial sums -> bump the tile counter once
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          const int old = atomicAdd(p.counters + tile, seg_kb);
-          *s_last = (old + seg_kb == p.kblocks) ? 1 : 0;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[16];
+        {
+          const uint32_t taddr = tmem_base + acc * kDlN + (static_cast<uint32_t>(q * 32) << 16);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr)
+              : "memory");
+          tmem_ld_wait();
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        last = (*s_last != 0);
-        if (last) {
-          __threadfence();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator buffer is free again
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+
+        const int row = tile * kDlM + et;  // output row n of W
+        float* wsr = p.ws + (long long)row * kDlN;
+        const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
+        float f[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
+        bool last = whole;
+        if (!whole) {
 #pragma unroll
           for (int b = 0; b < 16; ++b)
-            if (b < p.B) {
-              f[b] = __ldcg(wsr + b);
-              __stcg(wsr + b, 0.f);  // self-cleaning workspace
-            }
-          if (et == 0) p.counters[tile] = 0;
-        }
-      }
-      if (last) {
-        // ---------------- fused epilogue for the finished tile ----------------
-        if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
-        const bool row_ok = row < p.N;
-        float sq[16];
+            if (b < p.B) atomicAdd(wsr + b, f[b]);
+          // all 128 epilogue threads have issued their partial sums -> one release/acquire RMW on the tile
+          // counter publishes them (cumulativity through the CTA barrier) and tells us whether we are last
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            int old;
+            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.counters + tile), "r"(seg_kb) : "memory");
+            *s_last = (old + seg_kb == p.kblocks) ? 1 : 0;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          last = (*s_last != 0);
+          if (last) {
 #pragma unroll
-        for (int b = 0; b < 16; ++b) {
-          sq[b] = 0.f;
-          if (b < p.B) {
-            float val = f[b];
-            if (p.ssq_in) val *= rsqrtf(p.ssq_in[b] * p.inv_norm_dim + p.eps);
-            if (p.silu_pair) {
-              // rounding points of the unfused path: gate/up are bf16 before the activation
-              const float me = __bfloat162float(__float2bfloat16(val));
-              const float other = __shfl_down_sync(0xffffffffu, me, 1);
-              if (row_ok && (et & 1) == 0) {
-                const float o = me / (1.f + __expf(-me)) * other;
-                reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
+            for (int b = 0; b < 16; ++b)
+              if (b < p.B) {
+                f[b] = __ldcg(wsr + b);
+                __stcg(wsr + b, 0.f);  // self-cleaning workspace
               }
-            } else if (row_ok) {
-              if (p.residual) val += __bfloat162float(p.residual[(long long)b * p.ldr + row]);
-              if (p.y_dtype == U2_DT_BF16) {
-                const __nv_bfloat16 o = __float2bfloat16(val);
-                reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + row] = o;
-                val = __bfloat162float(o);
-              } else {
-                reinterpret_cast<float*>(p.y)[(long long)b * p.ldy + row] = val;
-              }
-              if (p.gamma_next) p.xg[(long long)b * p.ldxg + row] = __float2bfloat16(val * p.gamma_next[row]);
-              sq[b] = val * val;
-            }
+            if (et == 0) p.counters[tile] = 0;
           }
         }
-        if (p.ssq_out) {
+        if (last) {
+          // ---------------- fused epilogue for the finished tile ----------------
+          if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
+          const bool row_ok = row < p.N;
+          float sq[16];
 #pragma unroll
           for (int b = 0; b < 16; ++b) {
+            sq[b] = 0.f;
             if (b < p.B) {
-              float s = sq[b];
+              float val = f[b];
+              if (p.ssq_in) val *= rsqrtf(__ldcg(p.ssq_in + b) * p.inv_norm_dim + p.eps);
+              if (p.silu_pair) {
+                // rounding points of the unfused path: gate/up are bf16 before the activation
+                const float me = __bfloat162float(__float2bfloat16(val));
+                const float other = __shfl_down_sync(0xffffffffu, me, 1);
+                if (row_ok && (et & 1) == 0) {
+                  const float o = me / (1.f + __expf(-me)) * other;
+                  reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
+                }
+              } else if (row_ok) {
+                if (p.residual) {
+                  // may have been written by another CTA earlier in this launch: read through L2
+                  const unsigned short r = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
+                  val += __bfloat162float(__ushort_as_bfloat16(r));
+                }
+                if (p.y_dtype == U2_DT_BF16) {
+                  const __nv_bfloat16 o = __float2bfloat16(val);
+                  reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + row] = o;
+                  val = __bfloat162float(o);
+                } else {
+                  reinterpret_cast<float*>(p.y)[(long long)b * p.ldy + row] = val;
+                }
+                if (p.gamma_next) p.xg[(long long)b * p.ldxg + row] = __float2bfloat16(val * p.gamma_next[row]);
+                sq[b] = val * val;
+              }
+            }
+          }
+          if (p.ssq_out) {
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-              if (lane == 0) atomicAdd(p.ssq_out + b, s);
+            for (int b = 0; b < 16; ++b) {
+              if (b < p.B) {
+                float s = sq[b];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) atomicAdd(p.ssq_out + b, s);
+              }
             }
           }
         }
+      }
+      // this CTA's share of op `oi` is complete (partials published / tiles finalised): arrive at the grid
+      // barrier that gates the next op (release covers the whole epilogue warp-group through the CTA barrier)
+      if (oi + 1 < n_ops) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(mp.gridbar + oi) : "memory");
       }
     }
   }
@@ -310,8 +388,10 @@ dlinear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xg,
-                    float* __restrict__ ssq, float* __restrict__ ssq_zero, int E, long long vocab) {
+                    float* __restrict__ ssq, float* __restrict__ ssq_zero, int* __restrict__ step_counter, int E,
+                    long long vocab) {
   const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0 && step_counter) *step_counter += 1;  // grid-barrier epoch of this decode step
   long long id = ids[b];
   if (id < 0) id = 0;
   if (id >= vocab) id = vocab - 1;
@@ -341,68 +421,103 @@ decode_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __re
 
 using namespace u2;
 
-extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* d, void* stream) {
+static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc* d, DlinArgs* p, CUtensorMap* tw,
+                   CUtensorMap* tx) {
   if (!x || !w || !y || !d || !d->ws || !d->counters) return set_error(U2_ERR_ARG, "dlinear: null pointer");
   if (d->B < 1 || d->B > kDlN) return set_error(U2_ERR_UNSUPPORTED, "dlinear: 1 <= B <= 16 (got %d)", d->B);
   if (d->N <= 0 || d->K <= 0 || (d->K % kDlK)) return set_error(U2_ERR_ARG, "dlinear: K must be a positive multiple of 64");
   if ((d->ldx & 7) || (d->ldw & 7)) return set_error(U2_ERR_ARG, "dlinear: ldx/ldw must be multiples of 8");
   if (d->silu_pair && (d->N & 1)) return set_error(U2_ERR_ARG, "dlinear: silu_pair needs an even N");
   if (d->gamma_next && !d->xg) return set_error(U2_ERR_ARG, "dlinear: gamma_next needs xg");
+  p->B = d->B; p->N = d->N; p->K = d->K;
+  p->num_tiles = (d->N + kDlM - 1) / kDlM;
+  p->kblocks = d->K / kDlK;
+  p->ws = d->ws; p->counters = d->counters;
+  p->ssq_in = d->ssq_in;
+  p->inv_norm_dim = 1.0f / (float)d->K;
+  p->eps = d->eps;
+  p->residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p->ldr = d->ldr;
+  p->y = y; p->ldy = d->ldy; p->y_dtype = d->y_dtype;
+  p->silu_pair = d->silu_pair;
+  p->gamma_next = d->gamma_next;
+  p->xg = reinterpret_cast<__nv_bfloat16*>(d->xg);
+  p->ldxg = d->ldxg;
+  p->ssq_out = d->ssq_out;
+  p->ssq_zero = d->ssq_zero;
+  p->dbg = nullptr;
+  int rc = make_tmap_bf16_4d(tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kDlM);
+  if (rc) return rc;
+  return make_tmap_bf16_4d(tx, x, d->K, d->B, 1, 1, d->ldx, 0, 0, kDlK, kDlN);
+}
+
+static int launch_multi(DlinMulti& mp, int pdl, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dlinear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  DlinArgs p;
-  p.B = d->B; p.N = d->N; p.K = d->K;
-  p.num_tiles = (d->N + kDlM - 1) / kDlM;
-  p.kblocks = d->K / kDlK;
-  p.ws = d->ws; p.counters = d->counters;
-  p.ssq_in = d->ssq_in;
-  p.inv_norm_dim = 1.0f / (float)d->K;
-  p.eps = d->eps;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
-  p.ldr = d->ldr;
-  p.y = y; p.ldy = d->ldy; p.y_dtype = d->y_dtype;
-  p.silu_pair = d->silu_pair;
-  p.gamma_next = d->gamma_next;
-  p.xg = reinterpret_cast<__nv_bfloat16*>(d->xg);
-  p.ldxg = d->ldxg;
-  p.ssq_out = d->ssq_out;
-  p.ssq_zero = d->ssq_zero;
-  CUtensorMap tw, tx;
-  int rc = make_tmap_bf16_4d(&tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kDlM);
-  if (rc) return rc;
-  rc = make_tmap_bf16_4d(&tx, x, d->K, d->B, 1, 1, d->ldx, 0, 0, kDlK, kDlN);
-  if (rc) return rc;
-  const long long units = (long long)p.num_tiles * p.kblocks;
   int grid = num_sms();
   if (grid <= 0) return set_error(U2_ERR_CUDA, "dlinear: cannot query SM count");
-  if (units < grid) grid = (int)units;
+  if (mp.n_ops == 1) {
+    const long long units = (long long)mp.op[0].num_tiles * mp.op[0].kblocks;
+    if (units < grid) grid = (int)units;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kDlThreads);
   cfg.dynamicSmemBytes = kDlSmem;
-  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = d->pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, dlinear_tcgen05_kernel, tw, tx, p);
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dlinear_tcgen05_kernel, mp);
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear launch: %s", cudaGetErrorString(e));
   return U2_OK;
 }
 
+static const int kOneStep = 1;  // never dereferenced on the device for single-op launches
+
+extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* d, void* stream) {
+  static DlinMulti mp;  // large (tensor maps): keep off the stack; single-threaded use per the ABI contract
+  mp.n_ops = 1;
+  int rc = fill_op(x, w, y, d, &mp.op[0], &mp.tw[0], &mp.tx[0]);
+  if (rc) return rc;
+  mp.gridbar = nullptr;
+  // single op: the step counter is only read to form a barrier target that is never used; point it at any
+  // valid device int (the tile counters are zero between launches)
+  mp.step_dev = d->counters;
+  return launch_multi(mp, d->pdl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* const* w, void* const* y,
+                                            const u2_dlinear_desc* descs, int32_t n_ops, uint32_t* gridbar,
+                                            const int32_t* step_dev, int32_t pdl, void* stream) {
+  if (!x || !w || !y || !descs) return set_error(U2_ERR_ARG, "dlinear_multi: null pointer");
+  if (n_ops < 1 || n_ops > kDlMaxOps) return set_error(U2_ERR_ARG, "dlinear_multi: 1 <= n_ops <= %d", kDlMaxOps);
+  if (n_ops > 1 && (!gridbar || !step_dev)) return set_error(U2_ERR_ARG, "dlinear_multi: gridbar / step_dev required");
+  static DlinMulti mp;
+  mp.n_ops = n_ops;
+  for (int i = 0; i < n_ops; ++i) {
+    int rc = fill_op(x[i], w[i], y[i], &descs[i], &mp.op[i], &mp.tw[i], &mp.tx[i]);
+    if (rc) return rc;
+  }
+  mp.gridbar = gridbar;
+  mp.step_dev = step_dev ? step_dev : descs[0].counters;
+  return launch_multi(mp, pdl, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x,
-                                           void* xg, float* ssq, float* ssq_zero, int32_t B, int32_t E,
-                                           int64_t vocab, void* stream) {
+                                           void* xg, float* ssq, float* ssq_zero, int32_t* step_counter, int32_t B,
+                                           int32_t E, int64_t vocab, void* stream) {
   if (!ids || !table || !gamma || !x || !xg || !ssq) return set_error(U2_ERR_ARG, "decode_embed: null pointer");
   if (B < 1 || B > kDlN) return set_error(U2_ERR_UNSUPPORTED, "decode_embed: 1 <= B <= 16");
   decode_embed_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(ids), reinterpret_cast<const __nv_bfloat16*>(table), gamma,
-      reinterpret_cast<__nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(xg), ssq, ssq_zero, E, vocab);
+      reinterpret_cast<__nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(xg), ssq, ssq_zero, step_counter, E, vocab);
   U2_CHECK_LAUNCH("decode_embed");
   return U2_OK;
 }

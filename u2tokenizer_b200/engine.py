@@ -89,6 +89,7 @@ class U2Engine:
         self.decode_impl = decode_impl  # "tcgen05" (stream-K tensor-core linears) or "gemv" (CUDA-core GEMV)
         import os
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
+        self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
         if geom.attn_type not in ("rma", "rope"):
@@ -490,8 +491,17 @@ class U2Engine:
             tiles = (max_n + 127) // 128
             self._dec["ws"] = torch.zeros(tiles * 128 * 16, device=d, dtype=F32)
             self._dec["counters"] = torch.zeros(tiles, device=d, dtype=torch.int32)
+            self._dec["gridbar"] = torch.zeros(4 * g.num_hidden_layers, device=d, dtype=torch.int32)
+            self._dec["step"] = torch.zeros(1, device=d, dtype=torch.int32)
             self._dec_key = key
         return self._dec
+
+    def reset_decode_state(self, B: int):
+        """Grid-barrier epochs / self-cleaning workspaces back to zero (start of a generation, or after an
+        interrupted step)."""
+        bufs = self._decode_buffers(B)
+        for k in ("gridbar", "step", "ws", "counters", "ssq_a", "ssq_b"):
+            bufs[k].zero_()
 
     def _use_tc_decode(self, B: int) -> bool:
         g = self.g
@@ -499,30 +509,39 @@ class U2Engine:
         return self.decode_impl == "tcgen05" and B <= 16 and all(k % 64 == 0 for k in dims)
 
     def decode_step_tc(self, cache: "KVCache") -> torch.Tensor:
-        """Decode step with every linear on the tcgen05 stream-K kernel (u2_dlinear_bf16) and the RMSNorms
-        folded into its epilogues: 5 launches per layer."""
+        """Decode step with every linear on the tcgen05 stream-K kernel and the RMSNorms folded into its
+        epilogues. Launches per step: embed, qkv(0), then per layer [fused attention, one multi-op launch
+        o_proj -> gate|up -> down -> next qkv (or lm_head)], argmax  =  2 launches per layer."""
         g = self.g
         B = cache.batch
         hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
         bufs = self._decode_buffers(B)
         x, qkv, ctx, act, logits, ids, xg = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids", "xg"))
         ssq_a, ssq_b, ws, cnt = bufs["ssq_a"], bufs["ssq_b"], bufs["ws"], bufs["counters"]
+        gridbar, step = bufs["gridbar"], bufs["step"]
         eps = g.rms_norm_eps
-        nqkv = (hq + 2 * hkv) * dh
         nl = len(self.layers)
-        ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a)
+        common = dict(ws=ws, counters=cnt)
+        ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a, step)
+        ops.dlinear(xg, self.layers[0]["wqkv"], qkv, ssq_in=ssq_b, eps=eps, pdl=self.pdl, **common)
         for li, w in enumerate(self.layers):
-            ops.dlinear(xg, w["wqkv"], qkv, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_b, eps=eps)
             ops.decode_attention_fused(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
                                        inv_freq=self.inv_freq, scale=1.0 / math.sqrt(dh), pos_dev=cache.length_dev,
                                        q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps)
-            ops.dlinear(ctx, w["wo"], x, ws=ws, counters=cnt, pdl=self.pdl, residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a,
-                        ssq_zero=ssq_b)
-            ops.dlinear(xg, w["wgu"], act, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_a, eps=eps, silu_pair=True)
-            g_next = self.layers[li + 1]["ln1"] if li + 1 < nl else self.final_norm
-            ops.dlinear(act, w["wdown"], x, ws=ws, counters=cnt, pdl=self.pdl, residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b,
-                        ssq_zero=ssq_a)
-        ops.dlinear(xg, self.lm_head, logits, ws=ws, counters=cnt, pdl=self.pdl, ssq_in=ssq_b, eps=eps)
+            last = li + 1 == nl
+            g_next = self.final_norm if last else self.layers[li + 1]["ln1"]
+            chain = [
+                (ctx, w["wo"], x, dict(residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, **common)),
+                (xg, w["wgu"], act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, **common)),
+                (act, w["wdown"], x, dict(residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **common)),
+                (xg, self.lm_head, logits, dict(ssq_in=ssq_b, eps=eps, **common)) if last else
+                (xg, self.layers[li + 1]["wqkv"], qkv, dict(ssq_in=ssq_b, eps=eps, **common)),
+            ]
+            if self.multi_op:
+                ops.dlinear_multi(chain, gridbar=gridbar[li * 4:(li + 1) * 4], step_dev=step, pdl=self.pdl)
+            else:
+                for (xi, wi, yi, kw) in chain:
+                    ops.dlinear(xi, wi, yi, pdl=self.pdl, **kw)
         ops.argmax(logits, ids.view(B))
         cache.advance_device()
         return logits
@@ -567,6 +586,7 @@ class U2Engine:
         cache = self.new_cache(B, L + max_new_tokens)
         hidden = self.prefill(embeds, cache)
         bufs = self._decode_buffers(B)
+        self.reset_decode_state(B)
         logits0 = self.lm_logits(hidden[:, -1].contiguous())
         out = torch.empty(B, max_new_tokens, device=self.dev, dtype=torch.int64)
         margins = []

@@ -321,10 +321,8 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
-def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, ws: torch.Tensor, counters: torch.Tensor,
-            ssq_in=None, eps: float = 1e-6, residual=None, silu_pair: bool = False, gamma_next=None, xg=None,
-            ssq_out=None, ssq_zero=None, pdl: bool = True):
-    """Decode-step linear on tcgen05 (see u2_dlinear_desc): x [B<=16, K] bf16, w [N, K] bf16."""
+def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=None, silu_pair=False, gamma_next=None,
+                  xg=None, ssq_out=None, ssq_zero=None, pdl=True, dbg=None):
     _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
     d = _lib.DlinearDesc()
     d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
@@ -345,16 +343,37 @@ def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, ws: torch.Te
     d.ssq_out = _ptr(ssq_out)
     d.ssq_zero = _ptr(ssq_zero)
     d.pdl = int(pdl)
+    d.dbg = _ptr(dbg)
+    return d
+
+
+def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw):
+    """Decode-step linear on tcgen05 (see u2_dlinear_desc): x [B<=16, K] bf16, w [N, K] bf16."""
+    d = _dlinear_desc(x, w, out, **kw)
     _lib.check(_lib.load().u2_dlinear_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), C.byref(d), _stream()),
                "u2_dlinear_bf16")
     return out
 
 
+def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pdl: bool = True):
+    """Several dependent decode linears in ONE launch. ops_list: [(x, w, out, kwargs), ...] (max 4)."""
+    n = len(ops_list)
+    descs = (_lib.DlinearDesc * n)()
+    xs, ws_, ys = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+    for i, (x, w, out, kw) in enumerate(ops_list):
+        descs[i] = _dlinear_desc(x, w, out, **kw)
+        xs[i], ws_[i], ys[i] = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    _need_cuda(gridbar, step_dev)
+    _lib.check(_lib.load().u2_dlinear_multi_bf16(xs, ws_, ys, descs, n, gridbar.data_ptr(), step_dev.data_ptr(),
+                                                 int(pdl), _stream()), "u2_dlinear_multi_bf16")
+
+
 def decode_embed(ids: torch.Tensor, table: torch.Tensor, gamma: torch.Tensor, x: torch.Tensor, xg: torch.Tensor,
-                 ssq: torch.Tensor, ssq_zero: Optional[torch.Tensor]):
-    _need_cuda(ids, table, gamma, x, xg, ssq, ssq_zero)
+                 ssq: torch.Tensor, ssq_zero: Optional[torch.Tensor], step_counter: Optional[torch.Tensor] = None):
+    _need_cuda(ids, table, gamma, x, xg, ssq, ssq_zero, step_counter)
     _lib.check(_lib.load().u2_decode_embed_bf16(ids.data_ptr(), table.data_ptr(), gamma.data_ptr(), x.data_ptr(),
-                                                xg.data_ptr(), ssq.data_ptr(), _ptr(ssq_zero), ids.numel(),
+                                                xg.data_ptr(), ssq.data_ptr(), _ptr(ssq_zero), _ptr(step_counter),
+                                                ids.numel(),
                                                 table.shape[1], table.shape[0], _stream()), "u2_decode_embed_bf16")
     return x
 
