@@ -206,6 +206,8 @@ U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V
  *              ssq_out[b] += sum_n y^2 (prepares the next fused norm); ssq_zero[0..15] is reset to 0.
  * ws: fp32 [ceil(N/128)*128*16], counters: int32 [ceil(N/128)], both zero on entry and zero again on exit.
  * Replaces the HF decoder Linears at q_len == 1 (reference u2llama.py:123-126 -> GenerationMixin._sample). */
+#define U2_DLIN_STREAMK128 0
+#define U2_DLIN_TILES64 1
 typedef struct u2_dlinear_desc {
   int32_t B, N, K;
   int64_t ldx, ldw, ldy, ldr, ldxg;
@@ -221,16 +223,30 @@ typedef struct u2_dlinear_desc {
   float* ssq_out;
   float* ssq_zero;
   int32_t pdl; /* != 0: launch with programmatic stream serialization (weight prefetch overlaps the previous kernel) */
-  void* dbg;   /* optional uint64 [grid][8] globaltimer stamps (tuning aid), normally NULL */
+  void* dbg;   /* optional uint64 [grid][4][8] globaltimer stamps (tuning aid), normally NULL */
+  int32_t sched; /* U2_DLIN_STREAMK128 (128-row tiles, stream-K + workspace reduction) or
+                    U2_DLIN_TILES64 (whole 64-row tiles per CTA, no inter-CTA reduction) */
 } u2_dlinear_desc;
 U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
 /* Up to four DEPENDENT decode linears in one launch (o_proj -> gate|up -> down -> next qkv): software grid
  * barriers between them (gridbar: uint32[4], monotonically increasing; target = *step_dev * #SMs, step_dev is
  * the per-step counter u2_decode_embed_bf16 bumps), the weight stream of op i+1 is prefetched while op i
  * drains. x[i], w[i], y[i], descs[i] as for u2_dlinear_bf16. */
+/* Optional L2 look-ahead for u2_dlinear_multi_bf16: lookahead_units = per-CTA number of 16 KB weight tiles
+ * prefetched into L2 beyond the shared-memory ring while an in-launch dependency is pending; w[j] (N[j] x K[j],
+ * row stride ldw[j]) = weights the NEXT launch streams first, units[j] leading tiles per CTA are prefetched when
+ * this launch has issued all of its own loads (covers the launch gap / the attention kernel in between). */
+typedef struct u2_dlinear_next {
+  int32_t lookahead_units;
+  int32_t n;            /* 0..2 */
+  const void* w[2];
+  int32_t N[2], K[2];
+  int64_t ldw[2];
+  int32_t units[2];
+} u2_dlinear_next;
 U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* const* w, void* const* y,
                                  const u2_dlinear_desc* descs, int32_t n_ops, uint32_t* gridbar,
-                                 const int32_t* step_dev, int32_t pdl, void* stream);
+                                 const int32_t* step_dev, int32_t pdl, const u2_dlinear_next* next, void* stream);
 /* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0; *step_counter += 1
  * (start of a decode step; step_counter may be NULL) */
 U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x, void* xg,

@@ -266,9 +266,10 @@ def test_argmax():
     assert ops.argmax(lg)[1].item() == 77
 
 
+@pytest.mark.parametrize("sched", [0, 1])
 @pytest.mark.parametrize("B", [1, 4, 16])
 @pytest.mark.parametrize("N,K", [(4096, 4096), (1000, 320), (6144, 2048), (24576, 4096), (4096, 12288), (151936, 1024)])
-def test_dlinear(B, N, K):
+def test_dlinear(B, N, K, sched):
     """tcgen05 decode linear (swap-AB + stream-K): plain, fused-norm scale, residual + next-norm prep, silu pair."""
     from u2tokenizer_b200 import ops
     g = gen(B * N + K + 1)
@@ -283,7 +284,7 @@ def test_dlinear(B, N, K):
     ssq[:B] = torch.rand(B, device=DEV, generator=g) * K + 1.0
     out = torch.empty(B, N, device=DEV)
     for _ in range(2):  # twice: the workspace must come back clean
-        ops.dlinear(x, w, out, ws=ws, counters=cnt, ssq_in=ssq, eps=1e-6)
+        ops.dlinear(x, w, out, ws=ws, counters=cnt, ssq_in=ssq, eps=1e-6, sched=sched)
         close(out, ref * torch.rsqrt(ssq[:B] / K + 1e-6)[:, None])
     assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
     # (b) residual (in place) + xg + ssq_out + ssq_zero
@@ -293,7 +294,7 @@ def test_dlinear(B, N, K):
     xg = torch.empty(B, N, device=DEV, dtype=torch.bfloat16)
     sso = torch.zeros(16, device=DEV)
     ssz = torch.ones(16, device=DEV)
-    ops.dlinear(x, w, xres, ws=ws, counters=cnt, residual=xres, gamma_next=gam, xg=xg, ssq_out=sso, ssq_zero=ssz)
+    ops.dlinear(x, w, xres, ws=ws, counters=cnt, residual=xres, gamma_next=gam, xg=xg, ssq_out=sso, ssq_zero=ssz, sched=sched)
     want = (ref + res.float())
     close(xres, want)
     close(xg, xres.float() * gam, 1e-2)
@@ -302,7 +303,7 @@ def test_dlinear(B, N, K):
     # (c) silu pair on interleaved rows
     if N % 2 == 0:
         act = torch.empty(B, N // 2, device=DEV, dtype=torch.bfloat16)
-        ops.dlinear(x, w, act, ws=ws, counters=cnt, silu_pair=True)
+        ops.dlinear(x, w, act, ws=ws, counters=cnt, silu_pair=True, sched=sched)
         close(act, F.silu(ref[:, 0::2]) * ref[:, 1::2], 2e-2)
     assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
 
@@ -367,9 +368,10 @@ def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
     close(out, ref, 1e-2)
 
 
+@pytest.mark.parametrize("sched", [0, 1])
 @pytest.mark.parametrize("B", [1, 4])
 @pytest.mark.parametrize("E,I,NQ", [(4096, 12288, 6144), (256, 512, 384), (2048, 6144, 4096)])
-def test_dlinear_multi_chain(B, E, I, NQ):
+def test_dlinear_multi_chain(B, E, I, NQ, sched):
     """o_proj -> gate|up -> down -> qkv in ONE launch (grid barriers inside) == the same four ops launched
     one by one == fp32 torch. Run for several 'steps' so the barrier epochs and self-cleaning state cycle."""
     from u2tokenizer_b200 import ops
@@ -393,7 +395,7 @@ def test_dlinear_multi_chain(B, E, I, NQ):
             step += 1
             ssq_b.fill_(123.0)  # must be reset by op 0
             ctx = (ctx0 * (1 + 0.1 * it)).bfloat16()
-            common = dict(ws=ws, counters=cnt)
+            common = dict(ws=ws, counters=cnt, sched=sched)
             chain = [(ctx, wo, x, dict(residual=x, gamma_next=ln2, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, **common)),
                      (xg, wgu, act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, **common)),
                      (act, wdn, x, dict(residual=x, gamma_next=ln1n, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **common)),

@@ -90,6 +90,7 @@ class DlinearDesc(C.Structure):
         ("ssq_zero", C.c_void_p),
         ("pdl", C.c_int32),
         ("dbg", C.c_void_p),
+        ("sched", C.c_int32),
     ]
 
 
@@ -104,6 +105,17 @@ class FusedDecodeDesc(C.Structure):
         ("eps", C.c_float),
         ("inv_freq", C.c_void_p),
         ("scale", C.c_float),
+    ]
+
+
+class DlinearNext(C.Structure):
+    """Mirror of ``u2_dlinear_next``."""
+    _fields_ = [
+        ("lookahead_units", C.c_int32), ("n", C.c_int32),
+        ("w", C.c_void_p * 2),
+        ("N", C.c_int32 * 2), ("K", C.c_int32 * 2),
+        ("ldw", C.c_int64 * 2),
+        ("units", C.c_int32 * 2),
     ]
 
 
@@ -133,7 +145,7 @@ SIGNATURES = {
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
     "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
-    "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
 }
 
 

@@ -30,24 +30,31 @@
 
 namespace u2 {
 
-constexpr int kDlM = 128;      // weight rows per tile (UMMA M)
 constexpr int kDlN = 16;       // padded batch (UMMA N)
 constexpr int kDlK = 64;       // k-block: 64 bf16 = one 128-byte swizzle row
-#ifndef U2_DL_STAGES
-#define U2_DL_STAGES 10
-#endif
-constexpr int kDlStages = U2_DL_STAGES;  // 10 x 18 KB = 180 KB of weight tiles in flight per SM
-constexpr int kDlABytes = kDlM * kDlK * 2;   // 16 KB
 constexpr int kDlBBytes = kDlN * kDlK * 2;   // 2 KB
-constexpr int kDlStageBytes = kDlABytes + kDlBBytes;
-constexpr int kDlSmem = kDlStages * kDlStageBytes + 1024 + 256;
 constexpr int kDlThreads = 256;
 constexpr int kDlTmemCols = 32;  // 2 accumulator buffers x 16 columns
 
+// Two schedules:
+//   kM = 128, stream-K : (tile, k-block) units cut into equal contiguous ranges per CTA; partial tiles meet in
+//                        the fp32 workspace (atomics + per-tile counter + last-arriver epilogue)
+//   kM =  64, tiles    : every CTA owns whole 64-row tiles (round robin) and streams their full K range: no
+//                        inter-CTA reduction at all, so an op ends ~1 us after its last MMA. 64 rows x K is
+//                        still >= 0.5 MB per tile, and 64..96 active SMs already saturate HBM because one SM
+//                        can ingest far more than 1/148 of the HBM bandwidth through TMA.
+template <int kM>
+struct DlCfg {
+  static constexpr int kABytes = kM * kDlK * 2;                 // 16 KB / 8 KB
+  static constexpr int kStageBytes = kABytes + kDlBBytes;
+  static constexpr int kStages = (kM == 128) ? 10 : 18;         // ~180 KB of weight tiles in flight per SM
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 512;
+};
+
 struct DlinArgs {
   int B, N, K;                 // sequences, output rows of W, reduction length
-  int num_tiles, kblocks;      // ceil(N/128), K/64
-  float* ws;                   // [num_tiles*128][16] fp32, zero between launches
+  int num_tiles, kblocks;      // ceil(N/kM), K/64
+  float* ws;                   // [num_tiles*kM][16] fp32, zero between launches (stream-K schedule only)
   int* counters;               // [num_tiles] int32, zero between launches
   // epilogue
   const float* ssq_in;         // [16] sum of squares of the (un-normalised) input rows, or null
@@ -75,7 +82,24 @@ struct DlinMulti {
   int n_ops;
   unsigned int* gridbar;      // [kDlMaxOps] monotonically increasing arrival counters (grid barriers between ops)
   const int* step_dev;        // barrier target = *step_dev * gridDim.x (step counter bumped once per decode step)
+  unsigned long long* dbg;    // optional [gridDim][kDlMaxOps][8] globaltimer stamps (tuning aid)
+  // L2 look-ahead: weights of the linear(s) the NEXT launch will stream (they only depend on the model):
+  // issued when this launch has nothing left to load, so HBM keeps working through our tail, the launch gap
+  // and the attention kernel in between.
+  CUtensorMap tnext[2];
+  int next_tiles[2], next_kblocks[2], next_units[2];  // next_units: how many leading units per CTA to prefetch
+  int n_next;
+  int lookahead_units;        // per-CTA L2 prefetch depth beyond the smem ring at an in-launch op boundary
 };
+
+#define U2_STAMP(op, i)                                                                  \
+  do {                                                                                   \
+    if (mp.dbg) {                                                                        \
+      unsigned long long t__;                                                            \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                           \
+      mp.dbg[(blockIdx.x * kDlMaxOps + (op)) * 8 + (i)] = t__;                           \
+    }                                                                                    \
+  } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
@@ -83,26 +107,80 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// single-thread poll (relaxed loads: one L2 round trip each), acquire fence once the target is reached
 __device__ __forceinline__ void grid_barrier_wait(const unsigned int* bar, unsigned int target) {
-  while (ld_acquire_u32(bar) < target) __nanosleep(64);
+  unsigned int v;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+  } while (v < target);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// Work enumeration of one CTA inside one op: local unit index j -> (tile, k-block).
+struct OpRange {
+  long long base, n;  // stream-K: global unit range [base, base + n); tiles: n = my_tiles * kblocks
+  int kblocks;
+  bool tiles;
+  __device__ __forceinline__ void unit(long long j, int& tile, int& kb) const {
+    if (tiles) {
+      const long long t = j / kblocks;
+      tile = (int)(blockIdx.x + t * gridDim.x);
+      kb = (int)(j - t * kblocks);
+    } else {
+      const long long u = base + j;
+      tile = (int)(u / kblocks);
+      kb = (int)(u - (long long)tile * kblocks);
+    }
+  }
+  // length of the segment (same tile) that starts at local unit j
+  __device__ __forceinline__ int seg_len(long long j) const {
+    if (tiles) return kblocks;
+    const long long u = base + j;
+    const long long tile = u / kblocks;
+    long long e = (tile + 1) * kblocks;
+    if (e > base + n) e = base + n;
+    return (int)(e - u);
+  }
+};
+
+__device__ __forceinline__ OpRange make_range(const DlinArgs& p, bool tiles) {
+  OpRange r;
+  r.kblocks = p.kblocks;
+  r.tiles = tiles;
+  if (tiles) {
+    const int mine = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    r.base = 0;
+    r.n = (long long)mine * p.kblocks;
+  } else {
+    const long long units = (long long)p.num_tiles * p.kblocks;
+    r.base = units * blockIdx.x / gridDim.x;
+    r.n = units * (blockIdx.x + 1) / gridDim.x - r.base;
+  }
+  return r;
 }
 
 // One launch executes up to four dependent decode linears back to back (o_proj -> gate|up -> down -> next
 // layer's qkv): between two linears all CTAs meet at a software grid barrier, but the TMA producer keeps
 // the smem ring full with the NEXT linear's weight tiles while the current one drains and finalises, so the
 // HBM stream barely pauses at the dependency.
+template <int kM>
 __global__ void __launch_bounds__(kDlThreads, 1)
 dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
+  using Cfg = DlCfg<kM>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kABytes = Cfg::kABytes;
+  constexpr int kStageBytes = Cfg::kStageBytes;
+  constexpr bool kTiles = (kM == 64);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kDlStages * kDlABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDlStages * kDlStageBytes);
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kDlStages;
-  uint64_t* tmem_full_bar = bars + 2 * kDlStages;
-  uint64_t* tmem_empty_bar = bars + 2 * kDlStages + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDlStages + 4);
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   int* s_last = reinterpret_cast<int*>(tmem_base_slot + 1);
 
   const int warp_idx = threadIdx.x / 32;
@@ -116,7 +194,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
     }
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < kDlStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -143,27 +221,34 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       unsigned int target = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
         const DlinArgs& p = mp.op[oi];
-        const long long units = (long long)p.num_tiles * p.kblocks;
-        const long long u_begin = units * blockIdx.x / gridDim.x;
-        const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
-        long long npre = u_end - u_begin;
-        if (npre > kDlStages) npre = kDlStages;
+        const OpRange r = make_range(p, kTiles);
+        long long npre = r.n < kStages ? r.n : kStages;
         // (1) weights never depend on earlier kernels / ops: refill the ring with this op's W tiles as
         //     soon as the previous op's MMAs release the slots ...
         int st = stage;
         uint32_t ph = phase;
-        for (long long i = 0; i < npre; ++i) {
-          const long long u = u_begin + i;
-          const int tile = (int)(u / p.kblocks);
-          const int kb = (int)(u - (long long)tile * p.kblocks);
+        for (long long j = 0; j < npre; ++j) {
+          int tile, kb;
+          r.unit(j, tile, kb);
           mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[st], kDlStageBytes);
-          tma_load_4d(smem_a + st * kDlABytes, &mp.tw[oi], &full_bar[st], kb * kDlK, tile * kDlM, 0, 0);
-          if (++st == kDlStages) {
+          mbar_arrive_expect_tx(&full_bar[st], kStageBytes);
+          tma_load_4d(smem_a + st * kABytes, &mp.tw[oi], &full_bar[st], kb * kDlK, tile * kM, 0, 0);
+          if (++st == kStages) {
             st = 0;
             ph ^= 1;
           }
         }
+        // ... and keep HBM busy while we wait for the dependency: L2 prefetch of the tiles after the ring
+        {
+          long long la_end = npre + mp.lookahead_units;
+          if (la_end > r.n) la_end = r.n;
+          for (long long j = npre; j < la_end; ++j) {
+            int tile, kb;
+            r.unit(j, tile, kb);
+            tma_prefetch_l2_4d(&mp.tw[oi], kb * kDlK, tile * kM, 0, 0);
+          }
+        }
+        U2_STAMP(oi, 0);  // W prefetch issued
         // (2) ... then wait until the activations exist (previous kernel, or previous op of this launch)
         if (oi == 0) {
           asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -172,56 +257,67 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           grid_barrier_wait(mp.gridbar + (oi - 1), target);
           asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our TMA reads
         }
+        U2_STAMP(oi, 1);  // dependency satisfied
         // (3) add the activation tiles of the prefetched stages
-        for (long long i = 0; i < npre; ++i) {
-          const long long u = u_begin + i;
-          const int kb = (int)(u % p.kblocks);
+        for (long long j = 0; j < npre; ++j) {
+          int tile, kb;
+          r.unit(j, tile, kb);
           tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
-          if (++stage == kDlStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // (4) steady state
-        for (long long u = u_begin + npre; u < u_end; ++u) {
-          const int tile = (int)(u / p.kblocks);
-          const int kb = (int)(u - (long long)tile * p.kblocks);
+        for (long long j = npre; j < r.n; ++j) {
+          int tile, kb;
+          r.unit(j, tile, kb);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kDlStageBytes);
-          tma_load_4d(smem_a + stage * kDlABytes, &mp.tw[oi], &full_bar[stage], kb * kDlK, tile * kDlM, 0, 0);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_4d(smem_a + stage * kABytes, &mp.tw[oi], &full_bar[stage], kb * kDlK, tile * kM, 0, 0);
           tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
-          if (++stage == kDlStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
+        }
+      }
+      // nothing left to load for this launch: warm L2 with the next launch's leading weight tiles
+      for (int jn = 0; jn < mp.n_next; ++jn) {
+        DlinArgs q;
+        q.num_tiles = mp.next_tiles[jn];
+        q.kblocks = mp.next_kblocks[jn];
+        const OpRange r = make_range(q, kTiles);
+        long long ne = r.n < mp.next_units[jn] ? r.n : mp.next_units[jn];
+        for (long long j = 0; j < ne; ++j) {
+          int tile, kb;
+          r.unit(j, tile, kb);
+          tma_prefetch_l2_4d(&mp.tnext[jn], kb * kDlK, tile * kM, 0, 0);
         }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kDlM, kDlN);
+      constexpr uint32_t idesc = umma_idesc_bf16(kM, kDlN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
-        const DlinArgs& p = mp.op[oi];
-        const long long units = (long long)p.num_tiles * p.kblocks;
-        const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
-        long long u = units * blockIdx.x / gridDim.x;
-        while (u < u_end) {
-          const int tile = (int)(u / p.kblocks);
-          long long seg_end = (long long)(tile + 1) * p.kblocks;
-          if (seg_end > u_end) seg_end = u_end;
+        const OpRange r = make_range(mp.op[oi], kTiles);
+        long long j = 0;
+        while (j < r.n) {
+          const long long seg_end = j + r.seg_len(j);
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kDlN;
           bool first = true;
-          for (; u < seg_end; ++u) {
+          for (; j < seg_end; ++j) {
             mbar_wait(&full_bar[stage], phase);
+            if (j == 0) U2_STAMP(oi, 2);  // first stage of the op landed
             tc_fence_after();
-            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kDlABytes));
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
             const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kDlBBytes));
 #pragma unroll
             for (int k = 0; k < kDlK / 16; ++k) {
@@ -229,12 +325,13 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
             }
             first = false;
             umma_commit(&empty_bar[stage]);
-            if (++stage == kDlStages) {
+            if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
           umma_commit(&tmem_full_bar[acc]);
+          if (j == r.n) U2_STAMP(oi, 3);  // last MMA of the op committed
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -245,25 +342,32 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
     const int q = warp_idx - 4;
-    const int et = threadIdx.x - 128;  // 0..127: row within the tile
+    const int et = threadIdx.x - 128;  // 0..127
+    // accumulator row held by this thread: M = 128 -> TMEM lane == row; M = 64 -> rows 16q .. 16q+15 live in
+    // lanes 32q .. 32q+15 (the upper 16 lanes of every warp's quarter are unused)
+    const int trow = (kM == 128) ? et : (q * 16 + (lane & 15));
+    const bool tvalid = (kM == 128) ? true : (lane < 16);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // workspace / residual / ssq come from earlier kernels
     const unsigned int target = (unsigned int)(*reinterpret_cast<const volatile int*>(mp.step_dev)) * gridDim.x;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int oi = 0; oi < n_ops; ++oi) {
       const DlinArgs& p = mp.op[oi];
-      const long long units = (long long)p.num_tiles * p.kblocks;
-      const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
-      long long u = units * blockIdx.x / gridDim.x;
-      if (oi > 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);  // acquire: previous op fully finalised
-      while (u < u_end) {
-        const int tile = (int)(u / p.kblocks);
-        long long seg_end = (long long)(tile + 1) * p.kblocks;
-        if (seg_end > u_end) seg_end = u_end;
-        const int seg_kb = (int)(seg_end - u);
-        u = seg_end;
+      const OpRange r = make_range(p, kTiles);
+      if (oi > 0) {
+        // previous op fully finalised everywhere? one poller per CTA, the CTA barrier fans the acquire out
+        if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      long long j = 0;
+      while (j < r.n) {
+        int tile, kb0;
+        r.unit(j, tile, kb0);
+        const int seg_kb = r.seg_len(j);
+        j += seg_kb;
 
         mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (et == 0 && j == r.n) U2_STAMP(oi, 4);  // last accumulator of the op available
         tc_fence_after();
         uint32_t v[16];
         {
@@ -284,7 +388,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           acc_phase ^= 1;
         }
 
-        const int row = tile * kDlM + et;  // output row n of W
+        const int row = tile * kM + trow;  // output row n of W
         float* wsr = p.ws + (long long)row * kDlN;
         const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
         float f[16];
@@ -292,9 +396,11 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
         bool last = whole;
         if (!whole) {
+          if (tvalid) {
 #pragma unroll
-          for (int b = 0; b < 16; ++b)
-            if (b < p.B) atomicAdd(wsr + b, f[b]);
+            for (int b = 0; b < 16; ++b)
+              if (b < p.B) atomicAdd(wsr + b, f[b]);
+          }
           // all 128 epilogue threads have issued their partial sums -> one release/acquire RMW on the tile
           // counter publishes them (cumulativity through the CTA barrier) and tells us whether we are last
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -306,19 +412,21 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
           last = (*s_last != 0);
           if (last) {
+            if (tvalid) {
 #pragma unroll
-            for (int b = 0; b < 16; ++b)
-              if (b < p.B) {
-                f[b] = __ldcg(wsr + b);
-                __stcg(wsr + b, 0.f);  // self-cleaning workspace
-              }
+              for (int b = 0; b < 16; ++b)
+                if (b < p.B) {
+                  f[b] = __ldcg(wsr + b);
+                  __stcg(wsr + b, 0.f);  // self-cleaning workspace
+                }
+            }
             if (et == 0) p.counters[tile] = 0;
           }
         }
         if (last) {
           // ---------------- fused epilogue for the finished tile ----------------
           if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
-          const bool row_ok = row < p.N;
+          const bool row_ok = tvalid && row < p.N;
           float sq[16];
 #pragma unroll
           for (int b = 0; b < 16; ++b) {
@@ -330,15 +438,15 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                 // rounding points of the unfused path: gate/up are bf16 before the activation
                 const float me = __bfloat162float(__float2bfloat16(val));
                 const float other = __shfl_down_sync(0xffffffffu, me, 1);
-                if (row_ok && (et & 1) == 0) {
+                if (row_ok && (trow & 1) == 0) {
                   const float o = me / (1.f + __expf(-me)) * other;
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
                 }
               } else if (row_ok) {
                 if (p.residual) {
                   // may have been written by another CTA earlier in this launch: read through L2
-                  const unsigned short r = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
-                  val += __bfloat162float(__ushort_as_bfloat16(r));
+                  const unsigned short rr = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
+                  val += __bfloat162float(__ushort_as_bfloat16(rr));
                 }
                 if (p.y_dtype == U2_DT_BF16) {
                   const __nv_bfloat16 o = __float2bfloat16(val);
@@ -365,6 +473,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           }
         }
       }
+      if (et == 0) U2_STAMP(oi, 5);  // epilogue of the op done
       // this CTA's share of op `oi` is complete (partials published / tiles finalised): arrive at the grid
       // barrier that gates the next op (release covers the whole epilogue warp-group through the CTA barrier)
       if (oi + 1 < n_ops) {
@@ -422,7 +531,7 @@ decode_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __re
 using namespace u2;
 
 static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc* d, DlinArgs* p, CUtensorMap* tw,
-                   CUtensorMap* tx) {
+                   CUtensorMap* tx, int kM) {
   if (!x || !w || !y || !d || !d->ws || !d->counters) return set_error(U2_ERR_ARG, "dlinear: null pointer");
   if (d->B < 1 || d->B > kDlN) return set_error(U2_ERR_UNSUPPORTED, "dlinear: 1 <= B <= 16 (got %d)", d->B);
   if (d->N <= 0 || d->K <= 0 || (d->K % kDlK)) return set_error(U2_ERR_ARG, "dlinear: K must be a positive multiple of 64");
@@ -430,7 +539,7 @@ static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc*
   if (d->silu_pair && (d->N & 1)) return set_error(U2_ERR_ARG, "dlinear: silu_pair needs an even N");
   if (d->gamma_next && !d->xg) return set_error(U2_ERR_ARG, "dlinear: gamma_next needs xg");
   p->B = d->B; p->N = d->N; p->K = d->K;
-  p->num_tiles = (d->N + kDlM - 1) / kDlM;
+  p->num_tiles = (d->N + kM - 1) / kM;
   p->kblocks = d->K / kDlK;
   p->ws = d->ws; p->counters = d->counters;
   p->ssq_in = d->ssq_in;
@@ -446,68 +555,96 @@ static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc*
   p->ssq_out = d->ssq_out;
   p->ssq_zero = d->ssq_zero;
   p->dbg = nullptr;
-  int rc = make_tmap_bf16_4d(tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kDlM);
+  int rc = make_tmap_bf16_4d(tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kM);
   if (rc) return rc;
   return make_tmap_bf16_4d(tx, x, d->K, d->B, 1, 1, d->ldx, 0, 0, kDlK, kDlN);
 }
 
-static int launch_multi(DlinMulti& mp, int pdl, cudaStream_t stream) {
+template <int kM>
+static int launch_multi_t(DlinMulti& mp, int pdl, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dlinear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmem);
+    cudaError_t e = cudaFuncSetAttribute(dlinear_tcgen05_kernel<kM>, cudaFuncAttributeMaxDynamicSharedMemorySize, DlCfg<kM>::kSmem);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   int grid = num_sms();
   if (grid <= 0) return set_error(U2_ERR_CUDA, "dlinear: cannot query SM count");
   if (mp.n_ops == 1) {
-    const long long units = (long long)mp.op[0].num_tiles * mp.op[0].kblocks;
-    if (units < grid) grid = (int)units;
+    const long long work = (kM == 64) ? mp.op[0].num_tiles : (long long)mp.op[0].num_tiles * mp.op[0].kblocks;
+    if (work < grid) grid = (int)work;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kDlThreads);
-  cfg.dynamicSmemBytes = kDlSmem;
+  cfg.dynamicSmemBytes = DlCfg<kM>::kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, dlinear_tcgen05_kernel, mp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dlinear_tcgen05_kernel<kM>, mp);
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear launch: %s", cudaGetErrorString(e));
   return U2_OK;
 }
 
-static const int kOneStep = 1;  // never dereferenced on the device for single-op launches
+static int launch_multi(DlinMulti& mp, int kM, int pdl, cudaStream_t stream) {
+  return kM == 64 ? launch_multi_t<64>(mp, pdl, stream) : launch_multi_t<128>(mp, pdl, stream);
+}
+
+static inline int tile_m_of(const u2_dlinear_desc* d) { return d->sched == U2_DLIN_TILES64 ? 64 : 128; }
+
 
 extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* d, void* stream) {
   static DlinMulti mp;  // large (tensor maps): keep off the stack; single-threaded use per the ABI contract
   mp.n_ops = 1;
-  int rc = fill_op(x, w, y, d, &mp.op[0], &mp.tw[0], &mp.tx[0]);
+  if (!d) return set_error(U2_ERR_ARG, "dlinear: null descriptor");
+  const int kM = tile_m_of(d);
+  int rc = fill_op(x, w, y, d, &mp.op[0], &mp.tw[0], &mp.tx[0], kM);
   if (rc) return rc;
   mp.gridbar = nullptr;
+  mp.n_next = 0;
+  mp.lookahead_units = 0;
+  mp.dbg = reinterpret_cast<unsigned long long*>(d->dbg);
   // single op: the step counter is only read to form a barrier target that is never used; point it at any
   // valid device int (the tile counters are zero between launches)
   mp.step_dev = d->counters;
-  return launch_multi(mp, d->pdl, reinterpret_cast<cudaStream_t>(stream));
+  return launch_multi(mp, kM, d->pdl, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* const* w, void* const* y,
                                             const u2_dlinear_desc* descs, int32_t n_ops, uint32_t* gridbar,
-                                            const int32_t* step_dev, int32_t pdl, void* stream) {
+                                            const int32_t* step_dev, int32_t pdl, const u2_dlinear_next* next,
+                                            void* stream) {
   if (!x || !w || !y || !descs) return set_error(U2_ERR_ARG, "dlinear_multi: null pointer");
   if (n_ops < 1 || n_ops > kDlMaxOps) return set_error(U2_ERR_ARG, "dlinear_multi: 1 <= n_ops <= %d", kDlMaxOps);
   if (n_ops > 1 && (!gridbar || !step_dev)) return set_error(U2_ERR_ARG, "dlinear_multi: gridbar / step_dev required");
   static DlinMulti mp;
   mp.n_ops = n_ops;
+  const int kM = tile_m_of(&descs[0]);
   for (int i = 0; i < n_ops; ++i) {
-    int rc = fill_op(x[i], w[i], y[i], &descs[i], &mp.op[i], &mp.tw[i], &mp.tx[i]);
+    if (tile_m_of(&descs[i]) != kM) return set_error(U2_ERR_ARG, "dlinear_multi: all ops of a launch must share one schedule");
+    int rc = fill_op(x[i], w[i], y[i], &descs[i], &mp.op[i], &mp.tw[i], &mp.tx[i], kM);
     if (rc) return rc;
   }
   mp.gridbar = gridbar;
+  mp.lookahead_units = next ? next->lookahead_units : 0;
+  mp.n_next = 0;
+  if (next) {
+    for (int j = 0; j < 2 && j < next->n; ++j) {
+      if (!next->w[j] || next->K[j] % kDlK || next->N[j] <= 0) return set_error(U2_ERR_ARG, "dlinear_multi: bad look-ahead weight");
+      int rc = make_tmap_bf16_4d(&mp.tnext[j], next->w[j], next->K[j], next->N[j], 1, 1, next->ldw[j], 0, 0, kDlK, kM);
+      if (rc) return rc;
+      mp.next_tiles[j] = (next->N[j] + kM - 1) / kM;
+      mp.next_kblocks[j] = next->K[j] / kDlK;
+      mp.next_units[j] = next->units[j];
+      mp.n_next = j + 1;
+    }
+  }
+  mp.dbg = reinterpret_cast<unsigned long long*>(descs[0].dbg);
   mp.step_dev = step_dev ? step_dev : descs[0].counters;
-  return launch_multi(mp, pdl, reinterpret_cast<cudaStream_t>(stream));
+  return launch_multi(mp, kM, pdl, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x,

@@ -90,6 +90,9 @@ class U2Engine:
         import os
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
+        self.dl_sched = int(os.environ.get("U2_DL_SCHED", "1"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
+        self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "24"))  # x16 KB per CTA at op boundaries
+        self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
         if geom.attn_type not in ("rma", "rope"):
@@ -521,7 +524,7 @@ class U2Engine:
         gridbar, step = bufs["gridbar"], bufs["step"]
         eps = g.rms_norm_eps
         nl = len(self.layers)
-        common = dict(ws=ws, counters=cnt)
+        common = dict(ws=ws, counters=cnt, sched=self.dl_sched)
         ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a, step)
         ops.dlinear(xg, self.layers[0]["wqkv"], qkv, ssq_in=ssq_b, eps=eps, pdl=self.pdl, **common)
         for li, w in enumerate(self.layers):
@@ -538,7 +541,10 @@ class U2Engine:
                 (xg, self.layers[li + 1]["wqkv"], qkv, dict(ssq_in=ssq_b, eps=eps, **common)),
             ]
             if self.multi_op:
-                ops.dlinear_multi(chain, gridbar=gridbar[li * 4:(li + 1) * 4], step_dev=step, pdl=self.pdl)
+                # L2 look-ahead: next layer's o_proj (all of it) and the head of its gate|up stream
+                nxt = () if last else ((self.layers[li + 1]["wo"], 1 << 20), (self.layers[li + 1]["wgu"], self.l2_next_units))
+                ops.dlinear_multi(chain, gridbar=gridbar[li * 4:(li + 1) * 4], step_dev=step, pdl=self.pdl,
+                                  lookahead_units=self.l2_lookahead_units, next_weights=nxt)
             else:
                 for (xi, wi, yi, kw) in chain:
                     ops.dlinear(xi, wi, yi, pdl=self.pdl, **kw)

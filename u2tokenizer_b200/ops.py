@@ -322,7 +322,7 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 
 
 def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=None, silu_pair=False, gamma_next=None,
-                  xg=None, ssq_out=None, ssq_zero=None, pdl=True, dbg=None):
+                  xg=None, ssq_out=None, ssq_zero=None, pdl=True, dbg=None, sched=1):
     _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
     d = _lib.DlinearDesc()
     d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
@@ -344,6 +344,7 @@ def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=No
     d.ssq_zero = _ptr(ssq_zero)
     d.pdl = int(pdl)
     d.dbg = _ptr(dbg)
+    d.sched = int(sched)  # 0 = stream-K over 128-row tiles, 1 = whole 64-row tiles (no reduction)
     return d
 
 
@@ -355,8 +356,10 @@ def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw):
     return out
 
 
-def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pdl: bool = True):
-    """Several dependent decode linears in ONE launch. ops_list: [(x, w, out, kwargs), ...] (max 4)."""
+def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pdl: bool = True,
+                  lookahead_units: int = 0, next_weights=()):
+    """Several dependent decode linears in ONE launch. ops_list: [(x, w, out, kwargs), ...] (max 4).
+    next_weights: [(w, units_per_cta), ...] (max 2) to warm L2 for the next launch."""
     n = len(ops_list)
     descs = (_lib.DlinearDesc * n)()
     xs, ws_, ys = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
@@ -364,8 +367,14 @@ def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pd
         descs[i] = _dlinear_desc(x, w, out, **kw)
         xs[i], ws_[i], ys[i] = x.data_ptr(), w.data_ptr(), out.data_ptr()
     _need_cuda(gridbar, step_dev)
+    nx = _lib.DlinearNext()
+    nx.lookahead_units = lookahead_units
+    nx.n = len(next_weights)
+    for j, (wn, units) in enumerate(next_weights):
+        _need_cuda(wn)
+        nx.w[j], nx.N[j], nx.K[j], nx.ldw[j], nx.units[j] = wn.data_ptr(), wn.shape[0], wn.shape[1], wn.stride(0), units
     _lib.check(_lib.load().u2_dlinear_multi_bf16(xs, ws_, ys, descs, n, gridbar.data_ptr(), step_dev.data_ptr(),
-                                                 int(pdl), _stream()), "u2_dlinear_multi_bf16")
+                                                 int(pdl), C.byref(nx), _stream()), "u2_dlinear_multi_bf16")
 
 
 def decode_embed(ids: torch.Tensor, table: torch.Tensor, gamma: torch.Tensor, x: torch.Tensor, xg: torch.Tensor,
