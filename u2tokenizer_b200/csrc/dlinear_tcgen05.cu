@@ -116,47 +116,44 @@ __device__ __forceinline__ void grid_barrier_wait(const unsigned int* bar, unsig
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// Work enumeration of one CTA inside one op: local unit index j -> (tile, k-block).
-struct OpRange {
-  long long base, n;  // stream-K: global unit range [base, base + n); tiles: n = my_tiles * kblocks
-  int kblocks;
-  bool tiles;
-  __device__ __forceinline__ void unit(long long j, int& tile, int& kb) const {
-    if (tiles) {
-      const long long t = j / kblocks;
-      tile = (int)(blockIdx.x + t * gridDim.x);
-      kb = (int)(j - t * kblocks);
-    } else {
-      const long long u = base + j;
-      tile = (int)(u / kblocks);
-      kb = (int)(u - (long long)tile * kblocks);
+// Work enumeration of one CTA inside one op: an incremental (tile, k-block) cursor - the producer thread is
+// on the critical path of the weight stream, so no 64-bit divisions inside the loops.
+struct UnitIter {
+  int tile, kb, kblocks, tile_step;
+  int left;  // units remaining, including the current one
+  __device__ __forceinline__ void next() {
+    if (++kb == kblocks) {
+      kb = 0;
+      tile += tile_step;
     }
+    --left;
   }
-  // length of the segment (same tile) that starts at local unit j
-  __device__ __forceinline__ int seg_len(long long j) const {
-    if (tiles) return kblocks;
-    const long long u = base + j;
-    const long long tile = u / kblocks;
-    long long e = (tile + 1) * kblocks;
-    if (e > base + n) e = base + n;
-    return (int)(e - u);
+  // units of the current tile that belong to this CTA, starting at the cursor
+  __device__ __forceinline__ int seg_len() const {
+    const int r = kblocks - kb;
+    return r < left ? r : left;
   }
 };
 
-__device__ __forceinline__ OpRange make_range(const DlinArgs& p, bool tiles) {
-  OpRange r;
-  r.kblocks = p.kblocks;
-  r.tiles = tiles;
+__device__ __forceinline__ UnitIter make_iter(int num_tiles, int kblocks, bool tiles) {
+  UnitIter it;
+  it.kblocks = kblocks;
   if (tiles) {
-    const int mine = (p.num_tiles > (int)blockIdx.x) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    r.base = 0;
-    r.n = (long long)mine * p.kblocks;
+    const int mine = (num_tiles > (int)blockIdx.x) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    it.tile = blockIdx.x;
+    it.kb = 0;
+    it.tile_step = gridDim.x;
+    it.left = mine * kblocks;
   } else {
-    const long long units = (long long)p.num_tiles * p.kblocks;
-    r.base = units * blockIdx.x / gridDim.x;
-    r.n = units * (blockIdx.x + 1) / gridDim.x - r.base;
+    const long long units = (long long)num_tiles * kblocks;
+    const long long base = units * blockIdx.x / gridDim.x;
+    const long long end = units * (blockIdx.x + 1) / gridDim.x;
+    it.tile = (int)(base / kblocks);
+    it.kb = (int)(base - (long long)it.tile * kblocks);
+    it.tile_step = 1;
+    it.left = (int)(end - base);
   }
-  return r;
+  return it;
 }
 
 // One launch executes up to four dependent decode linears back to back (o_proj -> gate|up -> down -> next
@@ -221,18 +218,18 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       unsigned int target = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
         const DlinArgs& p = mp.op[oi];
-        const OpRange r = make_range(p, kTiles);
-        long long npre = r.n < kStages ? r.n : kStages;
+        UnitIter it = make_iter(p.num_tiles, p.kblocks, kTiles);
+        const int npre = it.left < kStages ? it.left : kStages;
         // (1) weights never depend on earlier kernels / ops: refill the ring with this op's W tiles as
         //     soon as the previous op's MMAs release the slots ...
         int st = stage;
         uint32_t ph = phase;
-        for (long long j = 0; j < npre; ++j) {
-          int tile, kb;
-          r.unit(j, tile, kb);
+        UnitIter pre = it;
+        for (int j = 0; j < npre; ++j) {
           mbar_wait(&empty_bar[st], ph ^ 1);
           mbar_arrive_expect_tx(&full_bar[st], kStageBytes);
-          tma_load_4d(smem_a + st * kABytes, &mp.tw[oi], &full_bar[st], kb * kDlK, tile * kM, 0, 0);
+          tma_load_4d(smem_a + st * kABytes, &mp.tw[oi], &full_bar[st], pre.kb * kDlK, pre.tile * kM, 0, 0);
+          pre.next();
           if (++st == kStages) {
             st = 0;
             ph ^= 1;
@@ -240,12 +237,10 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         }
         // ... and keep HBM busy while we wait for the dependency: L2 prefetch of the tiles after the ring
         {
-          long long la_end = npre + mp.lookahead_units;
-          if (la_end > r.n) la_end = r.n;
-          for (long long j = npre; j < la_end; ++j) {
-            int tile, kb;
-            r.unit(j, tile, kb);
-            tma_prefetch_l2_4d(&mp.tw[oi], kb * kDlK, tile * kM, 0, 0);
+          UnitIter la = pre;
+          for (int j = 0; j < mp.lookahead_units && la.left > 0; ++j) {
+            tma_prefetch_l2_4d(&mp.tw[oi], la.kb * kDlK, la.tile * kM, 0, 0);
+            la.next();
           }
         }
         U2_STAMP(oi, 0);  // W prefetch issued
@@ -259,23 +254,21 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         }
         U2_STAMP(oi, 1);  // dependency satisfied
         // (3) add the activation tiles of the prefetched stages
-        for (long long j = 0; j < npre; ++j) {
-          int tile, kb;
-          r.unit(j, tile, kb);
-          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
+        for (int j = 0; j < npre; ++j) {
+          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], it.kb * kDlK, 0, 0, 0);
+          it.next();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // (4) steady state
-        for (long long j = npre; j < r.n; ++j) {
-          int tile, kb;
-          r.unit(j, tile, kb);
+        while (it.left > 0) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_4d(smem_a + stage * kABytes, &mp.tw[oi], &full_bar[stage], kb * kDlK, tile * kM, 0, 0);
-          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], kb * kDlK, 0, 0, 0);
+          tma_load_4d(smem_a + stage * kABytes, &mp.tw[oi], &full_bar[stage], it.kb * kDlK, it.tile * kM, 0, 0);
+          tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], it.kb * kDlK, 0, 0, 0);
+          it.next();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -284,15 +277,10 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       }
       // nothing left to load for this launch: warm L2 with the next launch's leading weight tiles
       for (int jn = 0; jn < mp.n_next; ++jn) {
-        DlinArgs q;
-        q.num_tiles = mp.next_tiles[jn];
-        q.kblocks = mp.next_kblocks[jn];
-        const OpRange r = make_range(q, kTiles);
-        long long ne = r.n < mp.next_units[jn] ? r.n : mp.next_units[jn];
-        for (long long j = 0; j < ne; ++j) {
-          int tile, kb;
-          r.unit(j, tile, kb);
-          tma_prefetch_l2_4d(&mp.tnext[jn], kb * kDlK, tile * kM, 0, 0);
+        UnitIter la = make_iter(mp.next_tiles[jn], mp.next_kblocks[jn], kTiles);
+        for (int j = 0; j < mp.next_units[jn] && la.left > 0; ++j) {
+          tma_prefetch_l2_4d(&mp.tnext[jn], la.kb * kDlK, la.tile * kM, 0, 0);
+          la.next();
         }
       }
     }
@@ -305,17 +293,20 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
-        const OpRange r = make_range(mp.op[oi], kTiles);
-        long long j = 0;
-        while (j < r.n) {
-          const long long seg_end = j + r.seg_len(j);
+        UnitIter it = make_iter(mp.op[oi].num_tiles, mp.op[oi].kblocks, kTiles);
+        bool first_unit = true;
+        while (it.left > 0) {
+          const int seg = it.seg_len();
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kDlN;
           bool first = true;
-          for (; j < seg_end; ++j) {
+          for (int j = 0; j < seg; ++j) {
             mbar_wait(&full_bar[stage], phase);
-            if (j == 0) U2_STAMP(oi, 2);  // first stage of the op landed
+            if (first_unit) {
+              U2_STAMP(oi, 2);  // first stage of the op landed
+              first_unit = false;
+            }
             tc_fence_after();
             const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
             const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kDlBBytes));
@@ -325,13 +316,14 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
             }
             first = false;
             umma_commit(&empty_bar[stage]);
+            it.next();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
           umma_commit(&tmem_full_bar[acc]);
-          if (j == r.n) U2_STAMP(oi, 3);  // last MMA of the op committed
+          if (it.left == 0) U2_STAMP(oi, 3);  // last MMA of the op committed
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -353,21 +345,25 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
     uint32_t acc_phase = 0;
     for (int oi = 0; oi < n_ops; ++oi) {
       const DlinArgs& p = mp.op[oi];
-      const OpRange r = make_range(p, kTiles);
+      UnitIter it = make_iter(p.num_tiles, p.kblocks, kTiles);
       if (oi > 0) {
         // previous op fully finalised everywhere? one poller per CTA, the CTA barrier fans the acquire out
         if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      long long j = 0;
-      while (j < r.n) {
-        int tile, kb0;
-        r.unit(j, tile, kb0);
-        const int seg_kb = r.seg_len(j);
-        j += seg_kb;
+      while (it.left > 0) {
+        const int tile = it.tile;
+        const int seg_kb = it.seg_len();
+        // advance the cursor past this segment (always ends at a tile boundary or at the end of the range)
+        it.left -= seg_kb;
+        it.kb += seg_kb;
+        if (it.kb == it.kblocks) {
+          it.kb = 0;
+          it.tile += it.tile_step;
+        }
 
         mbar_wait(&tmem_full_bar[acc], acc_phase);
-        if (et == 0 && j == r.n) U2_STAMP(oi, 4);  // last accumulator of the op available
+        if (et == 0 && it.left == 0) U2_STAMP(oi, 4);  // last accumulator of the op available
         tc_fence_after();
         uint32_t v[16];
         {
