@@ -204,7 +204,8 @@ U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V
  *   silu_pair: rows (2j, 2j+1) of w are (gate_j, up_j):  y[b, j] = silu(v_2j) * v_2j+1
  *   else:      y[b, n] = v + residual[b, n];  optionally xg[b, n] = bf16(y * gamma_next[n]) and
  *              ssq_out[b] += sum_n y^2 (prepares the next fused norm); ssq_zero[0..15] is reset to 0.
- * ws: fp32 [ceil(N/128)*128*16], counters: int32 [ceil(N/128)], both zero on entry and zero again on exit.
+ * ws: fp32 partial-sum slots (ws_elems floats; u2_dlinear_ws_elems(N, K) gives the size needed by the stream-K
+ * schedule), counters: int32 [ceil(N/64)], zero on entry and zero again on exit.
  * Replaces the HF decoder Linears at q_len == 1 (reference u2llama.py:123-126 -> GenerationMixin._sample). */
 #define U2_DLIN_STREAMK128 0
 #define U2_DLIN_TILES64 1
@@ -224,10 +225,12 @@ typedef struct u2_dlinear_desc {
   float* ssq_zero;
   int32_t pdl; /* != 0: launch with programmatic stream serialization (weight prefetch overlaps the previous kernel) */
   void* dbg;   /* optional uint64 [grid][4][8] globaltimer stamps (tuning aid), normally NULL */
+  int64_t ws_elems; /* capacity of ws in floats */
   int32_t sched; /* U2_DLIN_STREAMK128 (128-row tiles, stream-K + workspace reduction) or
                     U2_DLIN_TILES64 (whole 64-row tiles per CTA, no inter-CTA reduction) */
 } u2_dlinear_desc;
 U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
+U2_API int64_t u2_dlinear_ws_elems(int32_t N, int32_t K); /* fp32 elements of workspace for an N x K linear */
 /* Up to four DEPENDENT decode linears in one launch (o_proj -> gate|up -> down -> next qkv): software grid
  * barriers between them (gridbar: uint32[4], monotonically increasing; target = *step_dev * #SMs, step_dev is
  * the per-step counter u2_decode_embed_bf16 bumps), the weight stream of op i+1 is prefetched while op i

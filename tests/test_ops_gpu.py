@@ -275,9 +275,8 @@ def test_dlinear(B, N, K, sched):
     g = gen(B * N + K + 1)
     x = torch.randn(B, K, device=DEV, generator=g).bfloat16()
     w = (torch.randn(N, K, device=DEV, generator=g) * K ** -0.5).bfloat16()
-    tiles = (N + 127) // 128
-    ws = torch.zeros(tiles * 128 * 16, device=DEV)
-    cnt = torch.zeros(tiles, device=DEV, dtype=torch.int32)
+    ws = torch.zeros(max(ops.dlinear_ws_elems(N, K), 1), device=DEV)
+    cnt = torch.zeros((N + 63) // 64, device=DEV, dtype=torch.int32)
     ref = x.float() @ w.float().t()
     # (a) fp32 output, fused RMSNorm scale
     ssq = torch.zeros(16, device=DEV)
@@ -286,7 +285,7 @@ def test_dlinear(B, N, K, sched):
     for _ in range(2):  # twice: the workspace must come back clean
         ops.dlinear(x, w, out, ws=ws, counters=cnt, ssq_in=ssq, eps=1e-6, sched=sched)
         close(out, ref * torch.rsqrt(ssq[:B] / K + 1e-6)[:, None])
-    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+    assert cnt.abs().max().item() == 0
     # (b) residual (in place) + xg + ssq_out + ssq_zero
     res = torch.randn(B, N, device=DEV, generator=g).bfloat16()
     xres = res.clone()
@@ -305,7 +304,7 @@ def test_dlinear(B, N, K, sched):
         act = torch.empty(B, N // 2, device=DEV, dtype=torch.bfloat16)
         ops.dlinear(x, w, act, ws=ws, counters=cnt, silu_pair=True, sched=sched)
         close(act, F.silu(ref[:, 0::2]) * ref[:, 1::2], 2e-2)
-    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+    assert cnt.abs().max().item() == 0
 
 
 def test_decode_embed():
@@ -384,7 +383,8 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched):
     eps = 1e-6
 
     def run(multi, ctx0, x0):
-        ws = torch.zeros(tiles * 128 * 16, device=DEV); cnt = torch.zeros(tiles, device=DEV, dtype=torch.int32)
+        ws = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=DEV)
+        cnt = torch.zeros(tiles * 2, device=DEV, dtype=torch.int32)
         gridbar = torch.zeros(4, device=DEV, dtype=torch.int32); step = torch.zeros(1, device=DEV, dtype=torch.int32)
         ssq_a, ssq_b = torch.zeros(16, device=DEV), torch.zeros(16, device=DEV)
         x, xg = x0.clone(), torch.empty(B, E, device=DEV, dtype=torch.bfloat16)
@@ -407,7 +407,7 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched):
                     ops.dlinear(a, w, y, **kw)
             torch.cuda.synchronize()
             outs.append((x.clone(), qkv.clone(), act.clone()))
-        assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0
+        assert cnt.abs().max().item() == 0
         return outs
 
     ctx0 = rnd(B, E)

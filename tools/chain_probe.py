@@ -10,14 +10,14 @@ W = [dict(wo=rnd(E, E, sc=E ** -0.5).bfloat16(), wgu=rnd(2 * I, E, sc=E ** -0.5)
           wqkv=rnd(NQ, E, sc=E ** -0.5).bfloat16()) for _ in range(nlay)]
 ln = 1 + 0.1 * rnd(E)
 tiles = (2 * I + 127) // 128
-ws = torch.zeros(tiles * 128 * 16, device=dev); cnt = torch.zeros(tiles, device=dev, dtype=torch.int32)
+ws = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=dev); cnt = torch.zeros(tiles * 2, device=dev, dtype=torch.int32)
 gridbar = torch.zeros(4 * nlay, device=dev, dtype=torch.int32); step = torch.zeros(1, device=dev, dtype=torch.int32)
 ssq_a, ssq_b = torch.zeros(16, device=dev), torch.zeros(16, device=dev)
 x = rnd(B, E).bfloat16(); xg = torch.empty_like(x); ctx = rnd(B, E).bfloat16()
 act = torch.empty(B, I, device=dev, dtype=torch.bfloat16); qkv = torch.empty(B, NQ, device=dev, dtype=torch.bfloat16)
 dbg = torch.zeros(148 * 4 * 8, device=dev, dtype=torch.int64)
 def chain(l, d=None):
-    w = W[l]; c = dict(ws=ws, counters=cnt, sched=int(os.environ.get("U2_DL_SCHED", "1")))
+    w = W[l]; c = dict(ws=ws, counters=cnt, sched=int(os.environ.get("U2_DL_SCHED", "0")))
     return [(ctx, w["wo"], x, dict(residual=x, gamma_next=ln, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, dbg=d, **c)),
             (xg, w["wgu"], act, dict(ssq_in=ssq_a, silu_pair=True, **c)),
             (act, w["wdn"], x, dict(residual=x, gamma_next=ln, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **c)),

@@ -90,6 +90,7 @@ class DlinearDesc(C.Structure):
         ("ssq_zero", C.c_void_p),
         ("pdl", C.c_int32),
         ("dbg", C.c_void_p),
+        ("ws_elems", C.c_int64),
         ("sched", C.c_int32),
     ]
 
@@ -145,6 +146,7 @@ SIGNATURES = {
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
     "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "u2_dlinear_ws_elems": (C.c_int64, [_I, _I]),
     "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
 }
 

@@ -54,8 +54,9 @@ struct DlCfg {
 struct DlinArgs {
   int B, N, K;                 // sequences, output rows of W, reduction length
   int num_tiles, kblocks;      // ceil(N/kM), K/64
-  float* ws;                   // [num_tiles*kM][16] fp32, zero between launches (stream-K schedule only)
-  int* counters;               // [num_tiles] int32, zero between launches
+  float* ws;                   // [num_tiles][max_slots][kM][16] fp32 partial-sum slots (stream-K schedule only)
+  int max_slots;
+  int* counters;               // [num_tiles] int32 arrival counters, zero between launches
   // epilogue
   const float* ssq_in;         // [16] sum of squares of the (un-normalised) input rows, or null
   float inv_norm_dim, eps;     // rstd = rsqrt(ssq_in[b] * inv_norm_dim + eps)
@@ -385,38 +386,56 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         }
 
         const int row = tile * kM + trow;  // output row n of W
-        float* wsr = p.ws + (long long)row * kDlN;
         const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
         float f[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
         bool last = whole;
         if (!whole) {
-          if (tvalid) {
-#pragma unroll
-            for (int b = 0; b < 16; ++b)
-              if (b < p.B) atomicAdd(wsr + b, f[b]);
-          }
-          // all 128 epilogue threads have issued their partial sums -> one release/acquire RMW on the tile
-          // counter publishes them (cumulativity through the CTA barrier) and tells us whether we are last
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et == 0) {
-            int old;
-            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.counters + tile), "r"(seg_kb) : "memory");
-            *s_last = (old + seg_kb == p.kblocks) ? 1 : 0;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          last = (*s_last != 0);
-          if (last) {
+          // Split tile (stream-K only). The CTA whose range contains k-block 0 of the tile finalises it - that
+          // segment is the LAST one of its range - while the CTAs holding the later k-blocks meet the tile as
+          // their FIRST segment: they drop their partial sums into a private slot (plain vector stores, nothing
+          // to wait for), bump the tile counter with a release and move on. By the time the finaliser gets
+          // there the slots are normally complete: one poll + one round of loads instead of an atomic/fence/
+          // counter/read-back chain.
+          const long long units = (long long)p.num_tiles * p.kblocks;
+          const long long u0 = (long long)tile * p.kblocks;
+          const int gf = (int)(((u0 + 1) * gridDim.x + units - 1) / units) - 1;
+          const int gl = (int)(((u0 + p.kblocks) * gridDim.x + units - 1) / units) - 1;
+          const int nvec = (p.B + 3) >> 2;
+          if (gf != (int)blockIdx.x) {
+            const int slot = (int)blockIdx.x - gf - 1;
+            float4* dst = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots + slot) * kM + trow) * kDlN);
             if (tvalid) {
 #pragma unroll
-              for (int b = 0; b < 16; ++b)
-                if (b < p.B) {
-                  f[b] = __ldcg(wsr + b);
-                  __stcg(wsr + b, 0.f);  // self-cleaning workspace
-                }
+              for (int c = 0; c < 4; ++c)
+                if (c < nvec) __stcg(dst + c, make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]));
             }
-            if (et == 0) p.counters[tile] = 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
+          } else {
+            const int n_contrib = gl - gf;
+            if (et == 0) {
+              int seen;
+              do {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+              } while (seen < n_contrib);
+              asm volatile("fence.acq_rel.gpu;" ::: "memory");
+              p.counters[tile] = 0;  // every contributor has arrived: safe to reset for the next launch
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tvalid) {
+              for (int sl = 0; sl < n_contrib; ++sl) {
+                const float4* src = reinterpret_cast<const float4*>(p.ws + (((long long)tile * p.max_slots + sl) * kM + trow) * kDlN);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (c < nvec) {
+                    const float4 t = __ldcg(src + c);
+                    f[4 * c] += t.x; f[4 * c + 1] += t.y; f[4 * c + 2] += t.z; f[4 * c + 3] += t.w;
+                  }
+              }
+            }
+            last = true;
           }
         }
         if (last) {
@@ -473,7 +492,6 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       // this CTA's share of op `oi` is complete (partials published / tiles finalised): arrive at the grid
       // barrier that gates the next op (release covers the whole epilogue warp-group through the CTA barrier)
       if (oi + 1 < n_ops) {
-        __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(mp.gridbar + oi) : "memory");
       }
@@ -538,6 +556,20 @@ static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc*
   p->num_tiles = (d->N + kM - 1) / kM;
   p->kblocks = d->K / kDlK;
   p->ws = d->ws; p->counters = d->counters;
+  p->max_slots = 1;
+  if (kM == 128) {
+    // contributors per split tile <= ceil(kblocks / shortest CTA range) + 1
+    const long long units = (long long)p->num_tiles * p->kblocks;
+    int g = num_sms();
+    if (g <= 0) g = 148;
+    long long rmin = units / g;
+    if (rmin < 1) rmin = 1;
+    const long long cmax = (p->kblocks + rmin - 1) / rmin + 1;
+    p->max_slots = (int)cmax;
+    if ((long long)p->num_tiles * cmax * kM * kDlN > d->ws_elems)
+      return set_error(U2_ERR_ARG, "dlinear: workspace too small (%lld fp32 needed for N=%d K=%d)",
+                       (long long)p->num_tiles * cmax * kM * kDlN, d->N, d->K);
+  }
   p->ssq_in = d->ssq_in;
   p->inv_norm_dim = 1.0f / (float)d->K;
   p->eps = d->eps;
@@ -591,6 +623,17 @@ static int launch_multi(DlinMulti& mp, int kM, int pdl, cudaStream_t stream) {
 
 static inline int tile_m_of(const u2_dlinear_desc* d) { return d->sched == U2_DLIN_TILES64 ? 64 : 128; }
 
+
+extern "C" U2_API int64_t u2_dlinear_ws_elems(int32_t N, int32_t K) {
+  if (N <= 0 || K <= 0) return 0;
+  const long long tiles = (N + 127) / 128, kblocks = (K + kDlK - 1) / kDlK;
+  int g = num_sms();
+  if (g <= 0) g = 148;
+  long long rmin = tiles * kblocks / g;
+  if (rmin < 1) rmin = 1;
+  const long long cmax = (kblocks + rmin - 1) / rmin + 1;
+  return tiles * cmax * 128 * kDlN;
+}
 
 extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* d, void* stream) {
   static DlinMulti mp;  // large (tensor maps): keep off the stack; single-threaded use per the ABI contract

@@ -90,7 +90,7 @@ class U2Engine:
         import os
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
-        self.dl_sched = int(os.environ.get("U2_DL_SCHED", "1"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
+        self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
         self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "24"))  # x16 KB per CTA at op boundaries
         self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
@@ -491,9 +491,9 @@ class U2Engine:
                 xg=torch.empty(B, E, device=d, dtype=BF16), ssq_a=torch.zeros(16, device=d, dtype=F32),
                 ssq_b=torch.zeros(16, device=d, dtype=F32))
             max_n = max(g.vocab_size, 2 * I, (hq + 2 * hkv) * dh, E)
-            tiles = (max_n + 127) // 128
-            self._dec["ws"] = torch.zeros(tiles * 128 * 16, device=d, dtype=F32)
-            self._dec["counters"] = torch.zeros(tiles, device=d, dtype=torch.int32)
+            shapes = [((hq + 2 * hkv) * dh, E), (E, hq * dh), (2 * I, E), (E, I), (g.vocab_size, E)]
+            self._dec["ws"] = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in shapes), device=d, dtype=F32)
+            self._dec["counters"] = torch.zeros((max_n + 63) // 64, device=d, dtype=torch.int32)
             self._dec["gridbar"] = torch.zeros(4 * g.num_hidden_layers, device=d, dtype=torch.int32)
             self._dec["step"] = torch.zeros(1, device=d, dtype=torch.int32)
             self._dec_key = key

@@ -326,9 +326,9 @@ def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=No
     _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
     d = _lib.DlinearDesc()
     d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
-    tiles = (d.N + 127) // 128
-    if ws.numel() < tiles * 128 * 16 or counters.numel() < tiles:
-        raise ValueError("dlinear workspace too small")
+    if counters.numel() < (d.N + 63) // 64:
+        raise ValueError("dlinear counters too small")
+    d.ws_elems = ws.numel()
     d.ldx, d.ldw, d.ldy = x.stride(0), w.stride(0), out.stride(0)
     d.ldr = residual.stride(0) if residual is not None else 0
     d.ldxg = xg.stride(0) if xg is not None else 0
@@ -346,6 +346,11 @@ def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=No
     d.dbg = _ptr(dbg)
     d.sched = int(sched)  # 0 = stream-K over 128-row tiles, 1 = whole 64-row tiles (no reduction)
     return d
+
+
+def dlinear_ws_elems(N: int, K: int) -> int:
+    """fp32 workspace elements the stream-K schedule needs for an N x K decode linear (needs a CUDA device)."""
+    return int(_lib.load().u2_dlinear_ws_elems(N, K))
 
 
 def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw):
