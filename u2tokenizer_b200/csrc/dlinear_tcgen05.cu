@@ -146,13 +146,21 @@ __device__ __forceinline__ UnitIter make_iter(int num_tiles, int kblocks, bool t
     it.tile_step = gridDim.x;
     it.left = mine * kblocks;
   } else {
+    // stream-K over G = min(#CTAs, #units) CTAs, so that every participating CTA owns >= 1 unit
     const long long units = (long long)num_tiles * kblocks;
-    const long long base = units * blockIdx.x / gridDim.x;
-    const long long end = units * (blockIdx.x + 1) / gridDim.x;
-    it.tile = (int)(base / kblocks);
-    it.kb = (int)(base - (long long)it.tile * kblocks);
+    const long long G = units < (long long)gridDim.x ? units : (long long)gridDim.x;
     it.tile_step = 1;
-    it.left = (int)(end - base);
+    if ((long long)blockIdx.x >= G) {
+      it.tile = 0;
+      it.kb = 0;
+      it.left = 0;
+    } else {
+      const long long base = units * blockIdx.x / G;
+      const long long end = units * (blockIdx.x + 1) / G;
+      it.tile = (int)(base / kblocks);
+      it.kb = (int)(base - (long long)it.tile * kblocks);
+      it.left = (int)(end - base);
+    }
   }
   return it;
 }
@@ -399,9 +407,10 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           // there the slots are normally complete: one poll + one round of loads instead of an atomic/fence/
           // counter/read-back chain.
           const long long units = (long long)p.num_tiles * p.kblocks;
+          const long long G = units < (long long)gridDim.x ? units : (long long)gridDim.x;
           const long long u0 = (long long)tile * p.kblocks;
-          const int gf = (int)(((u0 + 1) * gridDim.x + units - 1) / units) - 1;
-          const int gl = (int)(((u0 + p.kblocks) * gridDim.x + units - 1) / units) - 1;
+          const int gf = (int)(((u0 + 1) * G + units - 1) / units) - 1;
+          const int gl = (int)(((u0 + p.kblocks) * G + units - 1) / units) - 1;
           const int nvec = (p.B + 3) >> 2;
           if (gf != (int)blockIdx.x) {
             const int slot = (int)blockIdx.x - gf - 1;
