@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     f"-I{REPO / 'include'}", f"-I{CSRC}",
-]
+] + [f"-D{d}" for d in os.environ.get("U2_NVCC_DEFINES", "").split() if d]
 
 
 def _nvcc() -> str:

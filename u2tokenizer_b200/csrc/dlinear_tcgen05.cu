@@ -47,7 +47,10 @@ template <int kM>
 struct DlCfg {
   static constexpr int kABytes = kM * kDlK * 2;                 // 16 KB / 8 KB
   static constexpr int kStageBytes = kABytes + kDlBBytes;
-  static constexpr int kStages = (kM == 128) ? 10 : 18;         // ~180 KB of weight tiles in flight per SM
+#ifndef U2_DL_STAGES128
+#define U2_DL_STAGES128 10
+#endif
+  static constexpr int kStages = (kM == 128) ? U2_DL_STAGES128 : 18;  // <= ~180 KB of weight tiles in flight per SM
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 512;
 };
 

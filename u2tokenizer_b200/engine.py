@@ -91,7 +91,7 @@ class U2Engine:
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
-        self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "24"))  # x16 KB per CTA at op boundaries
+        self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "0"))  # x16 KB per CTA at op boundaries
         self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
@@ -542,7 +542,8 @@ class U2Engine:
             ]
             if self.multi_op:
                 # L2 look-ahead: next layer's o_proj (all of it) and the head of its gate|up stream
-                nxt = () if last else ((self.layers[li + 1]["wo"], 1 << 20), (self.layers[li + 1]["wgu"], self.l2_next_units))
+                nxt = () if (last or self.l2_next_units < 0) else (
+                    (self.layers[li + 1]["wo"], 1 << 20), (self.layers[li + 1]["wgu"], self.l2_next_units))
                 ops.dlinear_multi(chain, gridbar=gridbar[li * 4:(li + 1) * 4], step_dev=step, pdl=self.pdl,
                                   lookahead_units=self.l2_lookahead_units, next_weights=nxt)
             else:
