@@ -226,6 +226,14 @@ typedef struct u2_dlinear_desc {
   int32_t pdl; /* != 0: launch with programmatic stream serialization (weight prefetch overlaps the previous kernel) */
   void* dbg;   /* optional uint64 [grid][4][8] globaltimer stamps (tuning aid), normally NULL */
   int64_t ws_elems; /* capacity of ws in floats */
+  /* multi-op launches only - fine-grained dataflow instead of a grid-wide wait before the first MMA of an op:
+   * out_flags: int32 [ceil(N/128)] set to the step counter when a tile of THIS op is final;
+   * dep_flags/dep_shift: flags of the op producing our x; k-block kb needs producer tile kb >> dep_shift
+   * (1: 128 producer rows = 2 k-blocks; 0: a silu_pair producer, 128 rows = 64 activations = 1 k-block).
+   * Ops linked this way must use disjoint ws / counters / x buffers (see engine.py). */
+  const int32_t* dep_flags;
+  int32_t dep_shift;
+  int32_t* out_flags;
   int32_t sched; /* U2_DLIN_STREAMK128 (128-row tiles, stream-K + workspace reduction) or
                     U2_DLIN_TILES64 (whole 64-row tiles per CTA, no inter-CTA reduction) */
 } u2_dlinear_desc;

@@ -367,10 +367,10 @@ def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
     close(out, ref, 1e-2)
 
 
-@pytest.mark.parametrize("sched", [0, 1])
+@pytest.mark.parametrize("sched,fine", [(0, False), (0, True), (1, False)])
 @pytest.mark.parametrize("B", [1, 4])
 @pytest.mark.parametrize("E,I,NQ", [(4096, 12288, 6144), (256, 512, 384), (2048, 6144, 4096)])
-def test_dlinear_multi_chain(B, E, I, NQ, sched):
+def test_dlinear_multi_chain(B, E, I, NQ, sched, fine):
     """o_proj -> gate|up -> down -> qkv in ONE launch (grid barriers inside) == the same four ops launched
     one by one == fp32 torch. Run for several 'steps' so the barrier epochs and self-cleaning state cycle."""
     from u2tokenizer_b200 import ops
@@ -383,8 +383,13 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched):
     eps = 1e-6
 
     def run(multi, ctx0, x0):
-        ws = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=DEV)
-        cnt = torch.zeros(tiles * 2, device=DEV, dtype=torch.int32)
+        ws = torch.zeros(2, max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=DEV)
+        cnt = torch.zeros(2, tiles * 2 + 8, device=DEV, dtype=torch.int32)
+        flags = torch.zeros(4, 256, device=DEV, dtype=torch.int32)
+        use_fine = fine and multi
+        fl = flags if use_fine else [None] * 4
+        dep = lambda i, shift: dict(dep_flags=fl[i], dep_shift=shift) if use_fine else {}
+        xg2 = torch.empty(B, E, device=DEV, dtype=torch.bfloat16)
         gridbar = torch.zeros(4, device=DEV, dtype=torch.int32); step = torch.zeros(1, device=DEV, dtype=torch.int32)
         ssq_a, ssq_b = torch.zeros(16, device=DEV), torch.zeros(16, device=DEV)
         x, xg = x0.clone(), torch.empty(B, E, device=DEV, dtype=torch.bfloat16)
@@ -395,11 +400,12 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched):
             step += 1
             ssq_b.fill_(123.0)  # must be reset by op 0
             ctx = (ctx0 * (1 + 0.1 * it)).bfloat16()
-            common = dict(ws=ws, counters=cnt, sched=sched)
-            chain = [(ctx, wo, x, dict(residual=x, gamma_next=ln2, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, **common)),
-                     (xg, wgu, act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, **common)),
-                     (act, wdn, x, dict(residual=x, gamma_next=ln1n, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **common)),
-                     (xg, wqkv, qkv, dict(ssq_in=ssq_b, eps=eps, **common))]
+            c0 = dict(ws=ws[0], counters=cnt[0], sched=sched)
+            c1 = dict(ws=ws[1], counters=cnt[1], sched=sched)
+            chain = [(ctx, wo, x, dict(residual=x, gamma_next=ln2, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, out_flags=fl[0], **c0)),
+                     (xg, wgu, act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, out_flags=fl[1], **dep(0, 1), **c1)),
+                     (act, wdn, x, dict(residual=x, gamma_next=ln1n, xg=xg2, ssq_out=ssq_b, ssq_zero=ssq_a, out_flags=fl[2], **dep(1, 0), **c0)),
+                     (xg2, wqkv, qkv, dict(ssq_in=ssq_b, eps=eps, **dep(2, 1), **c1))]
             if multi:
                 ops.dlinear_multi(chain, gridbar=gridbar, step_dev=step)
             else:

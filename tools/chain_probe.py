@@ -10,18 +10,24 @@ W = [dict(wo=rnd(E, E, sc=E ** -0.5).bfloat16(), wgu=rnd(2 * I, E, sc=E ** -0.5)
           wqkv=rnd(NQ, E, sc=E ** -0.5).bfloat16()) for _ in range(nlay)]
 ln = 1 + 0.1 * rnd(E)
 tiles = (2 * I + 127) // 128
-ws = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=dev); cnt = torch.zeros(tiles * 2, device=dev, dtype=torch.int32)
+ws = torch.zeros(2, max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=dev); cnt = torch.zeros(2, tiles * 2 + 8, device=dev, dtype=torch.int32)
+FINE = os.environ.get("U2_FINE_DEPS", "1") != "0"
+flags = torch.zeros(nlay, 4, 256, device=dev, dtype=torch.int32)
 gridbar = torch.zeros(4 * nlay, device=dev, dtype=torch.int32); step = torch.zeros(1, device=dev, dtype=torch.int32)
 ssq_a, ssq_b = torch.zeros(16, device=dev), torch.zeros(16, device=dev)
-x = rnd(B, E).bfloat16(); xg = torch.empty_like(x); ctx = rnd(B, E).bfloat16()
+x = rnd(B, E).bfloat16(); xg = torch.empty_like(x); xg2 = torch.empty_like(x); ctx = rnd(B, E).bfloat16()
 act = torch.empty(B, I, device=dev, dtype=torch.bfloat16); qkv = torch.empty(B, NQ, device=dev, dtype=torch.bfloat16)
 dbg = torch.zeros(148 * 4 * 8, device=dev, dtype=torch.int64)
 def chain(l, d=None):
-    w = W[l]; c = dict(ws=ws, counters=cnt, sched=int(os.environ.get("U2_DL_SCHED", "0")))
-    return [(ctx, w["wo"], x, dict(residual=x, gamma_next=ln, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, dbg=d, **c)),
-            (xg, w["wgu"], act, dict(ssq_in=ssq_a, silu_pair=True, **c)),
-            (act, w["wdn"], x, dict(residual=x, gamma_next=ln, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **c)),
-            (xg, w["wqkv"], qkv, dict(ssq_in=ssq_b, **c))]
+    w = W[l]
+    sc = int(os.environ.get("U2_DL_SCHED", "0"))
+    c0 = dict(ws=ws[0], counters=cnt[0], sched=sc); c1 = dict(ws=ws[1], counters=cnt[1], sched=sc)
+    fl = flags[l] if FINE else [None] * 4
+    dep = lambda i, sh: dict(dep_flags=fl[i], dep_shift=sh) if FINE else {}
+    return [(ctx, w["wo"], x, dict(residual=x, gamma_next=ln, xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, dbg=d, out_flags=fl[0], **c0)),
+            (xg, w["wgu"], act, dict(ssq_in=ssq_a, silu_pair=True, out_flags=fl[1], **dep(0, 1), **c1)),
+            (act, w["wdn"], x, dict(residual=x, gamma_next=ln, xg=xg2, ssq_out=ssq_b, ssq_zero=ssq_a, out_flags=fl[2], **dep(1, 0), **c0)),
+            (xg2, w["wqkv"], qkv, dict(ssq_in=ssq_b, **dep(2, 1), **c1))]
 for it in range(3):
     step += 1
     for l in range(nlay):

@@ -91,6 +91,7 @@ class DlinearDesc(C.Structure):
         ("pdl", C.c_int32),
         ("dbg", C.c_void_p),
         ("ws_elems", C.c_int64),
+        ("dep_flags", C.c_void_p), ("dep_shift", C.c_int32), ("out_flags", C.c_void_p),
         ("sched", C.c_int32),
     ]
 

@@ -74,6 +74,10 @@ struct DlinArgs {
   long long ldxg;
   float* ssq_out;              // [16] += sum_n y^2 (of the bf16-rounded y), or null
   float* ssq_zero;             // [16] buffer to reset (the one the *next* producer accumulates into), or null
+  // fine-grained dataflow inside a multi-op launch (all optional):
+  const int* dep_flags;        // per-tile "finalised in step s" flags of the op that PRODUCES our x (same launch)
+  int dep_shift;               // our k-block kb needs producer tile (kb >> dep_shift)
+  int* out_flags;              // our own per-tile flags (consumed by the next op of the launch)
   unsigned long long* dbg;     // optional [gridDim][8] globaltimer stamps (tuning aid)
 };
 
@@ -168,6 +172,27 @@ __device__ __forceinline__ UnitIter make_iter(int num_tiles, int kblocks, bool t
   return it;
 }
 
+// Producer-thread helper: block until producer tile `t` carries this step's flag. Flags are fetched four at a
+// time (one 16-byte L2 round trip covers 8 k-blocks of activations), results cached in shared memory.
+__device__ __forceinline__ void wait_tile_flag(const int* flags, int t, int step, unsigned char* ready, int tag) {
+  if (ready[t] == (unsigned char)tag) return;
+  const int t4 = t & ~3;
+  for (;;) {
+    int4 f;
+    asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(f.x), "=r"(f.y), "=r"(f.z), "=r"(f.w)
+                 : "l"(flags + t4)
+                 : "memory");
+    if (f.x >= step) ready[t4] = (unsigned char)tag;
+    if (f.y >= step) ready[t4 + 1] = (unsigned char)tag;
+    if (f.z >= step) ready[t4 + 2] = (unsigned char)tag;
+    if (f.w >= step) ready[t4 + 3] = (unsigned char)tag;
+    if (ready[t] == (unsigned char)tag) break;
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy stores -> our TMA reads
+}
+
 // One launch executes up to four dependent decode linears back to back (o_proj -> gate|up -> down -> next
 // layer's qkv): between two linears all CTAs meet at a software grid barrier, but the TMA producer keeps
 // the smem ring full with the NEXT linear's weight tiles while the current one drains and finalises, so the
@@ -191,6 +216,8 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   int* s_last = reinterpret_cast<int*>(tmem_base_slot + 1);
+  __shared__ unsigned char s_ready[1024];  // producer-thread private: producer tile t known finalised for op (value)
+  if (threadIdx.x < 256) reinterpret_cast<unsigned int*>(s_ready)[threadIdx.x] = 0u;
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -228,6 +255,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       int stage = 0;
       uint32_t phase = 0;
       unsigned int target = 0;
+      int step = 0;
       for (int oi = 0; oi < n_ops; ++oi) {
         const DlinArgs& p = mp.op[oi];
         UnitIter it = make_iter(p.num_tiles, p.kblocks, kTiles);
@@ -256,17 +284,20 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           }
         }
         U2_STAMP(oi, 0);  // W prefetch issued
-        // (2) ... then wait until the activations exist (previous kernel, or previous op of this launch)
+        // (2) ... then wait until the activations exist: the previous kernel (first op), the producing tiles of
+        //     the previous op (per-tile flags: no grid-wide wait on the critical path), or the grid barrier
         if (oi == 0) {
           asm volatile("griddepcontrol.wait;" ::: "memory");
-          target = (unsigned int)(*reinterpret_cast<const volatile int*>(mp.step_dev)) * gridDim.x;
-        } else {
+          step = *reinterpret_cast<const volatile int*>(mp.step_dev);
+          target = (unsigned int)step * gridDim.x;
+        } else if (!p.dep_flags) {
           grid_barrier_wait(mp.gridbar + (oi - 1), target);
           asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our TMA reads
         }
         U2_STAMP(oi, 1);  // dependency satisfied
         // (3) add the activation tiles of the prefetched stages
         for (int j = 0; j < npre; ++j) {
+          if (oi > 0 && p.dep_flags) wait_tile_flag(p.dep_flags, it.kb >> p.dep_shift, step, s_ready, oi);
           tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], it.kb * kDlK, 0, 0, 0);
           it.next();
           if (++stage == kStages) {
@@ -279,6 +310,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_4d(smem_a + stage * kABytes, &mp.tw[oi], &full_bar[stage], it.kb * kDlK, it.tile * kM, 0, 0);
+          if (oi > 0 && p.dep_flags) wait_tile_flag(p.dep_flags, it.kb >> p.dep_shift, step, s_ready, oi);
           tma_load_4d(smem_b + stage * kDlBBytes, &mp.tx[oi], &full_bar[stage], it.kb * kDlK, 0, 0, 0);
           it.next();
           if (++stage == kStages) {
@@ -358,10 +390,12 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
     for (int oi = 0; oi < n_ops; ++oi) {
       const DlinArgs& p = mp.op[oi];
       UnitIter it = make_iter(p.num_tiles, p.kblocks, kTiles);
-      if (oi > 0) {
-        // previous op fully finalised everywhere? one poller per CTA, the CTA barrier fans the acquire out
+      bool prev_done = (oi == 0);  // "every tile of the previous op is finalised" already observed by this CTA?
+      if (oi > 0 && !p.dep_flags) {
+        // coarse mode: previous op fully finalised everywhere? one poller per CTA, the CTA barrier fans it out
         if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        prev_done = true;
       }
       while (it.left > 0) {
         const int tile = it.tile;
@@ -452,6 +486,13 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         }
         if (last) {
           // ---------------- fused epilogue for the finished tile ----------------
+          if (!prev_done) {
+            // fine-grained mode: our MMAs only needed the producing tiles, but ssq / residual / ssq_zero need the
+            // WHOLE previous op: by now that grid barrier has long been passed - this is a formality, not a stall
+            if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            prev_done = true;
+          }
           if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
           const bool row_ok = tvalid && row < p.N;
           float sq[16];
@@ -496,6 +537,15 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) atomicAdd(p.ssq_out + b, s);
               }
+            }
+          }
+          if (p.out_flags) {
+            // publish "tile finalised in this step" for the consumers of the next op (release after the CTA barrier
+            // covers all 128 threads' output stores)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+              const int stepv = (int)(target / gridDim.x);
+              asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.out_flags + tile), "r"(stepv) : "memory");
             }
           }
         }
@@ -594,6 +644,9 @@ static int fill_op(const void* x, const void* w, void* y, const u2_dlinear_desc*
   p->ldxg = d->ldxg;
   p->ssq_out = d->ssq_out;
   p->ssq_zero = d->ssq_zero;
+  p->dep_flags = d->dep_flags;
+  p->dep_shift = d->dep_shift;
+  p->out_flags = d->out_flags;
   p->dbg = nullptr;
   int rc = make_tmap_bf16_4d(tw, w, d->K, d->N, 1, 1, d->ldw, 0, 0, kDlK, kM);
   if (rc) return rc;

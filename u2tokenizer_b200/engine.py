@@ -90,6 +90,7 @@ class U2Engine:
         import os
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
+        self.fine_deps = os.environ.get("U2_FINE_DEPS", "1") != "0"  # per-tile flags instead of grid-wide waits
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
         self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "0"))  # x16 KB per CTA at op boundaries
         self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
@@ -488,12 +489,16 @@ class U2Engine:
                 x=torch.empty(B, E, device=d, dtype=BF16), qkv=torch.empty(B, (hq + 2 * hkv) * dh, device=d, dtype=BF16),
                 ctx=torch.empty(B, hq * dh, device=d, dtype=BF16), act=torch.empty(B, I, device=d, dtype=BF16),
                 logits=torch.empty(B, g.vocab_size, device=d, dtype=F32), ids=torch.zeros(B, 1, device=d, dtype=torch.int64),
-                xg=torch.empty(B, E, device=d, dtype=BF16), ssq_a=torch.zeros(16, device=d, dtype=F32),
+                xg=torch.empty(B, E, device=d, dtype=BF16), xg2=torch.empty(B, E, device=d, dtype=BF16),
+                ssq_a=torch.zeros(16, device=d, dtype=F32),
                 ssq_b=torch.zeros(16, device=d, dtype=F32))
             max_n = max(g.vocab_size, 2 * I, (hq + 2 * hkv) * dh, E)
             shapes = [((hq + 2 * hkv) * dh, E), (E, hq * dh), (2 * I, E), (E, I), (g.vocab_size, E)]
-            self._dec["ws"] = torch.zeros(max(ops.dlinear_ws_elems(n, k) for n, k in shapes), device=d, dtype=F32)
-            self._dec["counters"] = torch.zeros((max_n + 63) // 64, device=d, dtype=torch.int32)
+            # two of each: consecutive ops of a chained launch overlap in time (fine-grained dataflow)
+            wse = max(ops.dlinear_ws_elems(n, k) for n, k in shapes)
+            self._dec["ws"] = torch.zeros(2, wse, device=d, dtype=F32)
+            self._dec["counters"] = torch.zeros(2, (max_n + 63) // 64 + 8, device=d, dtype=torch.int32)
+            self._dec["flags"] = torch.zeros(g.num_hidden_layers, 4, 256, device=d, dtype=torch.int32)
             self._dec["gridbar"] = torch.zeros(4 * g.num_hidden_layers, device=d, dtype=torch.int32)
             self._dec["step"] = torch.zeros(1, device=d, dtype=torch.int32)
             self._dec_key = key
@@ -503,7 +508,7 @@ class U2Engine:
         """Grid-barrier epochs / self-cleaning workspaces back to zero (start of a generation, or after an
         interrupted step)."""
         bufs = self._decode_buffers(B)
-        for k in ("gridbar", "step", "ws", "counters", "ssq_a", "ssq_b"):
+        for k in ("gridbar", "step", "ws", "counters", "ssq_a", "ssq_b", "flags"):
             bufs[k].zero_()
 
     def _use_tc_decode(self, B: int) -> bool:
@@ -519,26 +524,31 @@ class U2Engine:
         B = cache.batch
         hq, hkv, dh = g.num_attention_heads, g.num_key_value_heads, g.head_dim
         bufs = self._decode_buffers(B)
-        x, qkv, ctx, act, logits, ids, xg = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids", "xg"))
-        ssq_a, ssq_b, ws, cnt = bufs["ssq_a"], bufs["ssq_b"], bufs["ws"], bufs["counters"]
+        x, qkv, ctx, act, logits, ids, xg_a, xg_b = (bufs[k] for k in ("x", "qkv", "ctx", "act", "logits", "ids", "xg", "xg2"))
+        ssq_a, ssq_b, ws, cnt, flags = bufs["ssq_a"], bufs["ssq_b"], bufs["ws"], bufs["counters"], bufs["flags"]
         gridbar, step = bufs["gridbar"], bufs["step"]
         eps = g.rms_norm_eps
         nl = len(self.layers)
-        common = dict(ws=ws, counters=cnt, sched=self.dl_sched)
-        ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg, ssq_b, ssq_a, step)
-        ops.dlinear(xg, self.layers[0]["wqkv"], qkv, ssq_in=ssq_b, eps=eps, pdl=self.pdl, **common)
+        c0 = dict(ws=ws[0], counters=cnt[0], sched=self.dl_sched)
+        c1 = dict(ws=ws[1], counters=cnt[1], sched=self.dl_sched)
+        ops.decode_embed(ids, self.embed, self.layers[0]["ln1"], x, xg_b, ssq_b, ssq_a, step)
+        ops.dlinear(xg_b, self.layers[0]["wqkv"], qkv, ssq_in=ssq_b, eps=eps, pdl=self.pdl, **c1)
         for li, w in enumerate(self.layers):
             ops.decode_attention_fused(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
                                        inv_freq=self.inv_freq, scale=1.0 / math.sqrt(dh), pos_dev=cache.length_dev,
                                        q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps)
             last = li + 1 == nl
             g_next = self.final_norm if last else self.layers[li + 1]["ln1"]
+            fl = flags[li] if (self.multi_op and self.fine_deps) else [None] * 4
+            dep = lambda i, shift: dict(dep_flags=fl[i], dep_shift=shift) if fl[i] is not None else {}
             chain = [
-                (ctx, w["wo"], x, dict(residual=x, gamma_next=w["ln2"], xg=xg, ssq_out=ssq_a, ssq_zero=ssq_b, **common)),
-                (xg, w["wgu"], act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, **common)),
-                (act, w["wdown"], x, dict(residual=x, gamma_next=g_next, xg=xg, ssq_out=ssq_b, ssq_zero=ssq_a, **common)),
-                (xg, self.lm_head, logits, dict(ssq_in=ssq_b, eps=eps, **common)) if last else
-                (xg, self.layers[li + 1]["wqkv"], qkv, dict(ssq_in=ssq_b, eps=eps, **common)),
+                (ctx, w["wo"], x, dict(residual=x, gamma_next=w["ln2"], xg=xg_a, ssq_out=ssq_a, ssq_zero=ssq_b,
+                                       out_flags=fl[0], **c0)),
+                (xg_a, w["wgu"], act, dict(ssq_in=ssq_a, eps=eps, silu_pair=True, out_flags=fl[1], **dep(0, 1), **c1)),
+                (act, w["wdown"], x, dict(residual=x, gamma_next=g_next, xg=xg_b, ssq_out=ssq_b, ssq_zero=ssq_a,
+                                          out_flags=fl[2], **dep(1, 0), **c0)),
+                (xg_b, self.lm_head, logits, dict(ssq_in=ssq_b, eps=eps, **dep(2, 1), **c1)) if last else
+                (xg_b, self.layers[li + 1]["wqkv"], qkv, dict(ssq_in=ssq_b, eps=eps, **dep(2, 1), **c1)),
             ]
             if self.multi_op:
                 # L2 look-ahead: next layer's o_proj (all of it) and the head of its gate|up stream

@@ -322,7 +322,8 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 
 
 def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=None, silu_pair=False, gamma_next=None,
-                  xg=None, ssq_out=None, ssq_zero=None, pdl=True, dbg=None, sched=1):
+                  xg=None, ssq_out=None, ssq_zero=None, pdl=True, dbg=None, sched=0, dep_flags=None, dep_shift=1,
+                  out_flags=None):
     _need_cuda(x, w, out, ws, counters, ssq_in, residual, gamma_next, xg, ssq_out, ssq_zero)
     d = _lib.DlinearDesc()
     d.B, d.N, d.K = x.shape[0], w.shape[0], w.shape[1]
@@ -344,6 +345,8 @@ def _dlinear_desc(x, w, out, *, ws, counters, ssq_in=None, eps=1e-6, residual=No
     d.ssq_zero = _ptr(ssq_zero)
     d.pdl = int(pdl)
     d.dbg = _ptr(dbg)
+    _need_cuda(dep_flags, out_flags)
+    d.dep_flags, d.dep_shift, d.out_flags = _ptr(dep_flags), dep_shift, _ptr(out_flags)
     d.sched = int(sched)  # 0 = stream-K over 128-row tiles, 1 = whole 64-row tiles (no reduction)
     return d
 
