@@ -384,7 +384,7 @@ template <int kDh, int kG>
 __global__ void __launch_bounds__(256)
 fused_decode_attention_kernel(const FusedDecodeArgs a) {
   constexpr int kEpl = kDh / 32;  // head_dim elements per lane in the PV phase
-  constexpr int kPf = 8;          // V rows prefetched per batch (memory-level parallelism in the PV loop)
+  constexpr int kPf = 16;         // V rows prefetched per batch (memory-level parallelism in the PV loop)
   const int hk = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: the QKV projection must have landed
@@ -430,14 +430,15 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
     for (int g = 0; g < kG; ++g) s[g] = 0.f;
     if (t < T) {
       const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)t * kDh);
+      // the whole K row of this lane's key in one burst of independent 16-byte loads (one L2 round trip)
+      uint4 u[kDh / 8];
+#pragma unroll
+      for (int c = 0; c < kDh / 8; ++c) u[c] = kr[c];
 #pragma unroll
       for (int c0 = 0; c0 < kDh / 8; c0 += 4) {
-        uint4 u[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) u[c] = kr[c0 + c];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[c]);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[c0 + c]);
           float kf[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
