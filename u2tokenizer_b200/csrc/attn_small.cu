@@ -324,6 +324,12 @@ extern "C" U2_API int u2_decode_attention_bf16(const void* q, const void* k_cach
 namespace u2 {
 
 constexpr int kFaMaxG = 8;
+// 16 warps (512 threads): <= 512 cached keys are covered in a single 32-keys-per-warp round; 8 warps where the
+// per-warp accumulator staging would not fit the 48 KB static shared memory
+template <int kDh, int kG>
+struct FaCfg {
+  static constexpr int kWarps = (kG * kDh * 16 * 4 > 40 * 1024) ? 8 : 16;
+};
 
 struct FusedDecodeArgs {
   const __nv_bfloat16* qkv;  // [B, (Hq + 2 Hkv) * dh]
@@ -381,8 +387,9 @@ __device__ __forceinline__ void norm_rope_head(const __nv_bfloat16* src, const f
 }
 
 template <int kDh, int kG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FaCfg<kDh, kG>::kWarps * 32)
 fused_decode_attention_kernel(const FusedDecodeArgs a) {
+  constexpr int kFaWarps = FaCfg<kDh, kG>::kWarps;
   constexpr int kEpl = kDh / 32;  // head_dim elements per lane in the PV phase
   constexpr int kPf = 16;         // V rows prefetched per batch (memory-level parallelism in the PV loop)
   const int hk = blockIdx.x, b = blockIdx.y;
@@ -392,14 +399,14 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
   const int pos = a.pos_dev ? *a.pos_dev : a.pos_host;
   const int T = min(pos + 1, a.Tmax);
   __shared__ __align__(16) float s_q[kG][kDh];
-  __shared__ float s_m[8][kG], s_l[8][kG];
-  __shared__ float s_acc[8][kG][kDh];
+  __shared__ float s_m[kFaWarps][kG], s_l[kFaWarps][kG];
+  __shared__ float s_acc[kFaWarps][kG][kDh];
 
   const __nv_bfloat16* row = a.qkv + (long long)b * a.ldq;
   __nv_bfloat16* kbase = a.kc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
   __nv_bfloat16* vbase = a.vc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
   // ---- phase A: new k (norm + rope -> cache), new v (-> cache), G query heads (norm + rope -> smem)
-  for (int job = warp; job < kG + 2; job += 8) {
+  for (int job = warp; job < kG + 2; job += kFaWarps) {
     if (job == 0) {
       norm_rope_head<kDh>(row + (long long)(a.Hq + hk) * kDh, a.k_norm_w, a.eps, a.inv_freq, pos, 1.f, nullptr,
                           kbase + (long long)pos * kDh, lane);
@@ -423,7 +430,7 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
 #pragma unroll
     for (int i = 0; i < kEpl; ++i) acc[g][i] = 0.f;
   }
-  for (int t0 = warp * 32; t0 < T; t0 += 8 * 32) {
+  for (int t0 = warp * 32; t0 < T; t0 += kFaWarps * 32) {
     const int t = t0 + lane;
     float s[kG];
 #pragma unroll
@@ -504,10 +511,10 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
     const int g = idx / kDh, e = idx - g * kDh;
     float gm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) gm = fmaxf(gm, s_m[w][g]);
+    for (int w = 0; w < kFaWarps; ++w) gm = fmaxf(gm, s_m[w][g]);
     float gl = 0.f, o = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kFaWarps; ++w) {
       if (s_m[w][g] != -INFINITY) {
         const float f = __expf(s_m[w][g] - gm);
         gl += s_l[w][g] * f;
@@ -521,10 +528,10 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
 template <int kDh>
 static int launch_fused_decode(const FusedDecodeArgs& a, int G, dim3 grid, cudaStream_t st) {
   switch (G) {
-    case 1: fused_decode_attention_kernel<kDh, 1><<<grid, 256, 0, st>>>(a); break;
-    case 2: fused_decode_attention_kernel<kDh, 2><<<grid, 256, 0, st>>>(a); break;
-    case 4: fused_decode_attention_kernel<kDh, 4><<<grid, 256, 0, st>>>(a); break;
-    case 8: fused_decode_attention_kernel<kDh, 8><<<grid, 256, 0, st>>>(a); break;
+    case 1: fused_decode_attention_kernel<kDh, 1><<<grid, FaCfg<kDh, 1>::kWarps * 32, 0, st>>>(a); break;
+    case 2: fused_decode_attention_kernel<kDh, 2><<<grid, FaCfg<kDh, 2>::kWarps * 32, 0, st>>>(a); break;
+    case 4: fused_decode_attention_kernel<kDh, 4><<<grid, FaCfg<kDh, 4>::kWarps * 32, 0, st>>>(a); break;
+    case 8: fused_decode_attention_kernel<kDh, 8><<<grid, FaCfg<kDh, 8>::kWarps * 32, 0, st>>>(a); break;
     default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: Hq/Hkv = %d (supported 1, 2, 4, 8)", G);
   }
   return U2_OK;
