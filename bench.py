@@ -371,7 +371,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from u2tokenizer_b200 import _lib
+    from u2tokenizer_b200 import _lib, parallel
     from u2tokenizer_b200.synthetic import synthetic_inputs
     log(f"[rank {rank}] building {spec['model']} ...")
     model = build_model(cfg, geom)
@@ -401,11 +401,7 @@ def main():
             r = fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), device="cuda")  # device time, slowest rank
         return ms, _lib.launches() - n0, r
 
     for _ in range(max(args.warmup, 3)):

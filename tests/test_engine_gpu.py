@@ -148,3 +148,28 @@ def test_full_size_shapes_one_layer():
     check(got_feats, feats, what="encode_images full width")
     vis = eng.visual_tokens(images.cuda(), qids.cuda())
     check(vis, ref_vis, what="visual tokens full width")
+
+
+def test_u2tokenizer_hard_selection():
+    """enable_diffts=False (reference svr.py:75-91): the top-k SET must agree with the oracle except for
+    candidates whose scores are closer than the bf16 noise; the pipeline output is compared on that basis."""
+    g = tiny_geometry(enable_diffts=False, enable_dmtp=False, u2t_top_k=8)
+    eng, sd = build(g, 8)
+    gen = torch.Generator().manual_seed(3)
+    v = torch.randn(2, 3, g.tokens_per_frame, g.hidden_size, generator=gen).bfloat16()
+    t = torch.randn(2, 5, g.hidden_size, generator=gen).bfloat16()
+    with torch.no_grad():
+        ref = O.u2tokenizer(sd, "model.u2tokenizer.", v.float(), t.float(), g)
+        x = v.float()
+        for i in range(g.u2t_num_layers):
+            x = O.svr_layer(sd, f"model.u2tokenizer.svt_module.attention_network.layers.{i}.", x, g.u2t_num_heads, g.attn_type)
+        scores = (x @ sd["model.u2tokenizer.svt_module.token_selection.score_net.weight"].t()).view(2, -1)
+        ref_idx = scores.topk(g.u2t_top_k, dim=1).indices
+    got = eng.u2tokenizer(v.cuda(), t.cuda()).float().cpu()
+    sel = eng.last_selection.cpu() - torch.arange(2)[:, None] * scores.shape[1]
+    # every selected token must be within bf16 noise of the oracle's k-th score
+    kth = scores.topk(g.u2t_top_k, dim=1).values[:, -1:]
+    picked = torch.gather(scores, 1, sel)
+    assert (picked >= kth - 3e-2 * scores.abs().max()).all()
+    if torch.equal(sel, ref_idx):
+        check(got, ref, what="hard-selection tokenizer")

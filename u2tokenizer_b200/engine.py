@@ -379,6 +379,20 @@ class U2Engine:
                  c_strides=(0, K * E))
         return sel
 
+    def _token_selection_hard(self, x2: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """TokenSelection (reference svr.py:75-91): Linear(E->1) scores, top-k over frames*tokens (sorted
+        descending like torch.topk), gather. The scalar bias shifts every score alike and cannot change the
+        selection."""
+        g = self.g
+        E, K = g.hidden_size, g.u2t_top_k
+        if K > T:
+            raise RuntimeError(f"selected index k out of range: top_k={K} > {T} tokens (torch.topk raises too)")
+        sc = torch.empty(B * T, 1, device=self.dev, dtype=F32)
+        ops.gemm(x2, self.score_w, sc, M=B * T, N=1, K=E, lda=E, ldb=E, ldc=1)
+        idx = ops.topk_rows(sc.view(B, T), K, idx_offset_per_row=T)  # row-global indices into x2
+        self.last_selection = idx
+        return ops.embed_splice(idx, x2, None)
+
     def u2tokenizer(self, v_tokens: torch.Tensor, t_tokens: torch.Tensor) -> torch.Tensor:
         """u2Tokenizer.forward (reference u2Tokenizer.py:40-47): v_tokens [B, C, N, E], t_tokens [B, Lt, E]
         -> [B, num_3d_query_token, E]."""
@@ -392,7 +406,7 @@ class U2Engine:
         if g.enable_diffts:
             sel = self._token_selection_diff(x, B, C * N)
         else:
-            raise NotImplementedError("hard TokenSelection (enable_diffts=False) is not implemented yet")
+            sel = self._token_selection_hard(x, B, C * N)
         vis = ops.multiscale_pool(sel, self.gate_w, self.gate_b, g.enable_dmtp) if g.use_multi_scale else sel
         Mv = vis.shape[1]
         vis2 = vis.view(B * Mv, E)

@@ -411,3 +411,15 @@ def decode_attention_fused(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: to
                                                           out.data_ptr(), C.byref(d), _stream()),
                "u2_decode_attention_fused_bf16")
     return out
+
+
+def topk_rows(scores: torch.Tensor, k: int, idx_offset_per_row: int = 0) -> torch.Tensor:
+    """Indices of the k largest entries of every row of fp32 `scores` [rows, T], sorted descending."""
+    _need_cuda(scores)
+    if scores.dtype != F32 or scores.stride(1) != 1:
+        raise TypeError("topk_rows expects fp32 rows")
+    rows, T = scores.shape
+    out = torch.empty(rows, k, device=scores.device, dtype=torch.int64)
+    _lib.check(_lib.load().u2_topk_rows_f32(scores.data_ptr(), out.data_ptr(), rows, T, k, scores.stride(0),
+                                            idx_offset_per_row, _stream()), "u2_topk_rows_f32")
+    return out
