@@ -448,9 +448,9 @@ def test_topk_rows(T, K):
     ref_vals = torch.topk(sc, K, dim=1).values
     assert torch.equal(vals, ref_vals)                       # same multiset of values in the same order
     assert (got.sort(dim=1).values.diff(dim=1) != 0).all() if K > 1 else True   # no index twice
-    # ties resolved towards the lower index (the order torch.topk uses on CPU)
-    cpu = torch.topk(sc.cpu(), K, dim=1).indices
-    same = (got.cpu() == cpu).float().mean().item()
-    assert same > 0.99 or T > 5000, same
+    # torch leaves the order among equal scores unspecified; ours is deterministic: lower index first
+    if K > 1:
+        tie = vals[:, 1:] == vals[:, :-1]
+        assert (got[:, 1:][tie] > got[:, :-1][tie]).all()
     off = ops.topk_rows(sc, K, idx_offset_per_row=T)
     assert torch.equal(off, got + torch.arange(3, device=DEV)[:, None] * T)
