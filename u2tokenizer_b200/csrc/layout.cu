@@ -416,6 +416,7 @@ topk_rows_kernel(const float* __restrict__ scores, long long ld, int T, int K, l
     unsigned long long k = ~0ull;
     if (i < T) {
       unsigned int u = __float_as_uint(s[i]);
+      if (u == 0x80000000u) u = 0u;  // -0.0 == +0.0
       u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map float -> uint
       k = ((unsigned long long)(~u) << 32) | (unsigned int)i;  // ascending key == descending score, then index
     }
