@@ -454,3 +454,25 @@ def test_topk_rows(T, K):
         assert (got[:, 1:][tie] > got[:, :-1][tie]).all()
     off = ops.topk_rows(sc, K, idx_offset_per_row=T)
     assert torch.equal(off, got + torch.arange(3, device=DEV)[:, None] * T)
+
+
+@pytest.mark.parametrize("Sq,Sk", [(2049, 2049), (128, 128), (300, 77), (1, 1), (130, 257)])
+def test_flash_attention_d64(Sq, Sk):
+    """Fused tcgen05 attention (ViT head_dim 64) vs fp32 torch on the same bf16 q/k/v, incl. ragged tails."""
+    from u2tokenizer_b200 import ops
+    B, H, dh = 2, 3, 64
+    g = gen(Sq * 3 + Sk)
+    Sp = (max(Sq, Sk) + 7) // 8 * 8
+    qkv = torch.randn(B, Sp, 3, H, dh, device=DEV, generator=g).bfloat16()   # fused layout like the ViT qkv Linear
+    q, k, v = qkv[:, :Sq, 0], qkv[:, :Sk, 1], qkv[:, :Sk, 2]
+    Skp = (Sk + 7) // 8 * 8
+    vt = torch.empty(B, H, dh, Skp, device=DEV, dtype=torch.bfloat16)
+    ops.transpose_heads(v, vt, B=B, S=Sk, H=H, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
+                        out_strides=(H * dh * Skp, dh * Skp), ld_out=Skp)
+    out = torch.zeros(B, Sp, H * dh, device=DEV, dtype=torch.bfloat16)
+    scale = dh ** -0.5
+    ops.flash_attention_d64(q, k, vt, out[:, :Sq], scale)
+    ref = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale, -1)
+    ref = torch.einsum("bhqk,bkhd->bqhd", ref, v.float()).reshape(B, Sq, H * dh)
+    close(out[:, :Sq], ref, 1e-2)
+    assert out[:, Sq:].abs().max().item() == 0 if Sp > Sq else True

@@ -121,6 +121,18 @@ class DlinearNext(C.Structure):
     ]
 
 
+class FaDesc(C.Structure):
+    """Mirror of ``u2_fa_desc``."""
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dh", C.c_int32),
+        ("scale", C.c_float),
+        ("q_sb", C.c_int64), ("q_ss", C.c_int64), ("q_sh", C.c_int64),
+        ("k_sb", C.c_int64), ("k_ss", C.c_int64), ("k_sh", C.c_int64),
+        ("vt_sb", C.c_int64), ("vt_sh", C.c_int64), ("vt_sd", C.c_int64),
+        ("out_sb", C.c_int64), ("out_ss", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -147,6 +159,7 @@ SIGNATURES = {
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
     "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "u2_flash_attention_d64_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FaDesc), _P]),
     "u2_topk_rows_f32": (C.c_int, [_P, _P, _I, _I, _I, _L, _L, _P]),
     "u2_dlinear_ws_elems": (C.c_int64, [_I, _I]),
     "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),

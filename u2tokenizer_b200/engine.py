@@ -90,6 +90,7 @@ class U2Engine:
         import os
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
+        self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
         self.fine_deps = os.environ.get("U2_FINE_DEPS", "0") != "0"  # per-tile flags instead of grid-wide waits
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
         self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "0"))  # x16 KB per CTA at op boundaries
@@ -238,6 +239,12 @@ class U2Engine:
         b, Sq, h, dh = q.shape
         Sk, hk = k.shape[1], k.shape[2]
         Skp = _pad8(Sk)
+        if dh == 64 and h == hk and rel_bias is None and not causal and self.use_flash:
+            # fused tcgen05 attention: scores never leave the SM (the ViT tower, S = 2049)
+            vt = torch.empty(b, hk, dh, Skp, device=q.device, dtype=BF16)
+            ops.transpose_heads(v, vt, B=b, S=Sk, H=hk, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
+                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
+            return ops.flash_attention_d64(q, k, vt, out, scale)
         per_b = h * Sq * Skp * 6 + hk * dh * Skp * 2
         chunk = max(1, min(b, self.attn_ws // max(per_b, 1)))
         dev = q.device
