@@ -196,7 +196,9 @@ typedef struct u2_gemv_desc {
   int32_t silu_pair;
 } u2_gemv_desc;
 U2_API int u2_gemv_bf16(const void* x, const void* w, void* y, const u2_gemv_desc* desc, void* stream);
-U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld, void* stream);
+/* ids[b] = argmax_v logits[b, v] (first index on ties). scratch: uint64 [B], zero on entry and zero again on exit. */
+U2_API int u2_argmax_f32(const float* logits, int64_t* out, uint64_t* scratch, int32_t B, int32_t V, int64_t ld,
+                         void* stream);
 
 /* Decode-step linear on the tensor cores (swap-AB, stream-K over all SMs, TMA weight stream; HBM-bound):
  *   acc[b, n] = sum_k x[b, k] * w[n, k]                       B <= 16, K % 64 == 0

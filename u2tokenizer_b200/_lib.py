@@ -155,7 +155,7 @@ SIGNATURES = {
     "u2_rope_bf16": (C.c_int, [_P, C.POINTER(RopeDesc), _P]),
     "u2_decode_attention_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _F, _P]),
     "u2_gemv_bf16": (C.c_int, [_P, _P, _P, C.POINTER(GemvDesc), _P]),
-    "u2_argmax_f32": (C.c_int, [_P, _P, _I, _I, _L, _P]),
+    "u2_argmax_f32": (C.c_int, [_P, _P, _P, _I, _I, _L, _P]),
     "u2_dlinear_bf16": (C.c_int, [_P, _P, _P, C.POINTER(DlinearDesc), _P]),
     "u2_decode_attention_fused_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FusedDecodeDesc), _P]),
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
@@ -189,7 +189,7 @@ def load():
 
 
 # kernels launched per entry point (u2_multiscale_pool_bf16: gate + write, counted at its maximum)
-KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2}
+KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2}
 _launches = 0
 
 

@@ -179,50 +179,48 @@ gemv_kernel(const GemvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// argmax over fp32 logits [B, V] -> int64 ids [B] (first index among equal maxima, like torch.argmax)
+// argmax over fp32 logits [B, V] -> int64 ids [B] (first index among equal maxima, like torch.argmax).
+// Two tiny launches: (1) every CTA reduces a slice of a row and folds its (value, index) candidate into a
+// 64-bit packed atomicMax per row; (2) one CTA unpacks the winners and clears the scratch for the next call.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-argmax_kernel(const float* __restrict__ logits, long long* __restrict__ out, int V, long long ld) {
-  const int b = blockIdx.x;
+__device__ __forceinline__ unsigned long long pack_candidate(float v, int idx) {
+  unsigned int u = __float_as_uint(v);
+  if (u == 0x80000000u) u = 0u;                            // -0.0 == +0.0
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // order-preserving float -> uint
+  return ((unsigned long long)u << 32) | (unsigned int)(0xffffffffu - (unsigned int)idx);  // ties -> lower index
+}
+
+__global__ void __launch_bounds__(256)
+argmax_partial_kernel(const float* __restrict__ logits, unsigned long long* __restrict__ scratch, int V, long long ld) {
+  const int b = blockIdx.y;
   const float* p = logits + b * ld;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float v = p[i];
-    if (v > best || (v == best && i < bi)) {
-      best = v;
-      bi = i;
-    }
+  const int per = (V + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per;
+  const int i1 = min(V, i0 + per);
+  unsigned long long best = 0ull;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const unsigned long long c = pack_candidate(p[i], i);
+    best = c > best ? c : best;
   }
-  __shared__ float sv[32];
-  __shared__ int si[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) {
-      best = ov;
-      bi = oi;
-    }
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
   }
-  if ((threadIdx.x & 31) == 0) {
-    sv[threadIdx.x >> 5] = best;
-    si[threadIdx.x >> 5] = bi;
-  }
+  __shared__ unsigned long long sb[8];
+  if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
-    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) {
-        best = ov;
-        bi = oi;
-      }
-    }
-    if (threadIdx.x == 0) out[b] = bi;
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = sb[w] > best ? sb[w] : best;
+    if (best) atomicMax(scratch + b, best);
+  }
+}
+
+__global__ void argmax_final_kernel(unsigned long long* __restrict__ scratch, long long* __restrict__ out, int B) {
+  const int b = threadIdx.x;
+  if (b < B) {
+    out[b] = (long long)(0xffffffffu - (unsigned int)(scratch[b] & 0xffffffffull));
+    scratch[b] = 0ull;
   }
 }
 
@@ -279,10 +277,18 @@ extern "C" U2_API int u2_gemv_bf16(const void* x, const void* w, void* y, const 
   }
 }
 
-extern "C" U2_API int u2_argmax_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld, void* stream) {
-  if (!logits || !out) return set_error(U2_ERR_ARG, "argmax: null pointer");
+extern "C" U2_API int u2_argmax_f32(const float* logits, int64_t* out, uint64_t* scratch, int32_t B, int32_t V,
+                                    int64_t ld, void* stream) {
+  if (!logits || !out || !scratch) return set_error(U2_ERR_ARG, "argmax: null pointer");
   if (B <= 0 || V <= 0) return U2_OK;
-  argmax_kernel<<<B, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, reinterpret_cast<long long*>(out), V, ld);
-  U2_CHECK_LAUNCH("argmax");
+  if (B > 1024) return set_error(U2_ERR_UNSUPPORTED, "argmax: B <= 1024");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = (V + 4095) / 4096;
+  if (chunks > 64) chunks = 64;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  argmax_partial_kernel<<<grid, 256, 0, st>>>(logits, reinterpret_cast<unsigned long long*>(scratch), V, ld);
+  U2_CHECK_LAUNCH("argmax partial");
+  argmax_final_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<unsigned long long*>(scratch), reinterpret_cast<long long*>(out), B);
+  U2_CHECK_LAUNCH("argmax final");
   return U2_OK;
 }

@@ -311,13 +311,19 @@ def gemv(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, residual=None, 
     return out
 
 
+_argmax_scratch = {}
+
+
 def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(logits)
     B, V = logits.shape
     if out is None:
         out = torch.empty(B, device=logits.device, dtype=torch.int64)
-    _lib.check(_lib.load().u2_argmax_f32(logits.data_ptr(), out.data_ptr(), B, V, logits.stride(0), _stream()),
-               "u2_argmax_f32")
+    sc = _argmax_scratch.get(logits.device)
+    if sc is None:
+        sc = _argmax_scratch[logits.device] = torch.zeros(1024, device=logits.device, dtype=torch.int64)
+    _lib.check(_lib.load().u2_argmax_f32(logits.data_ptr(), out.data_ptr(), sc.data_ptr(), B, V, logits.stride(0),
+                                         _stream()), "u2_argmax_f32")
     return out
 
 
