@@ -130,7 +130,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-TRAFFIC_NCU = {"dlinear_chain": None}
+TRAFFIC_NCU = {"dlinear_chain": 431787520}  # profiles/r1_ncu_summary.md (r1_dlinear_chain_full.ncu-rep)
 
 
 def measured_peaks():
