@@ -250,6 +250,7 @@ U2_API int64_t u2_dlinear_ws_elems(int32_t N, int32_t K); /* fp32 elements of wo
  * row stride ldw[j]) = weights the NEXT launch streams first, units[j] leading tiles per CTA are prefetched when
  * this launch has issued all of its own loads (covers the launch gap / the attention kernel in between). */
 typedef struct u2_dlinear_next {
+  int32_t pre_stages;   /* ring stages of the next op's weights requested before its dependency resolves (0 = all) */
   int32_t lookahead_units;
   int32_t n;            /* 0..2 */
   const void* w[2];

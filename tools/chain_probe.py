@@ -40,11 +40,11 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 step += 1
 e0.record()
 for l in range(nlay):
-    ops.dlinear_multi(chain(l), gridbar=gridbar[4 * l:4 * l + 4], step_dev=step, lookahead_units=LA, next_weights=nxw(l))
+    ops.dlinear_multi(chain(l), gridbar=gridbar[4 * l:4 * l + 4], step_dev=step, lookahead_units=LA, next_weights=nxw(l), pre_stages=int(os.environ.get("U2_PRE_STAGES", "0")))
 e1.record(); torch.cuda.synchronize()
 print(f"chain launch: {e0.elapsed_time(e1) * 1e3 / nlay:.1f} us each (stream-only bound {2 * (E * E + 2 * I * E + E * I + NQ * E) / 6.4e6:.1f} us)")
 step += 1
-ops.dlinear_multi(chain(2, dbg), gridbar=gridbar[8:12], step_dev=step, lookahead_units=LA, next_weights=nxw(2)); torch.cuda.synchronize()
+ops.dlinear_multi(chain(2, dbg), gridbar=gridbar[8:12], step_dev=step, lookahead_units=LA, next_weights=nxw(2), pre_stages=int(os.environ.get("U2_PRE_STAGES", "0"))); torch.cuda.synchronize()
 d = dbg.view(148, 4, 8).cpu()
 t0 = d[:, 0, 0].min().item()
 rel = (d - t0).float() / 1e3

@@ -113,7 +113,7 @@ class FusedDecodeDesc(C.Structure):
 class DlinearNext(C.Structure):
     """Mirror of ``u2_dlinear_next``."""
     _fields_ = [
-        ("lookahead_units", C.c_int32), ("n", C.c_int32),
+        ("pre_stages", C.c_int32), ("lookahead_units", C.c_int32), ("n", C.c_int32),
         ("w", C.c_void_p * 2),
         ("N", C.c_int32 * 2), ("K", C.c_int32 * 2),
         ("ldw", C.c_int64 * 2),

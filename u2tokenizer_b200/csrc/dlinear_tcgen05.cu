@@ -97,6 +97,7 @@ struct DlinMulti {
   CUtensorMap tnext[2];
   int next_tiles[2], next_kblocks[2], next_units[2];  // next_units: how many leading units per CTA to prefetch
   int n_next;
+  int pre_stages;             // ring stages filled with the next op's weights before its dependency resolves
   int lookahead_units;        // per-CTA L2 prefetch depth beyond the smem ring at an in-launch op boundary
 };
 
@@ -259,7 +260,10 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
       for (int oi = 0; oi < n_ops; ++oi) {
         const DlinArgs& p = mp.op[oi];
         UnitIter it = make_iter(p.num_tiles, p.kblocks, kTiles);
-        const int npre = it.left < kStages ? it.left : kStages;
+        // stages of weight tiles requested BEFORE the dependency is satisfied (first op: all; later ops: tunable -
+        // a full-ring burst queues the dependency's control traffic behind 24 MB of bulk loads)
+        const int pre_cap = (oi == 0 || mp.pre_stages <= 0 || mp.pre_stages > kStages) ? kStages : mp.pre_stages;
+        const int npre = it.left < pre_cap ? it.left : pre_cap;
         // (1) weights never depend on earlier kernels / ops: refill the ring with this op's W tiles as
         //     soon as the previous op's MMAs release the slots ...
         int st = stage;
@@ -435,32 +439,58 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         float f[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
-        bool last = whole;
+        // Split tile (stream-K only). The CTA whose range contains k-block 0 of the tile finalises it - that
+        // segment is the LAST one of its range - while the CTAs holding the later k-blocks meet the tile as
+        // their FIRST segment: they drop their partial sums into a private slot (plain vector stores, nothing
+        // to wait for), bump the tile counter with a release and move on.
+        int gf = (int)blockIdx.x, n_contrib = 0;
         if (!whole) {
-          // Split tile (stream-K only). The CTA whose range contains k-block 0 of the tile finalises it - that
-          // segment is the LAST one of its range - while the CTAs holding the later k-blocks meet the tile as
-          // their FIRST segment: they drop their partial sums into a private slot (plain vector stores, nothing
-          // to wait for), bump the tile counter with a release and move on. By the time the finaliser gets
-          // there the slots are normally complete: one poll + one round of loads instead of an atomic/fence/
-          // counter/read-back chain.
           const long long units = (long long)p.num_tiles * p.kblocks;
           const long long G = units < (long long)gridDim.x ? units : (long long)gridDim.x;
           const long long u0 = (long long)tile * p.kblocks;
-          const int gf = (int)(((u0 + 1) * G + units - 1) / units) - 1;
-          const int gl = (int)(((u0 + p.kblocks) * G + units - 1) / units) - 1;
-          const int nvec = (p.B + 3) >> 2;
-          if (gf != (int)blockIdx.x) {
-            const int slot = (int)blockIdx.x - gf - 1;
-            float4* dst = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots + slot) * kM + trow) * kDlN);
-            if (tvalid) {
+          gf = (int)(((u0 + 1) * G + units - 1) / units) - 1;
+          n_contrib = (int)(((u0 + p.kblocks) * G + units - 1) / units) - 1 - gf;
+        }
+        const bool finalizer = (gf == (int)blockIdx.x);
+        const int nvec = (p.B + 3) >> 2;
+        const bool row_ok = tvalid && row < p.N;
+        if (!finalizer) {
+          const int slot = (int)blockIdx.x - gf - 1;
+          float4* dst = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots + slot) * kM + trow) * kDlN);
+          if (tvalid) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < nvec) __stcg(dst + c, make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]));
-            }
+            for (int c = 0; c < 4; ++c)
+              if (c < nvec) __stcg(dst + c, make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]));
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
+        } else {
+          // ---------------- this CTA finalises the tile ----------------
+          if (!prev_done) {
+            // fine-grained mode: our MMAs only needed the producing tiles, but ssq / residual / ssq_zero need the
+            // WHOLE previous op: by now that grid barrier has long been passed - this is a formality, not a stall
+            if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
-          } else {
-            const int n_contrib = gl - gf;
+            prev_done = true;
+          }
+          // operands of the epilogue that do not depend on the other CTAs' partial sums: request them now so
+          // their L2 round trips overlap the wait for the contributors
+          float res_f[16], rs[16];
+          float gam = 0.f;
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            res_f[b] = 0.f;
+            rs[b] = 1.f;
+            if (b < p.B) {
+              if (p.residual && !p.silu_pair && row_ok) {
+                const unsigned short rr = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
+                res_f[b] = __bfloat162float(__ushort_as_bfloat16(rr));
+              }
+              if (p.ssq_in) rs[b] = __ldcg(p.ssq_in + b);
+            }
+          }
+          if (p.gamma_next && row_ok) gam = __ldg(p.gamma_next + row);
+          if (n_contrib > 0) {
             if (et == 0) {
               int seen;
               do {
@@ -471,37 +501,44 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tvalid) {
-              for (int sl = 0; sl < n_contrib; ++sl) {
-                const float4* src = reinterpret_cast<const float4*>(p.ws + (((long long)tile * p.max_slots + sl) * kM + trow) * kDlN);
+              // all slots of this row in one burst of independent loads (one L2 round trip, not n_contrib)
+              constexpr int kMaxSlots = 8;
+              const float4* src0 = reinterpret_cast<const float4*>(p.ws + (((long long)tile * p.max_slots) * kM + trow) * kDlN);
+              const long long slot_stride = (long long)kM * kDlN / 4;  // in float4
+              if (nvec == 1) {
+                float4 t[kMaxSlots];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (c < nvec) {
-                    const float4 t = __ldcg(src + c);
-                    f[4 * c] += t.x; f[4 * c + 1] += t.y; f[4 * c + 2] += t.z; f[4 * c + 3] += t.w;
-                  }
+                for (int sl = 0; sl < kMaxSlots; ++sl)
+                  t[sl] = (sl < n_contrib) ? __ldcg(src0 + sl * slot_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int sl = 0; sl < kMaxSlots; ++sl) {
+                  f[0] += t[sl].x; f[1] += t[sl].y; f[2] += t[sl].z; f[3] += t[sl].w;
+                }
+                for (int sl = kMaxSlots; sl < n_contrib; ++sl) {
+                  const float4 u = __ldcg(src0 + sl * slot_stride);
+                  f[0] += u.x; f[1] += u.y; f[2] += u.z; f[3] += u.w;
+                }
+              } else {
+                for (int sl = 0; sl < n_contrib; ++sl) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    if (c < nvec) {
+                      const float4 u = __ldcg(src0 + sl * slot_stride + c);
+                      f[4 * c] += u.x; f[4 * c + 1] += u.y; f[4 * c + 2] += u.z; f[4 * c + 3] += u.w;
+                    }
+                }
               }
             }
-            last = true;
           }
-        }
-        if (last) {
           // ---------------- fused epilogue for the finished tile ----------------
-          if (!prev_done) {
-            // fine-grained mode: our MMAs only needed the producing tiles, but ssq / residual / ssq_zero need the
-            // WHOLE previous op: by now that grid barrier has long been passed - this is a formality, not a stall
-            if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            prev_done = true;
-          }
           if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
-          const bool row_ok = tvalid && row < p.N;
           float sq[16];
 #pragma unroll
           for (int b = 0; b < 16; ++b) {
             sq[b] = 0.f;
             if (b < p.B) {
               float val = f[b];
-              if (p.ssq_in) val *= rsqrtf(__ldcg(p.ssq_in + b) * p.inv_norm_dim + p.eps);
+              if (p.ssq_in) val *= rsqrtf(rs[b] * p.inv_norm_dim + p.eps);
               if (p.silu_pair) {
                 // rounding points of the unfused path: gate/up are bf16 before the activation
                 const float me = __bfloat162float(__float2bfloat16(val));
@@ -511,11 +548,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
                 }
               } else if (row_ok) {
-                if (p.residual) {
-                  // may have been written by another CTA earlier in this launch: read through L2
-                  const unsigned short rr = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
-                  val += __bfloat162float(__ushort_as_bfloat16(rr));
-                }
+                val += res_f[b];
                 if (p.y_dtype == U2_DT_BF16) {
                   const __nv_bfloat16 o = __float2bfloat16(val);
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + row] = o;
@@ -523,7 +556,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                 } else {
                   reinterpret_cast<float*>(p.y)[(long long)b * p.ldy + row] = val;
                 }
-                if (p.gamma_next) p.xg[(long long)b * p.ldxg + row] = __float2bfloat16(val * p.gamma_next[row]);
+                if (p.gamma_next) p.xg[(long long)b * p.ldxg + row] = __float2bfloat16(val * gam);
                 sq[b] = val * val;
               }
             }
@@ -710,6 +743,7 @@ extern "C" U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, con
   mp.gridbar = nullptr;
   mp.n_next = 0;
   mp.lookahead_units = 0;
+  mp.pre_stages = 0;
   mp.dbg = reinterpret_cast<unsigned long long*>(d->dbg);
   // single op: the step counter is only read to form a barrier target that is never used; point it at any
   // valid device int (the tile counters are zero between launches)
@@ -734,6 +768,7 @@ extern "C" U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* co
   }
   mp.gridbar = gridbar;
   mp.lookahead_units = next ? next->lookahead_units : 0;
+  mp.pre_stages = next ? next->pre_stages : 0;
   mp.n_next = 0;
   if (next) {
     for (int j = 0; j < 2 && j < next->n; ++j) {

@@ -93,6 +93,7 @@ class U2Engine:
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
         self.fine_deps = os.environ.get("U2_FINE_DEPS", "0") != "0"  # per-tile flags instead of grid-wide waits
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
+        self.pre_stages = int(os.environ.get("U2_PRE_STAGES", "0"))  # 0 = fill the whole ring before the dependency
         self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "0"))  # x16 KB per CTA at op boundaries
         self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
@@ -576,7 +577,8 @@ class U2Engine:
                 nxt = () if (last or self.l2_next_units < 0) else (
                     (self.layers[li + 1]["wo"], 1 << 20), (self.layers[li + 1]["wgu"], self.l2_next_units))
                 ops.dlinear_multi(chain, gridbar=gridbar[li * 4:(li + 1) * 4], step_dev=step, pdl=self.pdl,
-                                  lookahead_units=self.l2_lookahead_units, next_weights=nxt)
+                                  lookahead_units=self.l2_lookahead_units, next_weights=nxt,
+                                  pre_stages=self.pre_stages)
             else:
                 for (xi, wi, yi, kw) in chain:
                     ops.dlinear(xi, wi, yi, pdl=self.pdl, **kw)

@@ -371,7 +371,7 @@ def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw):
 
 
 def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pdl: bool = True,
-                  lookahead_units: int = 0, next_weights=()):
+                  lookahead_units: int = 0, next_weights=(), pre_stages: int = 0):
     """Several dependent decode linears in ONE launch. ops_list: [(x, w, out, kwargs), ...] (max 4).
     next_weights: [(w, units_per_cta), ...] (max 2) to warm L2 for the next launch."""
     n = len(ops_list)
@@ -383,6 +383,7 @@ def dlinear_multi(ops_list, *, gridbar: torch.Tensor, step_dev: torch.Tensor, pd
     _need_cuda(gridbar, step_dev)
     nx = _lib.DlinearNext()
     nx.lookahead_units = lookahead_units
+    nx.pre_stages = pre_stages
     nx.n = len(next_weights)
     for j, (wn, units) in enumerate(next_weights):
         _need_cuda(wn)
