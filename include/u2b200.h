@@ -207,7 +207,8 @@ U2_API int u2_argmax_f32(const float* logits, int64_t* out, uint64_t* scratch, i
  *   else:      y[b, n] = v + residual[b, n];  optionally xg[b, n] = bf16(y * gamma_next[n]) and
  *              ssq_out[b] += sum_n y^2 (prepares the next fused norm); ssq_zero[0..15] is reset to 0.
  * ws: fp32 partial-sum slots (ws_elems floats; u2_dlinear_ws_elems(N, K) gives the size needed by the stream-K
- * schedule), counters: int32 [ceil(N/64)], zero on entry and zero again on exit.
+ * schedule): every 32-bit word must hold 0xffffffff ("empty") on entry and does so again on exit;
+ * counters: int32 [ceil(N/64)], zero on entry and on exit.
  * Replaces the HF decoder Linears at q_len == 1 (reference u2llama.py:123-126 -> GenerationMixin._sample). */
 #define U2_DLIN_STREAMK128 0
 #define U2_DLIN_TILES64 1

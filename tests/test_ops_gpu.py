@@ -275,7 +275,7 @@ def test_dlinear(B, N, K, sched):
     g = gen(B * N + K + 1)
     x = torch.randn(B, K, device=DEV, generator=g).bfloat16()
     w = (torch.randn(N, K, device=DEV, generator=g) * K ** -0.5).bfloat16()
-    ws = torch.zeros(max(ops.dlinear_ws_elems(N, K), 1), device=DEV)
+    ws = ops.dlinear_new_ws(ops.dlinear_ws_elems(N, K), device=DEV)
     cnt = torch.zeros((N + 63) // 64, device=DEV, dtype=torch.int32)
     ref = x.float() @ w.float().t()
     # (a) fp32 output, fused RMSNorm scale
@@ -383,7 +383,7 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched, fine):
     eps = 1e-6
 
     def run(multi, ctx0, x0):
-        ws = torch.zeros(2, max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=DEV)
+        ws = ops.dlinear_new_ws(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=DEV, lead=(2,))
         cnt = torch.zeros(2, tiles * 2 + 8, device=DEV, dtype=torch.int32)
         flags = torch.zeros(4, 256, device=DEV, dtype=torch.int32)
         use_fine = fine and multi

@@ -10,7 +10,7 @@ W = [dict(wo=rnd(E, E, sc=E ** -0.5).bfloat16(), wgu=rnd(2 * I, E, sc=E ** -0.5)
           wqkv=rnd(NQ, E, sc=E ** -0.5).bfloat16()) for _ in range(nlay)]
 ln = 1 + 0.1 * rnd(E)
 tiles = (2 * I + 127) // 128
-ws = torch.zeros(2, max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=dev); cnt = torch.zeros(2, tiles * 2 + 8, device=dev, dtype=torch.int32)
+ws = ops.dlinear_new_ws(max(ops.dlinear_ws_elems(n, k) for n, k in ((E, E), (2 * I, E), (E, I), (NQ, E))), device=dev, lead=(2,)); cnt = torch.zeros(2, tiles * 2 + 8, device=dev, dtype=torch.int32)
 FINE = os.environ.get("U2_FINE_DEPS", "0") != "0"
 flags = torch.zeros(nlay, 4, 256, device=dev, dtype=torch.int32)
 gridbar = torch.zeros(4 * nlay, device=dev, dtype=torch.int32); step = torch.zeros(1, device=dev, dtype=torch.int32)

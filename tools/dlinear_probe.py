@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from u2tokenizer_b200 import ops
 B = 4
 def probe(N, K, reps=40, nw=24, pdl=True):
-    ws = torch.zeros(ops.dlinear_ws_elems(N, K), device="cuda"); cnt = torch.zeros((N + 63) // 64, device="cuda", dtype=torch.int32)
+    ws = ops.dlinear_new_ws(ops.dlinear_ws_elems(N, K)); cnt = torch.zeros((N + 63) // 64, device="cuda", dtype=torch.int32)
     x = torch.randn(B, K, device="cuda").bfloat16()
     W = [(torch.randn(N, K, device="cuda") * 0.02).bfloat16() for _ in range(nw)]
     out = torch.empty(B, N, device="cuda", dtype=torch.bfloat16)

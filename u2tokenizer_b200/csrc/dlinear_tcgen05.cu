@@ -57,7 +57,8 @@ struct DlCfg {
 struct DlinArgs {
   int B, N, K;                 // sequences, output rows of W, reduction length
   int num_tiles, kblocks;      // ceil(N/kM), K/64
-  float* ws;                   // [num_tiles][max_slots][kM][16] fp32 partial-sum slots (stream-K schedule only)
+  float* ws;                   // [num_tiles][max_slots][kM][16] fp32 partial-sum slots (stream-K schedule only);
+                               // every word holds the sentinel 0xffffffff between uses
   int max_slots;
   int* counters;               // [num_tiles] int32 arrival counters, zero between launches
   // epilogue
@@ -457,13 +458,13 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
         if (!finalizer) {
           const int slot = (int)blockIdx.x - gf - 1;
           float4* dst = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots + slot) * kM + trow) * kDlN);
+          // self-validating slots: every 4-byte word of a slot holds either the sentinel (all ones, a NaN pattern no
+          // fp32 sum produces) or a final partial sum, so the finaliser polls the DATA - no flag, no fence, no RMW
           if (tvalid) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               if (c < nvec) __stcg(dst + c, make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]));
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
         } else {
           // ---------------- this CTA finalises the tile ----------------
           if (!prev_done) {
@@ -490,43 +491,39 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
             }
           }
           if (p.gamma_next && row_ok) gam = __ldg(p.gamma_next + row);
-          if (n_contrib > 0) {
-            if (et == 0) {
-              int seen;
-              do {
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
-              } while (seen < n_contrib);
-              asm volatile("fence.acq_rel.gpu;" ::: "memory");
-              p.counters[tile] = 0;  // every contributor has arrived: safe to reset for the next launch
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tvalid) {
-              // all slots of this row in one burst of independent loads (one L2 round trip, not n_contrib)
+          if (n_contrib > 0 && tvalid) {
+            // poll the contributors' slots of this row (independent loads, one L2 round trip per sweep); a slot is
+            // complete when none of its words is the sentinel; consumed slots are handed back as sentinels
+            const long long slot_stride = (long long)kM * kDlN / 4;  // in float4
+            float4* src0 = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots) * kM + trow) * kDlN);
+            const float4 sent = make_float4(__uint_as_float(0xffffffffu), __uint_as_float(0xffffffffu),
+                                            __uint_as_float(0xffffffffu), __uint_as_float(0xffffffffu));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c >= nvec) break;
               constexpr int kMaxSlots = 8;
-              const float4* src0 = reinterpret_cast<const float4*>(p.ws + (((long long)tile * p.max_slots) * kM + trow) * kDlN);
-              const long long slot_stride = (long long)kM * kDlN / 4;  // in float4
-              if (nvec == 1) {
+              for (int s0 = 0; s0 < n_contrib; s0 += kMaxSlots) {
                 float4 t[kMaxSlots];
+                bool ok;
+                unsigned int spins = 0;
+                do {
+                  ok = true;
+#pragma unroll
+                  for (int sl = 0; sl < kMaxSlots; ++sl)
+                    if (s0 + sl < n_contrib) t[sl] = __ldcg(src0 + (s0 + sl) * slot_stride + c);
+#pragma unroll
+                  for (int sl = 0; sl < kMaxSlots; ++sl)
+                    if (s0 + sl < n_contrib) {
+                      ok = ok && (__float_as_uint(t[sl].x) != 0xffffffffu) && (__float_as_uint(t[sl].y) != 0xffffffffu) &&
+                           (__float_as_uint(t[sl].z) != 0xffffffffu) && (__float_as_uint(t[sl].w) != 0xffffffffu);
+                    }
+                } while (!ok && ++spins < (1u << 24));  // bounded: a lost contributor must not hang the GPU
 #pragma unroll
                 for (int sl = 0; sl < kMaxSlots; ++sl)
-                  t[sl] = (sl < n_contrib) ? __ldcg(src0 + sl * slot_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int sl = 0; sl < kMaxSlots; ++sl) {
-                  f[0] += t[sl].x; f[1] += t[sl].y; f[2] += t[sl].z; f[3] += t[sl].w;
-                }
-                for (int sl = kMaxSlots; sl < n_contrib; ++sl) {
-                  const float4 u = __ldcg(src0 + sl * slot_stride);
-                  f[0] += u.x; f[1] += u.y; f[2] += u.z; f[3] += u.w;
-                }
-              } else {
-                for (int sl = 0; sl < n_contrib; ++sl) {
-#pragma unroll
-                  for (int c = 0; c < 4; ++c)
-                    if (c < nvec) {
-                      const float4 u = __ldcg(src0 + sl * slot_stride + c);
-                      f[4 * c] += u.x; f[4 * c + 1] += u.y; f[4 * c + 2] += u.z; f[4 * c + 3] += u.w;
-                    }
-                }
+                  if (s0 + sl < n_contrib) {
+                    f[4 * c] += t[sl].x; f[4 * c + 1] += t[sl].y; f[4 * c + 2] += t[sl].z; f[4 * c + 3] += t[sl].w;
+                    __stcg(src0 + (s0 + sl) * slot_stride + c, sent);
+                  }
               }
             }
           }

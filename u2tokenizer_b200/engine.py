@@ -518,7 +518,7 @@ class U2Engine:
             shapes = [((hq + 2 * hkv) * dh, E), (E, hq * dh), (2 * I, E), (E, I), (g.vocab_size, E)]
             # two of each: consecutive ops of a chained launch overlap in time (fine-grained dataflow)
             wse = max(ops.dlinear_ws_elems(n, k) for n, k in shapes)
-            self._dec["ws"] = torch.zeros(2, wse, device=d, dtype=F32)
+            self._dec["ws"] = ops.dlinear_new_ws(wse, device=d, lead=(2,))
             self._dec["counters"] = torch.zeros(2, (max_n + 63) // 64 + 8, device=d, dtype=torch.int32)
             self._dec["flags"] = torch.zeros(g.num_hidden_layers, 4, 256, device=d, dtype=torch.int32)
             self._dec["gridbar"] = torch.zeros(4 * g.num_hidden_layers, device=d, dtype=torch.int32)
@@ -530,8 +530,9 @@ class U2Engine:
         """Grid-barrier epochs / self-cleaning workspaces back to zero (start of a generation, or after an
         interrupted step)."""
         bufs = self._decode_buffers(B)
-        for k in ("gridbar", "step", "ws", "counters", "ssq_a", "ssq_b", "flags"):
+        for k in ("gridbar", "step", "counters", "ssq_a", "ssq_b", "flags"):
             bufs[k].zero_()
+        bufs["ws"].view(torch.int32).fill_(-1)  # "empty slot" sentinel
 
     def _use_tc_decode(self, B: int) -> bool:
         g = self.g

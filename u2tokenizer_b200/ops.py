@@ -362,6 +362,11 @@ def dlinear_ws_elems(N: int, K: int) -> int:
     return int(_lib.load().u2_dlinear_ws_elems(N, K))
 
 
+def dlinear_new_ws(n_elems: int, device="cuda", lead=()) -> torch.Tensor:
+    """Workspace for the stream-K split-tile slots: fp32 view of all-ones words (the 'empty slot' sentinel)."""
+    return torch.full((*lead, max(int(n_elems), 4)), -1, device=device, dtype=torch.int32).view(F32)
+
+
 def dlinear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw):
     """Decode-step linear on tcgen05 (see u2_dlinear_desc): x [B<=16, K] bf16, w [N, K] bf16."""
     d = _dlinear_desc(x, w, out, **kw)
