@@ -117,6 +117,16 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// polling load: volatile asm so that the compiler re-issues it on every sweep (a plain __ldcg is loop-invariant)
+__device__ __forceinline__ float4 ld_relaxed_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
 // single-thread poll (relaxed loads: one L2 round trip each), acquire fence once the target is reached
 __device__ __forceinline__ void grid_barrier_wait(const unsigned int* bar, unsigned int target) {
   unsigned int v;
@@ -510,14 +520,14 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                   ok = true;
 #pragma unroll
                   for (int sl = 0; sl < kMaxSlots; ++sl)
-                    if (s0 + sl < n_contrib) t[sl] = __ldcg(src0 + (s0 + sl) * slot_stride + c);
+                    if (s0 + sl < n_contrib) t[sl] = ld_relaxed_f4(src0 + (s0 + sl) * slot_stride + c);
 #pragma unroll
                   for (int sl = 0; sl < kMaxSlots; ++sl)
                     if (s0 + sl < n_contrib) {
                       ok = ok && (__float_as_uint(t[sl].x) != 0xffffffffu) && (__float_as_uint(t[sl].y) != 0xffffffffu) &&
                            (__float_as_uint(t[sl].z) != 0xffffffffu) && (__float_as_uint(t[sl].w) != 0xffffffffu);
                     }
-                } while (!ok && ++spins < (1u << 24));  // bounded: a lost contributor must not hang the GPU
+                } while (!ok && ++spins < (1u << 22));  // bounded: a lost contributor must not hang the GPU
 #pragma unroll
                 for (int sl = 0; sl < kMaxSlots; ++sl)
                   if (s0 + sl < n_contrib) {

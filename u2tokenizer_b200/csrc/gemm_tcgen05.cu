@@ -12,7 +12,8 @@
 //   warp 1   : MMA issuer     - one thread issues tcgen05.mma (128 x BLOCK_N x 16), accumulators
 //                               live in TMEM, double buffered so the epilogue overlaps the next tile
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue       - tcgen05.ld TMEM -> registers, alpha/bias/activation/residual, store
+//   warps 4-11: epilogue      - tcgen05.ld TMEM -> registers, alpha/bias/activation/residual, store
+//                               (two warps per TMEM lane quarter, each drains half of the columns)
 //
 // Reference call sites this replaces: every nn.Linear / torch.matmul on the path, e.g.
 // src/model/u2tokenizer/rma.py:52-58,60-73 and tta.py:42-69 (reference repo paths).
@@ -28,8 +29,9 @@ namespace u2 {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter, each takes half of the tile's columns
 
 template <int kBlockN>
 struct GemmCfg {
@@ -102,7 +104,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -178,7 +180,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= kEpiWarp0) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp_idx - kEpiWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+    const int q = (warp_idx - kEpiWarp0) & 3;    // == warp_idx % 4: the TMEM lane quarter this warp may read
+    const int half = (warp_idx - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -204,7 +207,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
       const uint32_t taddr = tmem_base + acc * kBlockN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+      for (int c0 = half * (kBlockN / 2); c0 < (half + 1) * (kBlockN / 2); c0 += 32) {
         const int col0 = n_blk * kBlockN + c0;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
