@@ -307,6 +307,14 @@ typedef struct u2_fa_desc {
 U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* vt, void* out, const u2_fa_desc* desc,
                                        void* stream);
 
+/* Sampled decoding head: ids[b] ~ multinomial(top_p(top_k(softmax(logits[b] / temperature)))) - the HF warper chain
+ * behind generate(do_sample=True, temperature, top_k, top_p) used by the reference's eval scripts
+ * (eval/mrg.py:74-75). top_k <= 0 disables top-k, top_p = 1 disables nucleus filtering. Counter-based RNG
+ * keyed by (seed, step or *step_dev, row). */
+U2_API int u2_sample_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld, float temperature,
+                         int32_t top_k, float top_p, uint64_t seed, const int32_t* step_dev, int32_t step,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,20 @@ def test_eos_padding_semantics():
     first = (free[0] == eos).nonzero()[0].item()
     assert torch.equal(got[0, :first + 1], free[0, :first + 1])
     assert (got[0, first + 1:] == 0).all()
+
+
+def test_sampled_generate_surface():
+    """generate(do_sample=True, top_p, temperature) - the call every eval script of the reference makes
+    (eval/mrg.py:74-75): runs on the CUDA sampling head, is reproducible for a fixed seed, varies across seeds, and
+    collapses to greedy when the nucleus is a single token."""
+    model, g, sd = make("qwen3")
+    images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12)
+    kw = dict(question_ids=qids.cuda(), max_new_tokens=8, do_sample=True, top_p=0.9, temperature=1.0)
+    a = model.generate(images.cuda(), ids.cuda(), seed=11, **kw).cpu()
+    b = model.generate(images.cuda(), ids.cuda(), seed=11, **kw).cpu()
+    c = model.generate(images.cuda(), ids.cuda(), seed=12, **kw).cpu()
+    assert a.shape == (2, 8) and torch.equal(a, b) and not torch.equal(a, c)
+    greedy = model.generate(images.cuda(), ids.cuda(), question_ids=qids.cuda(), max_new_tokens=8, do_sample=False).cpu()
+    tiny_nucleus = model.generate(images.cuda(), ids.cuda(), question_ids=qids.cuda(), max_new_tokens=8, do_sample=True,
+                                  top_p=1e-6, temperature=1.0, seed=5).cpu()
+    assert torch.equal(tiny_nucleus, greedy)

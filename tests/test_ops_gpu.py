@@ -476,3 +476,45 @@ def test_flash_attention_d64(Sq, Sk):
     ref = torch.einsum("bhqk,bkhd->bqhd", ref, v.float()).reshape(B, Sq, H * dh)
     close(out[:, :Sq], ref, 1e-2)
     assert out[:, Sq:].abs().max().item() == 0 if Sp > Sq else True
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(1.0, 0, 1.0), (0.7, 50, 0.9), (1.3, 5, 1.0), (1.0, 0, 0.5)])
+def test_sampling_distribution(temperature, top_k, top_p):
+    """Statistical parity with the HF warper chain (temperature -> top-k -> top-p) + multinomial: empirical token
+    frequencies over many draws match the filtered distribution; filtered-out tokens are never drawn."""
+    from u2tokenizer_b200 import ops
+    V, n = 300, 40000
+    g = gen(int(temperature * 10) + top_k)
+    row = torch.randn(V, device=DEV, generator=g) * 2.0
+    logits = row.expand(1024, V).contiguous()
+    # reference distribution (HF semantics)
+    x = row.double() / temperature
+    if top_k > 0:
+        kth = x.topk(top_k).values[-1]
+        x = x.masked_fill(x < kth, float("-inf"))
+    p = torch.softmax(x, -1)
+    if top_p < 1.0:
+        sp, si = p.sort(descending=True)
+        cum = sp.cumsum(0)
+        keep_sorted = (cum - sp) < top_p          # keep tokens until the mass reaches top_p (the crossing one included)
+        keep = torch.zeros(V, dtype=torch.bool, device=DEV)
+        keep[si[keep_sorted]] = True
+        p = torch.where(keep, p, torch.zeros_like(p))
+        p = p / p.sum()
+    counts = torch.zeros(V, device=DEV, dtype=torch.float64)
+    draws = 0
+    step = 0
+    while draws < n:
+        ids = ops.sample(logits, temperature=temperature, top_k=top_k, top_p=top_p, seed=1234, step=step)
+        counts += torch.bincount(ids, minlength=V).double()
+        draws += ids.numel()
+        step += 1
+    freq = counts / draws
+    assert (freq[p == 0] == 0).all(), "a filtered-out token was drawn"
+    # total-variation distance; sampling noise ~ sqrt(support / draws)
+    tv = 0.5 * (freq - p).abs().sum().item()
+    assert tv < 0.03, tv
+    # same (seed, step) -> same draw; different rows decorrelated
+    a = ops.sample(logits, temperature=temperature, top_k=top_k, top_p=top_p, seed=7, step=3)
+    b2 = ops.sample(logits, temperature=temperature, top_k=top_k, top_p=top_p, seed=7, step=3)
+    assert torch.equal(a, b2) and a.unique().numel() > 1

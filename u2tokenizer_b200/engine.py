@@ -107,6 +107,7 @@ class U2Engine:
             self._prep_tokenizer(t)
         self._prep_decoder(t)
         self._gen_state = None
+        self._sampling = None
 
     # =========================================================================================
     # weight preparation
@@ -583,9 +584,19 @@ class U2Engine:
             else:
                 for (xi, wi, yi, kw) in chain:
                     ops.dlinear(xi, wi, yi, pdl=self.pdl, **kw)
-        ops.argmax(logits, ids.view(B))
+        self._pick_next(logits, ids.view(B), bufs["step"])
         cache.advance_device()
         return logits
+
+    def _pick_next(self, logits: torch.Tensor, ids_out: torch.Tensor, step_dev: Optional[torch.Tensor], step: int = 0):
+        """Greedy argmax, or the sampled head (temperature -> top-k -> top-p -> multinomial) when a sampling
+        configuration is active (HF generate(do_sample=True, ...), reference eval/mrg.py:74-75)."""
+        sp = self._sampling
+        if sp is None:
+            ops.argmax(logits, ids_out)
+        else:
+            ops.sample(logits, ids_out, temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"],
+                       seed=sp["seed"], step=step, step_dev=step_dev)
 
     def decode_step(self, cache: "KVCache") -> torch.Tensor:
         """Consumes buffers['ids'] [B,1] (the last token of every sequence), appends to the cache at
@@ -611,7 +622,8 @@ class U2Engine:
             ops.gemv(x, w["wgu"], act, norm_gamma=w["ln2"], norm_eps=g.rms_norm_eps, silu_pair=True)
             ops.gemv(act, w["wdown"], x, residual=x)
         ops.gemv(x, self.lm_head, logits, norm_gamma=self.final_norm, norm_eps=g.rms_norm_eps)
-        ops.argmax(logits, ids.view(B))
+        bufs["step"] += 1  # the gemv path has no decode_embed kernel to bump the step counter
+        self._pick_next(logits, ids.view(B), bufs["step"])
         cache.advance_device()
         return logits
 
@@ -619,15 +631,27 @@ class U2Engine:
     # greedy generation (reference u2llama.py:90-127 with do_sample=False)
     # =========================================================================================
     @torch.no_grad()
+    def generate(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None, do_sample: bool = False,
+                 temperature: float = 1.0, top_k: int = 50, top_p: float = 1.0, seed: int = 0, use_graph: bool = True):
+        """Greedy (do_sample=False) or sampled decoding; same loop, only the token-picking head differs."""
+        self._sampling = dict(temperature=float(temperature), top_k=int(top_k or 0), top_p=float(top_p),
+                              seed=int(seed)) if do_sample else None
+        try:
+            return self.generate_greedy(embeds, max_new_tokens, eos_token_id=eos_token_id, use_graph=use_graph)
+        finally:
+            self._sampling = None
+
     def generate_greedy(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None,
                         use_graph: bool = True, return_margins: bool = False):
-        """Prefill on `embeds` [B, L, E], then max_new_tokens greedy steps. Returns new ids [B, n]
-        (and the per-step top-1/top-2 logit margins when asked, for margin-aware parity checks)."""
+        """Prefill on `embeds` [B, L, E], then max_new_tokens decode steps (greedy unless a sampling configuration
+        was installed by generate()). Returns new ids [B, n] (and the per-step top-1/top-2 logit margins when
+        asked, for margin-aware parity checks)."""
         from . import _lib
         B, L, _ = embeds.shape
         # the static KV cache and the captured decode-step graph are kept across calls with the same
         # (batch, capacity): capture + instantiation cost ~0.1 s, which would otherwise be paid per request
-        key = (B, L + max_new_tokens, self.decode_impl, self.multi_op, self.fine_deps)
+        key = (B, L + max_new_tokens, self.decode_impl, self.multi_op, self.fine_deps,
+               tuple(sorted(self._sampling.items())) if self._sampling else None)
         st = self._gen_state if (self._gen_state is not None and self._gen_state["key"] == key) else None
         if st is None:
             self._gen_state = None  # drop the old cache before allocating the new one
@@ -641,7 +665,7 @@ class U2Engine:
         logits0 = self.lm_logits(hidden[:, -1].contiguous())
         out = torch.empty(B, max_new_tokens, device=self.dev, dtype=torch.int64)
         margins = []
-        ops.argmax(logits0, bufs["ids"].view(B))
+        self._pick_next(logits0, bufs["ids"].view(B), None, step=0)
         out[:, 0] = bufs["ids"].view(B)
         if return_margins:
             t2 = logits0.topk(2, dim=-1).values

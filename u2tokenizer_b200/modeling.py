@@ -286,13 +286,24 @@ class U2MetaForCausalLM(ABC):
                 inputs_embeds = eng.embed_tokens(inputs)
         else:
             inputs_embeds = eng.embed_tokens(inputs)
-        if kwargs.pop("do_sample", False) or kwargs.get("num_beams", 1) != 1:
-            raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is implemented on the "
-                                      "CUDA path; sampling is listed under 'next' in DESIGN.md")
-        for k in ("top_p", "top_k", "temperature", "num_beams"):
-            kwargs.pop(k, None)
-        L = inputs_embeds.shape[1]
+        if kwargs.pop("num_beams", 1) != 1:
+            raise NotImplementedError("beam search is not implemented on the CUDA path (greedy and sampling are)")
         gc = getattr(self, "generation_config", None)
+        do_sample = kwargs.pop("do_sample", None)
+        if do_sample is None:
+            do_sample = bool(getattr(gc, "do_sample", False))
+
+        def opt(name, default):
+            v = kwargs.pop(name, None)
+            if v is None and gc is not None:
+                v = getattr(gc, name, None)
+            return default if v is None else v
+        temperature, top_k, top_p = opt("temperature", 1.0), opt("top_k", 50), opt("top_p", 1.0)
+        seed = kwargs.pop("seed", None)
+        if seed is None:
+            seed = int(torch.initial_seed()) + self.__dict__.setdefault("_u2_sample_calls", 0)
+            self.__dict__["_u2_sample_calls"] += 1
+        L = inputs_embeds.shape[1]
         max_new = kwargs.pop("max_new_tokens", None)
         if max_new is None:
             max_len = kwargs.pop("max_length", None) or (gc.max_length if gc is not None else 20)
@@ -303,7 +314,8 @@ class U2MetaForCausalLM(ABC):
         pad = kwargs.pop("pad_token_id", None)
         if pad is None and gc is not None:
             pad = gc.pad_token_id
-        ids = eng.generate_greedy(inputs_embeds.to(torch.bfloat16), max_new_tokens=max_new, eos_token_id=eos)
+        ids = eng.generate(inputs_embeds.to(torch.bfloat16), max_new_tokens=max_new, eos_token_id=eos,
+                           do_sample=bool(do_sample), temperature=temperature, top_k=top_k, top_p=top_p, seed=seed)
         if eos is not None:
             eos_t = torch.as_tensor(eos if isinstance(eos, (list, tuple)) else [eos], device=ids.device)
             hit = torch.isin(ids, eos_t)

@@ -454,3 +454,16 @@ def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out:
     _lib.check(_lib.load().u2_flash_attention_d64_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(),
                                                        C.byref(d), _stream()), "u2_flash_attention_d64_bf16")
     return out
+
+
+def sample(logits: torch.Tensor, out: Optional[torch.Tensor] = None, *, temperature: float = 1.0, top_k: int = 50,
+           top_p: float = 1.0, seed: int = 0, step: int = 0, step_dev=None) -> torch.Tensor:
+    """ids ~ multinomial(top_p(top_k(softmax(logits / temperature)))) per row (HF sampling warper chain)."""
+    _need_cuda(logits, step_dev)
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    _lib.check(_lib.load().u2_sample_f32(logits.data_ptr(), out.data_ptr(), B, V, logits.stride(0), temperature,
+                                         int(top_k), float(top_p), int(seed) & ((1 << 64) - 1), _ptr(step_dev),
+                                         int(step), _stream()), "u2_sample_f32")
+    return out
