@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "host_util.h"
+#include "ptx.cuh"
 #include "u2b200.h"
 
 namespace u2 {
@@ -65,6 +66,49 @@ patchify_kernel(const float* __restrict__ vol, __nv_bfloat16* __restrict__ rows,
     o.x = *reinterpret_cast<uint32_t*>(&lo);
     o.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(rows + row * pd + col) = o;
+  }
+}
+
+// TMA-staged variant (the default when the brick slab fits shared memory): one CTA per (frame, a0, a1) loads the
+// [p0][p1][D2] fp32 slab that holds the g2 patches of one patch row with a single 3-D bulk tensor copy
+// (fully coalesced 1 KB lines), converts to bf16 and writes the g2 consecutive output rows (g2 * pd * 2 bytes,
+// one contiguous span) with 16-byte stores that are consecutive across the warp: both directions move whole lines.
+__global__ void __launch_bounds__(256)
+patchify_tma_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __restrict__ rows, int D0, int g1,
+                    int g2, int p0, int p1, int p2, int D2) {
+  extern __shared__ __align__(128) float slab[];  // [p0][p1][D2]
+  __shared__ uint64_t bar;
+  const int a1 = blockIdx.x, a0 = blockIdx.y, f = blockIdx.z;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, (uint32_t)(p0 * p1 * D2 * sizeof(float)));
+    tma_load_3d(slab, &tmap, &bar, 0, a1 * p1, f * D0 + a0 * p0);
+  }
+  mbar_wait(&bar, 0);
+  const int pd = p0 * p1 * p2;
+  const int cpp = pd >> 3;  // 16-byte output chunks per patch
+  const long long row0 = ((long long)f * (D0 / p0) * g1 + (long long)a0 * g1 + a1) * g2;
+  __nv_bfloat16* dst = rows + row0 * pd;
+  for (int c = threadIdx.x; c < g2 * cpp; c += blockDim.x) {
+    const int a2 = c / cpp;
+    const int col = (c - a2 * cpp) << 3;
+    const int b0 = col / (p1 * p2);
+    const int b1 = (col / p2) % p1;
+    const int b2 = col % p2;
+    const float* sp = slab + ((b0 * p1 + b1) * D2 + a2 * p2 + b2);
+    const float4 v0 = *reinterpret_cast<const float4*>(sp);
+    const float4 v1 = *reinterpret_cast<const float4*>(sp + 4);
+    uint4 o;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+    h2[0] = __floats2bfloat162_rn(v0.x, v0.y);
+    h2[1] = __floats2bfloat162_rn(v0.z, v0.w);
+    h2[2] = __floats2bfloat162_rn(v1.x, v1.y);
+    h2[3] = __floats2bfloat162_rn(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(dst + (long long)a2 * pd + col) = o;
   }
 }
 
@@ -317,7 +361,24 @@ extern "C" U2_API int u2_patchify_f32_bf16(const float* vol, void* rows, int64_t
   if (reinterpret_cast<uintptr_t>(vol) & 15) return set_error(U2_ERR_ARG, "patchify: volume must be 16-byte aligned");
   const long long total = (long long)frames * d0 * d1 * (d2 / 4);
   if (total <= 0) return U2_OK;
-  patchify_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(vol, BF(rows), frames, d0, d1, d2, p0, p1, p2);
+  const size_t slab_bytes = (size_t)p0 * p1 * d2 * sizeof(float);
+  const bool tma_ok = d2 <= 256 && p1 <= 256 && p0 <= 256 && (p2 % 8) == 0 && slab_bytes <= 96 * 1024 &&
+                      frames <= 65535 && (d0 / p0) <= 65535 && (long long)frames * d0 < (1LL << 31);
+  if (tma_ok) {
+    CUtensorMap tm;
+    int rc = make_tmap_f32_3d(&tm, vol, d2, d1, (int64_t)frames * d0, d2, (int64_t)d1 * d2, d2, p1, p0);
+    if (rc) return rc;
+    static size_t configured = 0;
+    if (slab_bytes > 48 * 1024 && slab_bytes > configured) {
+      cudaError_t e = cudaFuncSetAttribute(patchify_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
+      if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "patchify smem: %s", cudaGetErrorString(e));
+      configured = slab_bytes;
+    }
+    dim3 grid((unsigned)(d1 / p1), (unsigned)(d0 / p0), (unsigned)frames);
+    patchify_tma_kernel<<<grid, 256, slab_bytes, ST(stream)>>>(tm, BF(rows), d0, d1 / p1, d2 / p2, p0, p1, p2, d2);
+  } else {
+    patchify_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(vol, BF(rows), frames, d0, d1, d2, p0, p1, p2);
+  }
   U2_CHECK_LAUNCH("patchify");
   return U2_OK;
 }
