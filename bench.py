@@ -222,6 +222,57 @@ def roofline_probe(model, spec, geom):
             "flops_per_launch": fl, "us_per_launch": round(sec * 1e6, 2)}
 
 
+def extra_rooflines(model, spec, geom):
+    """Secondary kernels named by BASELINE.json's north star, timed live (CUDA events, inputs larger than L2):
+    the 3-D patch-embed brick gather (HBM) and the decoder prefill gate|up GEMM (tensor pipe)."""
+    from u2tokenizer_b200 import ops
+    eng = model.engine()
+    hbm, tf, src = measured_peaks()
+    out = []
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # --- patch-embed gather: fp32 volume -> bf16 patch rows, 32 frames = 268 MB in, 134 MB out per launch
+    Fr = 32
+    D0, D1, D2 = geom.image_size
+    vols = [torch.rand(Fr, D0, D1, D2, device="cuda") for _ in range(2)]
+    rows = [torch.empty(Fr * geom.n_patches, geom.patch_dim, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    for i in range(2):
+        ops.patchify(vols[i], geom.patch_size, out=rows[i])
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    for r in range(8):
+        ops.patchify(vols[r % 2], geom.patch_size, out=rows[r % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / 8
+    by = Fr * D0 * D1 * D2 * 6
+    out.append({"kernel": "patchify_tma_kernel (3-D patch-embed brick gather, fp32 volume -> bf16 patch rows)", "bound": "hbm",
+                "achieved": round(by / sec / 1e9, 1), "peak": hbm, "unit": "GB/s", "frac": round(by / sec / 1e9 / hbm, 4),
+                "bytes_per_launch": by, "us_per_launch": round(sec * 1e6, 2), "peak_source": src})
+    del vols, rows
+    # --- decoder prefill GEMM (gate|up): M = batch * prompt rows
+    M = max(spec["batch"], 1) * (geom.num_3d_query_token + spec["n_question"])
+    E, I = geom.hidden_size, geom.intermediate_size
+    a = (torch.randn(M, E, device="cuda") * 0.05).bfloat16()
+    c = torch.empty(M, 2 * I, device="cuda", dtype=torch.bfloat16)
+    nl = len(eng.layers)
+    for li in range(min(nl, 4)):
+        ops.linear(a, eng.layers[li]["wgu"], out=c)
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    for li in range(nl):
+        ops.linear(a, eng.layers[li]["wgu"], out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / nl
+    fl = 2.0 * M * 2 * I * E
+    out.append({"kernel": f"gemm_bf16_tcgen05_kernel<256> (decoder prefill gate|up, M={M} N={2 * I} K={E})", "bound": "tensor",
+                "achieved": round(fl / sec / 1e12, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(fl / sec / 1e12 / tf, 4),
+                "flops_per_launch": fl, "us_per_launch": round(sec * 1e6, 2), "peak_source": src})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port on host cores, bounded sample, extrapolated by layer counts
 # ------------------------------------------------------------------------------------------------
@@ -437,6 +488,10 @@ def main():
         out["roofline"] = roofline_probe(model, spec, geom)
     except Exception as e:  # the probe must never cost the bench line
         out["roofline"] = {"error": repr(e)}
+    try:
+        out["roofline_other_kernels"] = extra_rooflines(model, spec, geom)
+    except Exception as e:
+        out["roofline_other_kernels"] = [{"error": repr(e)}]
     if world == 1 and not args.no_cpu_baseline:
         try:
             del model
