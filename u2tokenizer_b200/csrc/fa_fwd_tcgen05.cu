@@ -17,6 +17,7 @@
 // 100-105,120-122), which materialises a [frames*12, 2049, 2049] fp32 score tensor per block.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -270,6 +271,238 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two query tiles per CTA (256 rows), two softmax warp-groups: the tile-A group exponentiates while the tensor
+// pipe runs PV / the next QK^T of tile B and vice versa (ping-pong). The softmax is issue-bound with one warp per
+// scheduler; the second group doubles the CUDA-core side and both tiles share every K / V^T tile brought in by TMA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFa2Threads = 384;
+constexpr int kFa2Smem = 2 * kFaQBytes + 2 * kFaKBytes + 2 * kFaVBytes + 2 * kFaPBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kFa2Threads, 1)
+fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_vt, const FaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                       // [2 tiles]
+  uint8_t* sK = sQ + 2 * kFaQBytes;         // [2 stages]
+  uint8_t* sV = sK + 2 * kFaKBytes;         // [2 stages]
+  uint8_t* sP = sV + 2 * kFaVBytes;         // [2 tiles]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kFaPBytes);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // 2 (stage)
+  uint64_t* kv_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;      // 2 (tile)
+  uint64_t* s_empty = bars + 7;     // 2
+  uint64_t* p_full = bars + 9;      // 2
+  uint64_t* p_empty = bars + 11;    // 2
+  uint64_t* o_full = bars + 13;     // 2
+  uint64_t* o_empty = bars + 15;    // 2
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kFaBM;
+  const int J = (p.Sk + kFaBN - 1) / kFaBN;
+  const bool has_b = (q0 + kFaBM) < p.Sq;  // second query tile holds at least one valid row
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_vt);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc<kFaTmemCols>(tmem_base_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tS = tmem_base;         // S[tile] at columns tile * 128
+  const uint32_t tO = tmem_base + 256;   // O[tile] at columns 256 + tile * 64
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, has_b ? 2 * kFaQBytes : kFaQBytes);
+      tma_load_4d(sQ, &tmap_q, q_full, 0, q0, h, b);
+      if (has_b) tma_load_4d(sQ + kFaQBytes, &tmap_q, q_full, 0, q0 + kFaBM, h, b);
+      for (int j = 0; j < J; ++j) {
+        const int st = j & 1, n = j >> 1;
+        mbar_wait(&kv_empty[st], (n & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], kFaKBytes + kFaVBytes);
+        tma_load_4d(sK + st * kFaKBytes, &tmap_k, &kv_full[st], 0, j * kFaBN, h, b);
+        tma_load_4d(sV + st * kFaVBytes, &tmap_vt, &kv_full[st], j * kFaBN, 0, h, b);
+        tma_load_4d(sV + st * kFaVBytes + kFaVBytes / 2, &tmap_vt, &kv_full[st], j * kFaBN + 64, 0, h, b);
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kFaBM, kFaBN);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kFaBM, kFaDh);
+      const int ntile = has_b ? 2 : 1;
+      auto issue_qk = [&](int t, int j) {
+        const int st = j & 1;
+        mbar_wait(&s_empty[t], (j & 1) ^ 1);  // softmax group t finished reading S[t] of key tile j - 1
+        tc_fence_after();
+        const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(sQ + t * kFaQBytes));
+        const uint64_t k_desc = umma_desc_kmajor_sw128(smem_u32(sK + st * kFaKBytes));
+#pragma unroll
+        for (int k = 0; k < kFaDh / 16; ++k) umma_f16(tS + t * kFaBN, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {
+        const int st = j & 1;
+        mbar_wait(&p_full[t], j & 1);
+        mbar_wait(&o_empty[t], (j & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + t * kFaPBytes);
+        const uint32_t v_addr = smem_u32(sV + st * kFaVBytes);
+#pragma unroll
+        for (int k = 0; k < kFaBN / 16; ++k) {
+          const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (kFaPBytes / 2)) + 2 * (k & 3);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(v_addr + (k >> 2) * (kFaVBytes / 2)) + 2 * (k & 3);
+          umma_f16(tO + t * kFaDh, a_desc, b_desc, idesc_pv, k != 0);
+        }
+        umma_commit(&o_full[t]);
+        umma_commit(&p_empty[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      for (int t = 0; t < ntile; ++t) issue_qk(t, 0);
+      for (int j = 0; j < J; ++j) {
+        const bool more = (j + 1 < J);
+        if (more) mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        for (int t = 0; t < ntile; ++t) {
+          issue_pv(t, j);
+          if (t == ntile - 1) umma_commit(&kv_empty[j & 1]);  // every MMA that reads stage j & 1 has been issued
+          if (more) issue_qk(t, j + 1);  // tile t's next scores: overlaps the other group's softmax
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int t = (warp_idx - 4) >> 2;          // softmax group == query tile
+    if (t == 0 || has_b) {
+      const int q = (warp_idx - 4) & 3;
+      const int r = (threadIdx.x - 128) & 127;  // row inside the tile
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      float m = -INFINITY, l = 0.f;
+      float o[kFaDh];
+#pragma unroll
+      for (int d = 0; d < kFaDh; ++d) o[d] = 0.f;
+      uint8_t* prow = sP + t * kFaPBytes + r * 128;
+
+      for (int j = 0; j < J; ++j) {
+        const int nk = min(kFaBN, p.Sk - j * kFaBN);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kFaBN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + t * kFaBN + lane_off + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < nk) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float m_new = fmaxf(m, mx * p.scale_log2e);
+        const float alpha = ex2_approx(m - m_new);
+        if (j > 0) {
+          mbar_wait(&o_full[t], (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kFaDh; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tO + t * kFaDh + lane_off + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+          }
+          tc_fence_before();
+          mbar_arrive(&o_empty[t]);
+        }
+        mbar_wait(&p_empty[t], (j & 1) ^ 1);
+        float rowsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kFaBN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + t * kFaBN + lane_off + c, v);
+          tmem_ld_wait();
+          float pr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = (c + i < nk) ? ex2_approx(__uint_as_float(v[i]) * p.scale_log2e - m_new) : 0.f;
+            pr[i] = e;
+            rowsum += e;
+          }
+          uint8_t* slab = prow + (c >> 6) * (kFaPBytes / 2);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(pr[g * 8 + 2 * e], pr[g * 8 + 2 * e + 1]);
+            const int chunk = ((c & 63) >> 3) + g;
+            *reinterpret_cast<uint4*>(slab + ((chunk ^ (r & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);
+        l = l * alpha + rowsum;
+#pragma unroll
+        for (int d = 0; d < kFaDh; ++d) o[d] *= alpha;
+        m = m_new;
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[t]);
+      }
+      mbar_wait(&o_full[t], (J - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kFaDh; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + t * kFaDh + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+      }
+      const int row = q0 + t * kFaBM + r;
+      if (row < p.Sq) {
+        const float inv = 1.f / l;
+        __nv_bfloat16* dst = p.out + (long long)b * p.out_sb + (long long)row * p.out_ss + h * kFaDh;
+#pragma unroll
+        for (int d = 0; d < kFaDh; d += 8) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(o[d + 2 * e] * inv, o[d + 2 * e + 1] * inv);
+          *reinterpret_cast<uint4*>(dst + d) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<kFaTmemCols>(tmem_base);
+  }
+}
+
 }  // namespace u2
 
 extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* vt, void* out,
@@ -301,6 +534,19 @@ extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, 
   a.scale_log2e = d->scale * 1.4426950408889634f;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.out_sb = d->out_sb; a.out_ss = d->out_ss;
+  const bool two_tiles = d->Sq > kFaBM && !getenv("U2_FA_V1");
+  if (two_tiles) {
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(fa_fwd2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFa2Smem);
+      if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "flash_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured2 = true;
+    }
+    dim3 grid2((unsigned)((d->Sq + 2 * kFaBM - 1) / (2 * kFaBM)), (unsigned)d->H, (unsigned)d->B);
+    fa_fwd2_tcgen05_kernel<<<grid2, kFa2Threads, kFa2Smem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+    U2_CHECK_LAUNCH("flash_attention (2 query tiles)");
+    return U2_OK;
+  }
   dim3 grid((unsigned)((d->Sq + kFaBM - 1) / kFaBM), (unsigned)d->H, (unsigned)d->B);
   fa_fwd_tcgen05_kernel<<<grid, kFaThreads, kFaSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   U2_CHECK_LAUNCH("flash_attention");
