@@ -48,6 +48,10 @@ ops.dlinear_multi(chain(2, dbg), gridbar=gridbar[8:12], step_dev=step, lookahead
 d = dbg.view(148, 4, 8).cpu()
 t0 = d[:, 0, 0].min().item()
 rel = (d - t0).float() / 1e3
-names = ["Wpre", "dep ok", "1st full", "last commit", "last acc", "epi done"]
+names = ["Wpre", "dep ok", "1st full", "last commit", "last acc", "epi done", "fin wait", "fin got"]
 for oi, on in enumerate(["o_proj", "gate_up", "down", "qkv"]):
-    print(f"{on:8s} " + " | ".join(f"{n} {rel[:, oi, i].min():.1f}/{rel[:, oi, i].median():.1f}/{rel[:, oi, i].max():.1f}" for i, n in enumerate(names)))
+    print(f"{on:8s} " + " | ".join(f"{n} {rel[:, oi, i].min():.1f}/{rel[:, oi, i].median():.1f}/{rel[:, oi, i].max():.1f}" for i, n in enumerate(names[:6])))
+    fin = d[:, oi, 6] > 0
+    if fin.any():
+        fw, fg, ed = rel[fin, oi, 6], rel[fin, oi, 7], rel[fin, oi, 5]
+        print(f"         finalisers ({int(fin.sum())}): wait-start {fw.min():.1f}/{fw.median():.1f}/{fw.max():.1f} | sums in {fg.min():.1f}/{fg.median():.1f}/{fg.max():.1f} | done {ed.min():.1f}/{ed.median():.1f}/{ed.max():.1f}")

@@ -423,6 +423,47 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           it.tile += it.tile_step;
         }
 
+        // ---- role of this CTA for the tile, and the epilogue operands that do not depend on any partial sum: both
+        //      are resolved BEFORE waiting for the accumulator, so their L2 round trips hide behind the weight stream
+        const int row = tile * kM + trow;  // output row n of W
+        const bool whole = (seg_kb == p.kblocks);  // this CTA sees the entire K range of the tile
+        // Split tile (stream-K only). The CTA whose range contains k-block 0 of the tile finalises it - that
+        // segment is the LAST one of its range - while the CTAs holding the later k-blocks meet the tile as
+        // their FIRST segment: they drop their partial sums into a private slot and move on.
+        int gf = (int)blockIdx.x, n_contrib = 0;
+        if (!whole) {
+          const long long units = (long long)p.num_tiles * p.kblocks;
+          const long long G = units < (long long)gridDim.x ? units : (long long)gridDim.x;
+          const long long u0 = (long long)tile * p.kblocks;
+          gf = (int)(((u0 + 1) * G + units - 1) / units) - 1;
+          n_contrib = (int)(((u0 + p.kblocks) * G + units - 1) / units) - 1 - gf;
+        }
+        const bool finalizer = (gf == (int)blockIdx.x);
+        const int nvec = (p.B + 3) >> 2;
+        const bool row_ok = tvalid && row < p.N;
+        unsigned short res_raw[16];
+        float rs[16];
+        float gam = 0.f;
+        if (finalizer) {
+          if (!prev_done) {
+            // fine-grained mode: ssq / residual / ssq_zero need the WHOLE previous op (long since finished)
+            if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            prev_done = true;
+          }
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            res_raw[b] = 0;
+            rs[b] = 1.f;
+            if (b < p.B) {
+              if (p.residual && !p.silu_pair && row_ok)
+                res_raw[b] = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
+              if (p.ssq_in) rs[b] = __ldcg(p.ssq_in + b);
+            }
+          }
+          if (p.gamma_next && row_ok) gam = __ldg(p.gamma_next + row);
+        }
+
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (et == 0 && it.left == 0) U2_STAMP(oi, 4);  // last accumulator of the op available
         tc_fence_after();
@@ -445,26 +486,9 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           acc_phase ^= 1;
         }
 
-        const int row = tile * kM + trow;  // output row n of W
-        const bool whole = (seg_kb == p.kblocks);  // this CTA saw the entire K range of the tile
         float f[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) f[b] = __uint_as_float(v[b]);
-        // Split tile (stream-K only). The CTA whose range contains k-block 0 of the tile finalises it - that
-        // segment is the LAST one of its range - while the CTAs holding the later k-blocks meet the tile as
-        // their FIRST segment: they drop their partial sums into a private slot (plain vector stores, nothing
-        // to wait for), bump the tile counter with a release and move on.
-        int gf = (int)blockIdx.x, n_contrib = 0;
-        if (!whole) {
-          const long long units = (long long)p.num_tiles * p.kblocks;
-          const long long G = units < (long long)gridDim.x ? units : (long long)gridDim.x;
-          const long long u0 = (long long)tile * p.kblocks;
-          gf = (int)(((u0 + 1) * G + units - 1) / units) - 1;
-          n_contrib = (int)(((u0 + p.kblocks) * G + units - 1) / units) - 1 - gf;
-        }
-        const bool finalizer = (gf == (int)blockIdx.x);
-        const int nvec = (p.B + 3) >> 2;
-        const bool row_ok = tvalid && row < p.N;
         if (!finalizer) {
           const int slot = (int)blockIdx.x - gf - 1;
           float4* dst = reinterpret_cast<float4*>(p.ws + (((long long)tile * p.max_slots + slot) * kM + trow) * kDlN);
@@ -477,30 +501,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           }
         } else {
           // ---------------- this CTA finalises the tile ----------------
-          if (!prev_done) {
-            // fine-grained mode: our MMAs only needed the producing tiles, but ssq / residual / ssq_zero need the
-            // WHOLE previous op: by now that grid barrier has long been passed - this is a formality, not a stall
-            if (et == 0) grid_barrier_wait(mp.gridbar + (oi - 1), target);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            prev_done = true;
-          }
-          // operands of the epilogue that do not depend on the other CTAs' partial sums: request them now so
-          // their L2 round trips overlap the wait for the contributors
-          float res_f[16], rs[16];
-          float gam = 0.f;
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            res_f[b] = 0.f;
-            rs[b] = 1.f;
-            if (b < p.B) {
-              if (p.residual && !p.silu_pair && row_ok) {
-                const unsigned short rr = __ldcg(reinterpret_cast<const unsigned short*>(p.residual) + (long long)b * p.ldr + row);
-                res_f[b] = __bfloat162float(__ushort_as_bfloat16(rr));
-              }
-              if (p.ssq_in) rs[b] = __ldcg(p.ssq_in + b);
-            }
-          }
-          if (p.gamma_next && row_ok) gam = __ldg(p.gamma_next + row);
+          if (et == 0) U2_STAMP(oi, 6);  // finaliser: start waiting for the contributors
           if (n_contrib > 0 && tvalid) {
             // poll the contributors' slots of this row (independent loads, one L2 round trip per sweep); a slot is
             // complete when none of its words is the sentinel; consumed slots are handed back as sentinels
@@ -537,6 +538,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
               }
             }
           }
+          if (et == 0) U2_STAMP(oi, 7);  // finaliser: all partial sums in
           // ---------------- fused epilogue for the finished tile ----------------
           if (p.ssq_zero && tile == 0 && et < 16) p.ssq_zero[et] = 0.f;
           float sq[16];
@@ -555,7 +557,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
                 }
               } else if (row_ok) {
-                val += res_f[b];
+                val += __bfloat162float(__ushort_as_bfloat16(res_raw[b]));
                 if (p.y_dtype == U2_DT_BF16) {
                   const __nv_bfloat16 o = __float2bfloat16(val);
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + row] = o;
