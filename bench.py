@@ -130,7 +130,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-TRAFFIC_NCU = {"dlinear_chain": 431787520}  # profiles/r1_ncu_summary.md (r1_dlinear_chain_full.ncu-rep)
+TRAFFIC_NCU = {"dlinear_chain": 398770688}  # profiles/r1_ncu_summary.md (r1b_dlinear_chain_full.ncu-rep, mean of 2 launches)
 
 
 def measured_peaks():
@@ -460,7 +460,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    prof = os.environ.get("U2_PROFILE_TIMED", "0") != "0"  # ncu --profile-from-start off: capture only the timed region
+    if prof:
+        torch.cuda.profiler.start()
     ms_dev, launches, res = timed(lambda: run(d_images, d_ids, d_q), args.steps)
+    if prof:
+        torch.cuda.profiler.stop()
 
     def e2e_step():
         out = run(h_images.cuda(non_blocking=True), h_ids.cuda(non_blocking=True), h_q.cuda(non_blocking=True))

@@ -95,7 +95,7 @@ class U2Engine:
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
         self.pre_stages = int(os.environ.get("U2_PRE_STAGES", "0"))  # 0 = fill the whole ring before the dependency
         self.l2_lookahead_units = int(os.environ.get("U2_L2_LOOKAHEAD", "0"))  # x16 KB per CTA at op boundaries
-        self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "20"))            # x16 KB per CTA of the next gate|up
+        self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "-1"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
         if geom.attn_type not in ("rma", "rope"):
