@@ -315,6 +315,30 @@ U2_API int u2_sample_f32(const float* logits, int64_t* out, int32_t B, int32_t V
                          int32_t top_k, float top_p, uint64_t seed, const int32_t* step_dev, int32_t step,
                          void* stream);
 
+/* Fused lm_head + selective log-softmax (the DPO / SFT log-probability head) -----------------------------------
+ * logp[r] = log_softmax(hidden[r] . W^T)[labels[r]]  (0 where labels[r] < 0) without materialising the [R, V] logits:
+ * the GEMM's epilogue reduces every 128-column half tile to (max, sum exp, sum) per row, a second small kernel merges
+ * them. Replaces lm_head + `selective_log_softmax(logits, labels)` in u2DPOTrainer.concatenated_forward
+ * (src/train/dpo_u2trainer.py:267-300; [2B, 1024, 151936] logits = 622 MB per pair in bf16) and HF's
+ * ForCausalLMLoss in forward(labels=...) (src/model/language_model/u2llama.py:76-87).
+ * hidden [R, E] bf16 (row stride ldh), W [V, E] bf16 (row stride ldw), labels int64 [R]; optional outputs: lse [R]
+ * (log-sum-exp), logit_sum [R] (sum of the row's V logits: the trainer's mean_*_logits statistics,
+ * dpo_u2trainer.py:343-350), nll_acc [2] (+= sum of -logp and the number of labelled rows; the caller zeroes it).
+ * ws: workspace of u2_logprob_ws_bytes(R, V) bytes, 16-byte aligned. */
+typedef struct u2_logprob_desc {
+  int32_t R, V, E;
+  int64_t ldh, ldw;
+  const int64_t* labels;
+  void* ws;
+  int64_t ws_bytes;
+  float* lse;
+  float* logit_sum;
+  float* nll_acc;
+} u2_logprob_desc;
+U2_API int64_t u2_logprob_ws_bytes(int32_t R, int32_t V);
+U2_API int u2_lmhead_logprob_bf16(const void* hidden, const void* W, float* logp, const u2_logprob_desc* desc,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,3 +392,38 @@ def greedy_generate(sd: SD, input_ids, images, question_ids, cfg, max_new_tokens
                 break
         logits, past = decoder_forward(sd, F.embedding(nxt[:, None], sd["model.embed_tokens.weight"]), cfg, past)
     return torch.stack(out, dim=1), torch.stack(margins, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# log-probability head (training / DPO evaluation side of the decoder output)
+# ------------------------------------------------------------------------------------------------
+def selective_log_softmax(logits: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """`trl.trainer.utils.selective_log_softmax` (third-party trl, pinned `trl==0.9.6` in the reference's
+    requirements.txt:138 although the function only exists in later trl releases; not installed here): the published
+    definition is log_softmax(logits)[index] computed as gather(logits, index) - logsumexp(logits) in fp32.
+    Call site: src/train/dpo_u2trainer.py:296. parity unpinned (no reference test or golden vector holds it)."""
+    logits = logits.float()
+    return logits.gather(-1, index.unsqueeze(-1)).squeeze(-1) - torch.logsumexp(logits, dim=-1)
+
+
+def dpo_per_token_logps(logits: torch.Tensor, input_ids: torch.Tensor, loss_mask: torch.Tensor):
+    """u2DPOTrainer.concatenated_forward, non-padding-free branch (src/train/dpo_u2trainer.py:274-302, 343-350):
+    labels = input_ids rolled left by one, masked positions use the dummy label 0 and contribute 0, the result is rolled
+    back right by one. Returns (per_token_logps [B, L], all_logps [B], mean of the masked rows' logits)."""
+    labels = torch.roll(input_ids, shifts=-1, dims=1)
+    mask = torch.roll(loss_mask, shifts=-1, dims=1).bool()
+    if logits.shape[:2] != labels.shape[:2]:
+        logits = logits[:, -labels.shape[1]:]
+    labels = labels.clone()
+    labels[~mask] = 0
+    ptl = selective_log_softmax(logits, labels)
+    ptl[~mask] = 0
+    ptl = torch.roll(ptl, shifts=1, dims=1)
+    return ptl, ptl.sum(-1), logits.float()[mask].mean()
+
+
+def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """HF ForCausalLMLoss behind forward(labels=...) (u2llama.py:76-87): shift by one, mean NLL over labels != -100."""
+    sl = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
+    tl = labels[:, 1:].reshape(-1)
+    return F.cross_entropy(sl, tl, ignore_index=-100)

@@ -133,6 +133,16 @@ class FaDesc(C.Structure):
     ]
 
 
+class LogprobDesc(C.Structure):
+    """Mirror of ``u2_logprob_desc``."""
+    _fields_ = [
+        ("R", C.c_int32), ("V", C.c_int32), ("E", C.c_int32),
+        ("ldh", C.c_int64), ("ldw", C.c_int64),
+        ("labels", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
+        ("lse", C.c_void_p), ("logit_sum", C.c_void_p), ("nll_acc", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -164,6 +174,8 @@ SIGNATURES = {
     "u2_topk_rows_f32": (C.c_int, [_P, _P, _I, _I, _I, _L, _L, _P]),
     "u2_dlinear_ws_elems": (C.c_int64, [_I, _I]),
     "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "u2_logprob_ws_bytes": (C.c_int64, [_I, _I]),
+    "u2_lmhead_logprob_bf16": (C.c_int, [_P, _P, _P, C.POINTER(LogprobDesc), _P]),
 }
 
 
@@ -190,7 +202,7 @@ def load():
 
 
 # kernels launched per entry point (u2_multiscale_pool_bf16: gate + write, counted at its maximum)
-KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2}
+KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2, "u2_lmhead_logprob_bf16": 2}
 _launches = 0
 
 

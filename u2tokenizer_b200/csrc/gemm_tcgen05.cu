@@ -56,6 +56,11 @@ struct GemmDev {
   int res_row_mod;
   int row_div, row_stride, row_off;
   void* C;
+  // kMode 1 (fused lm_head + log-softmax statistics): nothing of the N-wide result is stored
+  const long long* labels;  // [M], label column per row (< 0: none)
+  float4* part;             // [2 * num_n_blocks][part_ld]: (running max, sum exp(x - max), sum x, -) per row and half tile
+  float* lab_logit;         // [part_ld]: the logit at the label column
+  long long part_ld;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -64,7 +69,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int kBlockN>
+template <int kBlockN, int kMode = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
@@ -206,6 +211,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           p.residual ? p.residual + (p.res_row_mod > 0 ? 0 : zoff) + res_row * p.ldr : nullptr;
 
       const uint32_t taddr = tmem_base + acc * kBlockN + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (kMode == 1) {
+        // log-softmax statistics of this thread's row over its half of the tile's columns; the logits never leave
+        // the SM (reference dpo_u2trainer.py:289-300 materialises [rows, vocab] logits and log-softmaxes them)
+        const long long lab = row_ok ? p.labels[row] : -1;
+        float mx = -INFINITY, se = 0.f, sx = 0.f;
+#pragma unroll 1
+        for (int c0 = half * (kBlockN / 2); c0 < (half + 1) * (kBlockN / 2); c0 += 32) {
+          const int col0 = n_blk * kBlockN + c0;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          tmem_ld_wait();
+          const int nv = min(32, p.N - col0);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]) * p.alpha;
+            v[j] = __float_as_uint(x);
+            if (j < nv) cm = fmaxf(cm, x);
+          }
+          const float nm = fmaxf(mx, cm);
+          const long long ljl = lab - col0;
+          const uint32_t hit = (ljl >= 0 && ljl < nv) ? (1u << (int)ljl) : 0u;  // one-hot of the label column
+          float acc_e = 0.f, acc_x = 0.f, pick = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            if (j < nv) {
+              acc_e += __expf(x - nm);
+              acc_x += x;
+            }
+            pick += (hit >> j) & 1u ? x : 0.f;
+          }
+          se = se * __expf(mx - nm) + acc_e;  // mx == -inf on the first chunk: exp(-inf) == 0
+          sx += acc_x;
+          mx = nm;
+          if (hit) p.lab_logit[row] = pick;
+        }
+        if (row_ok && n_blk * kBlockN + half * (kBlockN / 2) < p.N)
+          p.part[(long long)(n_blk * 2 + half) * p.part_ld + row] = make_float4(mx, se, sx, 0.f);
+      } else {
 #pragma unroll 1
       for (int c0 = half * (kBlockN / 2); c0 < (half + 1) * (kBlockN / 2); c0 += 32) {
         const int col0 = n_blk * kBlockN + c0;
@@ -276,6 +322,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
+      }  // kMode
       // hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -297,13 +344,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kBlockN>
+template <int kBlockN, int kMode = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int num_sms,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kBlockN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kBlockN, kMode>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
@@ -312,13 +359,103 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   const int num_n = (p.N + kBlockN - 1) / kBlockN;
   const long long tiles = (long long)num_m * num_n * p.zi * p.zo;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<kBlockN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<kBlockN, kMode><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return U2_OK;
 }
 
+// Merge of the per-half-tile statistics: one thread per (row, partial group), 8 groups per row.
+//   lse = m + log(sum_p s_p * exp(m_p - m)),  logp = logit[label] - lse
+__global__ void __launch_bounds__(256) logprob_merge_kernel(const float4* __restrict__ part, const float* __restrict__ lab_logit,
+                                                            const long long* __restrict__ labels, int R, int P, long long part_ld,
+                                                            float* __restrict__ logp, float* __restrict__ lse_out,
+                                                            float* __restrict__ logit_sum, float* __restrict__ nll_acc) {
+  __shared__ float s_m[8][32], s_s[8][32], s_x[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 32 + lane;
+  float m = -INFINITY, s = 0.f, x = 0.f;
+  if (r < R) {
+    for (int pi = grp; pi < P; pi += 8) {
+      const float4 v = __ldcs(part + (long long)pi * part_ld + r);
+      const float nm = fmaxf(m, v.x);
+      s = s * __expf(m - nm) + v.y * __expf(v.x - nm);
+      x += v.z;
+      m = nm;
+    }
+  }
+  s_m[grp][lane] = m;
+  s_s[grp][lane] = s;
+  s_x[grp][lane] = x;
+  __syncthreads();
+  if (grp == 0 && r < R) {
+    float gm = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) gm = fmaxf(gm, s_m[g][lane]);
+    float gs = 0.f, gx = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (s_m[g][lane] != -INFINITY) gs += s_s[g][lane] * __expf(s_m[g][lane] - gm);
+      gx += s_x[g][lane];
+    }
+    const float lse = gm + logf(gs);
+    const bool has = labels[r] >= 0;
+    const float lp = has ? lab_logit[r] - lse : 0.f;
+    logp[r] = lp;
+    if (lse_out) lse_out[r] = lse;
+    if (logit_sum) logit_sum[r] = gx;
+    if (nll_acc && has) {
+      atomicAdd(nll_acc, -lp);
+      atomicAdd(nll_acc + 1, 1.f);
+    }
+  }
+}
+
 }  // namespace u2
+
+extern "C" U2_API int64_t u2_logprob_ws_bytes(int32_t R, int32_t V) {
+  if (R <= 0 || V <= 0) return 0;
+  const long long r_pad = ((long long)R + 127) / 128 * 128;
+  const long long P = 2LL * ((V + 255) / 256);
+  return P * r_pad * 16 + r_pad * 4;
+}
+
+extern "C" U2_API int u2_lmhead_logprob_bf16(const void* hidden, const void* W, float* logp, const u2_logprob_desc* d,
+                                             void* stream) {
+  using namespace u2;
+  if (!hidden || !W || !logp || !d || !d->labels || !d->ws) return set_error(U2_ERR_ARG, "lmhead_logprob: null pointer");
+  if (d->R <= 0 || d->V <= 0 || d->E <= 0) return set_error(U2_ERR_ARG, "lmhead_logprob: R, V, E must be > 0");
+  if ((d->ldh & 7) || (d->ldw & 7)) return set_error(U2_ERR_ARG, "lmhead_logprob: row strides must be multiples of 8 elements (16 B, TMA)");
+  if ((reinterpret_cast<uintptr_t>(hidden) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(d->ws) & 15))
+    return set_error(U2_ERR_ARG, "lmhead_logprob: hidden / W / ws must be 16-byte aligned");
+  if (d->ws_bytes < u2_logprob_ws_bytes(d->R, d->V))
+    return set_error(U2_ERR_ARG, "lmhead_logprob: workspace too small (%lld < %lld bytes)", (long long)d->ws_bytes,
+                     (long long)u2_logprob_ws_bytes(d->R, d->V));
+  constexpr int kBn = 256;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_4d(&ta, hidden, d->E, d->R, 1, 1, d->ldh, 0, 0, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_4d(&tb, W, d->E, d->V, 1, 1, d->ldw, 0, 0, kBlockK, kBn);
+  if (rc) return rc;
+  const long long r_pad = ((long long)d->R + 127) / 128 * 128;
+  const int P = 2 * ((d->V + kBn - 1) / kBn);
+  GemmDev p = {};
+  p.M = d->R; p.N = d->V; p.K = d->E;
+  p.zi = 1; p.zo = 1; p.b_zi_div = 1;
+  p.alpha = 1.f;
+  p.labels = reinterpret_cast<const long long*>(d->labels);
+  p.part = reinterpret_cast<float4*>(d->ws);
+  p.lab_logit = reinterpret_cast<float*>(reinterpret_cast<char*>(d->ws) + (long long)P * r_pad * 16);
+  p.part_ld = r_pad;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  rc = launch_gemm<kBn, 1>(ta, tb, p, num_sms(), s);
+  if (rc) return rc;
+  logprob_merge_kernel<<<(unsigned)((d->R + 31) / 32), 256, 0, s>>>(p.part, p.lab_logit, p.labels, d->R, P, r_pad, logp, d->lse,
+                                                                    d->logit_sum, d->nll_acc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "lmhead_logprob merge launch: %s", cudaGetErrorString(e));
+  return U2_OK;
+}
 
 extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const u2_gemm_desc* d, void* stream) {
   using namespace u2;
@@ -353,7 +490,7 @@ extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const 
   rc = make_tmap_bf16_4d(&tb, B, d->K, d->N, zi_b, zo, d->ldb, zi_b > 1 ? d->b_stride_zi : 0, zo > 1 ? d->b_stride_zo : 0, kBlockK, block_n);
   if (rc) return rc;
 
-  GemmDev p;
+  GemmDev p = {};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.zi = zi; p.zo = zo; p.b_zi_div = bdiv;
   p.ldc = d->ldc; p.c_stride_zi = d->c_stride_zi; p.c_stride_zo = d->c_stride_zo;

@@ -499,6 +499,20 @@ class U2Engine:
         """lm_head over [.., E] hidden states -> [.., V] logits."""
         return ops.linear(hidden, self.lm_head, out_dtype=out_dtype)
 
+    def token_logps(self, hidden: torch.Tensor, labels: torch.Tensor, *, want_lse=False, want_logit_sum=False,
+                    nll_acc: Optional[torch.Tensor] = None):
+        """log_softmax(lm_head(hidden))[labels] per position without materialising the [.., V] logits
+        (reference: lm_head + trl selective_log_softmax, src/train/dpo_u2trainer.py:267-300). hidden [.., E] bf16,
+        labels [..] int64 (< 0: ignored, log-probability 0). Returns (logp, lse or None, logit_sum or None), fp32 [..]."""
+        shp = labels.shape
+        h2 = hidden.reshape(-1, hidden.shape[-1])
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        logp, lse, lsum = ops.lmhead_logprob(h2, self.lm_head, labels.reshape(-1).contiguous(), want_lse=want_lse,
+                                             want_logit_sum=want_logit_sum, nll_acc=nll_acc)
+        rs = lambda t: None if t is None else t.view(shp)
+        return rs(logp), rs(lse), rs(lsum)
+
     # =========================================================================================
     # decoder: one KV-cached decode step (weight streaming)
     # =========================================================================================

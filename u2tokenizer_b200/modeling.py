@@ -261,13 +261,38 @@ class U2MetaForCausalLM(ABC):
         logits = eng.lm_logits(hidden)
         loss = None
         if labels is not None:
-            # HF ForCausalLMLoss: shift, mean over non-ignored positions (training head; not a hot-path kernel yet)
-            shift_logits = logits[:, :-1].reshape(-1, logits.shape[-1]).float()
-            shift_labels = labels[:, 1:].reshape(-1).to(shift_logits.device)
-            loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
+            # HF ForCausalLMLoss (shift by one, mean NLL over labels != -100) on the fused lm_head + log-softmax head:
+            # the loss never reads the [B, L, V] logits
+            acc = torch.zeros(2, device=hidden.device, dtype=torch.float32)
+            shift = labels[:, 1:].to(hidden.device, torch.int64).contiguous()
+            eng.token_logps(hidden[:, :-1], shift, nll_acc=acc)
+            loss = acc[0] / acc[1]
         if return_dict is False:
             return (loss, logits) if loss is not None else (logits,)
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None)
+
+    @torch.no_grad()
+    def per_token_logps(self, images=None, input_ids=None, question_ids=None, loss_mask=None, attention_mask=None):
+        """The log-probability side of `u2DPOTrainer.concatenated_forward` (reference src/train/dpo_u2trainer.py:267-302,
+        343-350) without the [B, L, V] logits: labels are `input_ids` rolled left by one, positions whose rolled
+        `loss_mask` is 0 contribute 0, the result is rolled back right by one. Returns a dict with `per_token_logps`
+        [B, L] fp32, `all_logps` [B] and `mean_logits` (mean of the masked rows' logits, as the trainer logs it)."""
+        eng = self.engine()
+        (_, _, _, _, inputs_embeds, _) = self.prepare_inputs_for_multimodal(input_ids, None, attention_mask, None, None,
+                                                                            images, question_ids)
+        if inputs_embeds is None:
+            inputs_embeds = eng.embed_tokens(input_ids)
+        hidden = eng.prefill(inputs_embeds.to(torch.bfloat16))
+        ids = input_ids.to(hidden.device, torch.int64)
+        if loss_mask is None:
+            loss_mask = torch.ones_like(ids)
+        labels = torch.roll(ids, shifts=-1, dims=1)
+        mask = torch.roll(loss_mask.to(hidden.device), shifts=-1, dims=1).bool()
+        labels = labels.masked_fill(~mask, -1)
+        logp, _, lsum = eng.token_logps(hidden, labels, want_logit_sum=True)
+        ptl = torch.roll(logp, shifts=1, dims=1)
+        n = mask.sum().clamp(min=1) * eng.g.vocab_size
+        return {"per_token_logps": ptl, "all_logps": ptl.sum(-1), "mean_logits": (lsum * mask).sum() / n}
 
     @torch.no_grad()
     def _u2_generate(self, images=None, inputs=None, question_ids=None, **kwargs):

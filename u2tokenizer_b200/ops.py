@@ -467,3 +467,33 @@ def sample(logits: torch.Tensor, out: Optional[torch.Tensor] = None, *, temperat
                                          int(top_k), float(top_p), int(seed) & ((1 << 64) - 1), _ptr(step_dev),
                                          int(step), _stream()), "u2_sample_f32")
     return out
+
+
+def lmhead_logprob(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, *, want_lse: bool = False,
+                   want_logit_sum: bool = False, nll_acc: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None):
+    """logp[r] = log_softmax(hidden[r] @ weight.T)[labels[r]] (0 where labels[r] < 0) without materialising the logits.
+    hidden [R, E] bf16, weight [V, E] bf16, labels [R] int64. Returns (logp fp32 [R], lse or None, logit_sum or None).
+    nll_acc: optional fp32 [2] accumulator (+= sum(-logp), += number of labelled rows)."""
+    _need_cuda(hidden, weight, labels, nll_acc, ws)
+    R, E = hidden.shape
+    V = weight.shape[0]
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or labels.dtype != torch.int64:
+        raise TypeError("lmhead_logprob: hidden / weight must be bf16, labels int64")
+    if weight.shape[1] != E or labels.shape != (R,) or hidden.stride(1) != 1 or weight.stride(1) != 1 or not labels.is_contiguous():
+        raise ValueError("lmhead_logprob: shape / stride mismatch")
+    lib = _lib.load()
+    need = int(lib.u2_logprob_ws_bytes(R, V))
+    if ws is None:
+        ws = torch.empty(need, device=hidden.device, dtype=torch.uint8)
+    elif ws.numel() * ws.element_size() < need:
+        raise ValueError(f"lmhead_logprob: workspace of {need} bytes required")
+    logp = torch.empty(R, device=hidden.device, dtype=torch.float32)
+    lse = torch.empty(R, device=hidden.device, dtype=torch.float32) if want_lse else None
+    lsum = torch.empty(R, device=hidden.device, dtype=torch.float32) if want_logit_sum else None
+    d = _lib.LogprobDesc()
+    d.R, d.V, d.E, d.ldh, d.ldw = R, V, E, hidden.stride(0), weight.stride(0)
+    d.labels, d.ws, d.ws_bytes = labels.data_ptr(), ws.data_ptr(), ws.numel() * ws.element_size()
+    d.lse, d.logit_sum, d.nll_acc = _ptr(lse), _ptr(lsum), _ptr(nll_acc)
+    _lib.check(lib.u2_lmhead_logprob_bf16(hidden.data_ptr(), weight.data_ptr(), logp.data_ptr(), C.byref(d), _stream()),
+               "u2_lmhead_logprob_bf16")
+    return logp, lse, lsum
