@@ -101,3 +101,29 @@ def test_sampled_generate_surface():
     tiny_nucleus = model.generate(images.cuda(), ids.cuda(), question_ids=qids.cuda(), max_new_tokens=8, do_sample=True,
                                   top_p=1e-6, temperature=1.0, seed=5).cpu()
     assert torch.equal(tiny_nucleus, greedy)
+
+
+def test_multi_sample_generate_shares_the_prefill():
+    """generate(do_sample=True, num_return_sequences=n): one vision + prefill pass, the prompt's KV rows replicated into
+    the decode cache (the reference's DPO-data workflow draws its 8 samples per study with separate full passes,
+    green_refactored/pred_then_green.py:77-83). HF row order: row b*n + s is sample s of prompt b."""
+    model, g, sd = make("qwen3")
+    images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12)
+    args = (images.cuda(), ids.cuda())
+    greedy = model.generate(*args, question_ids=qids.cuda(), max_new_tokens=7, do_sample=False).cpu()
+    # a single-token nucleus makes every sample the greedy continuation: checks the replicated KV rows exactly,
+    # including the 16-sequence chunking of the decode batch (2 prompts x 9 samples = 16 + 2 rows)
+    for n in (3, 9):
+        out = model.generate(*args, question_ids=qids.cuda(), max_new_tokens=7, do_sample=True, top_p=1e-6,
+                             num_return_sequences=n, seed=3).cpu()
+        assert out.shape == (2 * n, 7)
+        assert torch.equal(out, greedy.repeat_interleave(n, dim=0))
+    kw = dict(question_ids=qids.cuda(), max_new_tokens=7, do_sample=True, top_p=0.98, temperature=2.0, num_return_sequences=4)
+    a = model.generate(*args, seed=21, **kw).cpu()
+    b = model.generate(*args, seed=21, **kw).cpu()
+    c = model.generate(*args, seed=22, **kw).cpu()
+    assert a.shape == (8, 7) and torch.equal(a, b) and not torch.equal(a, c)
+    assert len({tuple(r.tolist()) for r in a[:4]}) > 1      # the samples of one prompt are distinct draws
+    assert int(a.min()) >= 0 and int(a.max()) < g.vocab_size
+    with pytest.raises(ValueError):
+        model.generate(*args, question_ids=qids.cuda(), max_new_tokens=4, do_sample=False, num_return_sequences=2)

@@ -520,6 +520,8 @@ class U2Engine:
         g = self.g
         key = ("dec", B)
         if getattr(self, "_dec_key", None) != key:
+            if getattr(self, "_gen_state", None) is not None:
+                self._gen_state["graph"] = None  # a captured step points at the buffers that are about to be replaced
             hq, hkv, dh, I, E = g.num_attention_heads, g.num_key_value_heads, g.head_dim, g.intermediate_size, g.hidden_size
             d = self.dev
             self._dec = dict(
@@ -646,37 +648,80 @@ class U2Engine:
     # =========================================================================================
     @torch.no_grad()
     def generate(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None, do_sample: bool = False,
-                 temperature: float = 1.0, top_k: int = 50, top_p: float = 1.0, seed: int = 0, use_graph: bool = True):
-        """Greedy (do_sample=False) or sampled decoding; same loop, only the token-picking head differs."""
+                 temperature: float = 1.0, top_k: int = 50, top_p: float = 1.0, seed: int = 0, use_graph: bool = True,
+                 num_return_sequences: int = 1):
+        """Greedy (do_sample=False) or sampled decoding; same loop, only the token-picking head differs.
+        num_return_sequences > 1 (HF semantics: row b * n + s is sample s of prompt b) shares ONE vision + prefill pass:
+        the prompt's KV rows are replicated into the decode cache (the reference's DPO-data workflow draws 8 samples per
+        study by re-running the whole model per sample, green_refactored/pred_then_green.py:77-83)."""
         self._sampling = dict(temperature=float(temperature), top_k=int(top_k or 0), top_p=float(top_p),
                               seed=int(seed)) if do_sample else None
         try:
+            if num_return_sequences > 1:
+                return self._generate_multi(embeds, max_new_tokens, eos_token_id, use_graph, int(num_return_sequences))
             return self.generate_greedy(embeds, max_new_tokens, eos_token_id=eos_token_id, use_graph=use_graph)
         finally:
             self._sampling = None
+
+    def _gen_state_for(self, B: int, cap: int):
+        """The static KV cache and the captured decode-step graph are kept across calls with the same (batch, capacity,
+        head configuration): capture + instantiation cost ~0.1 s, which would otherwise be paid per request."""
+        key = (B, cap, self.decode_impl, self.multi_op, self.fine_deps,
+               tuple(sorted(self._sampling.items())) if self._sampling else None)
+        st = self._gen_state if (self._gen_state is not None and self._gen_state["key"] == key) else None
+        if st is None:
+            self._gen_state = None  # drop the old cache before allocating the new one
+            st = dict(key=key, cache=self.new_cache(B, cap), graph=None, n_graph=0)
+            self._gen_state = st
+        return st
 
     def generate_greedy(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None,
                         use_graph: bool = True, return_margins: bool = False):
         """Prefill on `embeds` [B, L, E], then max_new_tokens decode steps (greedy unless a sampling configuration
         was installed by generate()). Returns new ids [B, n] (and the per-step top-1/top-2 logit margins when
         asked, for margin-aware parity checks)."""
-        from . import _lib
         B, L, _ = embeds.shape
-        # the static KV cache and the captured decode-step graph are kept across calls with the same
-        # (batch, capacity): capture + instantiation cost ~0.1 s, which would otherwise be paid per request
-        key = (B, L + max_new_tokens, self.decode_impl, self.multi_op, self.fine_deps,
-               tuple(sorted(self._sampling.items())) if self._sampling else None)
-        st = self._gen_state if (self._gen_state is not None and self._gen_state["key"] == key) else None
-        if st is None:
-            self._gen_state = None  # drop the old cache before allocating the new one
-            st = dict(key=key, cache=self.new_cache(B, L + max_new_tokens), graph=None, n_graph=0)
-            self._gen_state = st
+        st = self._gen_state_for(B, L + max_new_tokens)
         cache = st["cache"]
         cache.set_length(0)
         hidden = self.prefill(embeds, cache)
+        logits0 = self.lm_logits(hidden[:, -1].contiguous())
+        return self._decode_loop(st, logits0, max_new_tokens, eos_token_id, use_graph, return_margins)
+
+    def _generate_multi(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id, use_graph: bool, n: int):
+        B, L, _ = embeds.shape
+        pc = self.new_cache(B, L)
+        hidden = self.prefill(embeds, pc)
+        logits0 = self.lm_logits(hidden[:, -1].contiguous())
+        rows = B * n
+        chunk = 16 if self._use_tc_decode(16) else 8  # sequences one decode step can carry (dlinear N / gemv batch)
+        base = dict(self._sampling) if self._sampling else None
+        outs = []
+        for ci, c0 in enumerate(range(0, rows, chunk)):
+            src = torch.arange(c0, min(rows, c0 + chunk), device=self.dev) // n  # prompt of every row of this chunk
+            if base is not None:  # distinct random streams per chunk (the sampler keys its stream by (seed, step, row))
+                self._sampling = dict(base, seed=(base["seed"] + 0x9E3779B97F4A7C15 * ci) & ((1 << 64) - 1))
+            st = self._gen_state_for(int(src.numel()), L + max_new_tokens)
+            cache = st["cache"]
+            cache.k[:, :, :, :L].copy_(pc.k.index_select(1, src))
+            cache.v[:, :, :, :L].copy_(pc.v.index_select(1, src))
+            cache.set_length(L)
+            outs.append(self._decode_loop(st, logits0.index_select(0, src), max_new_tokens, eos_token_id, use_graph, False))
+        width = max(o.shape[1] for o in outs)
+        if any(o.shape[1] != width for o in outs):  # chunks that hit EOS early: pad with EOS (masked by the caller)
+            fill = eos_token_id[0] if isinstance(eos_token_id, (list, tuple)) else eos_token_id
+            outs = [torch.nn.functional.pad(o, (0, width - o.shape[1]), value=int(fill)) for o in outs]
+        return torch.cat(outs, dim=0)
+
+    def _decode_loop(self, st, logits0: torch.Tensor, max_new_tokens: int, eos_token_id, use_graph: bool,
+                     return_margins: bool):
+        """Pick the first token from `logits0`, then run max_new_tokens - 1 decode steps on st['cache'] (whose length
+        is the prompt length); the steps after the first replay one captured CUDA graph."""
+        from . import _lib
+        cache = st["cache"]
+        B = cache.batch
         bufs = self._decode_buffers(B)
         self.reset_decode_state(B)
-        logits0 = self.lm_logits(hidden[:, -1].contiguous())
         out = torch.empty(B, max_new_tokens, device=self.dev, dtype=torch.int64)
         margins = []
         self._pick_next(logits0, bufs["ids"].view(B), None, step=0)

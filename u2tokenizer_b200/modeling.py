@@ -339,8 +339,12 @@ class U2MetaForCausalLM(ABC):
         pad = kwargs.pop("pad_token_id", None)
         if pad is None and gc is not None:
             pad = gc.pad_token_id
+        n_ret = int(opt("num_return_sequences", 1))
+        if n_ret > 1 and not do_sample:
+            raise ValueError("num_return_sequences > 1 needs do_sample=True (greedy decoding is deterministic; HF raises too)")
         ids = eng.generate(inputs_embeds.to(torch.bfloat16), max_new_tokens=max_new, eos_token_id=eos,
-                           do_sample=bool(do_sample), temperature=temperature, top_k=top_k, top_p=top_p, seed=seed)
+                           do_sample=bool(do_sample), temperature=temperature, top_k=top_k, top_p=top_p, seed=seed,
+                           num_return_sequences=n_ret)
         if eos is not None:
             eos_t = torch.as_tensor(eos if isinstance(eos, (list, tuple)) else [eos], device=ids.device)
             hit = torch.isin(ids, eos_t)
