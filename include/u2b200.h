@@ -281,6 +281,8 @@ typedef struct u2_fused_decode_desc {
   float eps;
   const float* inv_freq;
   float scale;
+  int32_t kv_splits;   /* 0/1: one CTA per (sequence, KV head); 2/4/8: a cluster of that many CTAs splits the cached
+                          keys and merges over distributed shared memory (fills the SMs when B * Hkv is small) */
 } u2_fused_decode_desc;
 U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_cache, void* v_cache, void* out,
                                           const u2_fused_decode_desc* desc, void* stream);

@@ -329,10 +329,23 @@ def test_decode_embed():
 @pytest.mark.parametrize("dh,Hq,Hkv", [(128, 32, 8), (128, 16, 8), (64, 32, 8), (32, 4, 2), (64, 8, 8)])
 @pytest.mark.parametrize("pos", [0, 5, 290, 543])
 @pytest.mark.parametrize("qk_norm", [True, False])
-def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
-    """Fused q/k-norm + RoPE + cache append + attention vs the unfused kernels' arithmetic in fp32 torch."""
+@pytest.mark.parametrize("splits", [1, 4])
+def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm, splits):
+    """Fused q/k-norm + RoPE + cache append + attention vs the unfused kernels' arithmetic in fp32 torch
+    (splits > 1: the split-KV cluster variant, partial results merged over distributed shared memory)."""
+    _check_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm, splits, Tmax=600)
+
+
+@pytest.mark.parametrize("splits,pos,Tmax", [(2, 1100, 1200), (8, 3, 64), (8, 2500, 2600), (2, 31, 600), (4, 1024, 1200)])
+@pytest.mark.parametrize("dh,Hq,Hkv", [(128, 32, 8), (64, 8, 8), (32, 4, 2)])
+def test_decode_attention_fused_split_rounds(dh, Hq, Hkv, splits, pos, Tmax):
+    """More keys than one round of the cluster covers (S x 256), fewer keys than CTAs, group boundaries."""
+    _check_decode_attention_fused(dh, Hq, Hkv, pos, True, splits, Tmax=Tmax)
+
+
+def _check_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm, splits, Tmax):
     from u2tokenizer_b200 import ops
-    B, Tmax = 3, 600
+    B = 3
     g = gen(dh * 7 + pos + Hq)
     ld = (Hq + 2 * Hkv) * dh
     qkv = torch.randn(B, ld, device=DEV, generator=g).bfloat16()
@@ -345,7 +358,7 @@ def test_decode_attention_fused(dh, Hq, Hkv, pos, qk_norm):
     out = torch.empty(B, Hq * dh, device=DEV, dtype=torch.bfloat16)
     pd = torch.tensor([pos], device=DEV, dtype=torch.int32)
     ops.decode_attention_fused(qkv, kc, vc, out, B=B, Hq=Hq, Hkv=Hkv, dh=dh, Tmax=Tmax, inv_freq=inv,
-                               scale=1 / math.sqrt(dh), pos_dev=pd, q_norm_w=qw, k_norm_w=kw, eps=1e-6)
+                               scale=1 / math.sqrt(dh), pos_dev=pd, q_norm_w=qw, k_norm_w=kw, eps=1e-6, kv_splits=splits)
     t = qkv.float().view(B, Hq + 2 * Hkv, dh)
     q, k, v = t[:, :Hq], t[:, Hq:Hq + Hkv], t[:, Hq + Hkv:]
     if qk_norm:

@@ -4,6 +4,7 @@
 //   rope / qk_norm_rope rotate-half RoPE (optionally per-head RMSNorm first: Qwen3) applied in place
 //                       on a fused QKV buffer, and the KV-cache append of the decoder
 //   decode_attention    one query token against the KV cache (HBM-bound, GQA)
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -525,8 +526,243 @@ fused_decode_attention_kernel(const FusedDecodeArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-KV variant: a cluster of S CTAs shares one (sequence, KV head); the 32-key groups of the cache are dealt
+// round-robin to the S x 8 warps, so that for up to S*256 cached keys every warp owns ONE group and the whole K/V
+// read is a single round trip. The group's K row (lane == key) and V slices (lane == head-dim slice, all 32 rows)
+// are requested BEFORE the new token's norm / RoPE work, which depends on nothing in the cache; the new token's own
+// k / v never go through global memory (every CTA recomputes them into shared memory, rank 0 appends them to the
+// cache). CTA partials (m, l, o) are merged by rank 0 over distributed shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int kDh, int kG>
+__global__ void __launch_bounds__(256)
+fused_decode_attention_split_kernel(const FusedDecodeArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int kW = 8;
+  constexpr int kEpl = kDh / 32;           // head_dim elements per lane in the PV phase
+  constexpr int kVw = (kEpl + 1) / 2;      // 32-bit words holding one V row slice
+  const int S = (int)gridDim.z, rank = (int)blockIdx.z;  // the cluster spans the grid's z extent
+  const int hk = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pos = a.pos_dev ? *a.pos_dev : a.pos_host;
+  const int T = min(pos + 1, a.Tmax);
+  __shared__ __align__(16) float s_q[kG][kDh];
+  __shared__ __align__(16) __nv_bfloat16 s_knew[kDh];
+  __shared__ __align__(16) __nv_bfloat16 s_vnew[kDh];
+  __shared__ float s_m[kW][kG], s_l[kW][kG];
+  __shared__ float s_acc[kW][kG][kDh];
+  __shared__ float c_m[kG], c_l[kG];
+  __shared__ __align__(16) float c_o[kG][kDh];
+
+  const __nv_bfloat16* row = a.qkv + (long long)b * a.ldq;
+  __nv_bfloat16* kbase = a.kc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
+  __nv_bfloat16* vbase = a.vc + ((long long)b * a.Hkv + hk) * a.Tmax * kDh;
+
+  // ---- request this warp's first key group (rows >= pos are stale: they are replaced from shared memory below)
+  uint4 ku[kDh / 8];
+  uint32_t vw[32][kVw];
+  int t0 = (warp * S + rank) * 32;
+  auto request = [&](int base) {
+    const int t = min(base + lane, T - 1);
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)t * kDh);
+#pragma unroll
+    for (int c = 0; c < kDh / 8; ++c) ku[c] = kr[c];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int tj = min(base + jj, T - 1);
+      const __nv_bfloat16* vp = vbase + (long long)tj * kDh + lane * kEpl;
+      if constexpr (kEpl == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(vp);
+        vw[jj][0] = u.x;
+        vw[jj][1] = u.y;
+      } else if constexpr (kEpl == 2) {
+        vw[jj][0] = *reinterpret_cast<const uint32_t*>(vp);
+      } else {
+        vw[jj][0] = *reinterpret_cast<const unsigned short*>(vp);
+      }
+    }
+  };
+  if (t0 < T) request(t0);
+
+  // ---- phase A: G query heads (norm + rope -> smem), new k (norm + rope) and new v -> smem (+ cache on rank 0)
+  for (int job = warp; job < kG + 2; job += kW) {
+    if (job == kG) {
+      norm_rope_head<kDh>(row + (long long)(a.Hq + hk) * kDh, a.k_norm_w, a.eps, a.inv_freq, pos, 1.f, nullptr, s_knew, lane);
+      __syncwarp();
+      if (rank == 0)
+        for (int e = lane; e < kDh; e += 32) kbase[(long long)pos * kDh + e] = s_knew[e];
+    } else if (job == kG + 1) {
+      const __nv_bfloat16* v = row + (long long)(a.Hq + a.Hkv + hk) * kDh;
+      for (int e = lane; e < kDh; e += 32) {
+        const __nv_bfloat16 x = v[e];
+        s_vnew[e] = x;
+        if (rank == 0) vbase[(long long)pos * kDh + e] = x;
+      }
+    } else {
+      norm_rope_head<kDh>(row + (long long)(hk * kG + job) * kDh, a.q_norm_w, a.eps, a.inv_freq, pos, a.scale, s_q[job],
+                          nullptr, lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: online softmax over this warp's groups
+  float m[kG], l[kG], acc[kG][kEpl];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    m[g] = -INFINITY;
+    l[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) acc[g][i] = 0.f;
+  }
+  while (t0 < T) {
+    const int t = t0 + lane;
+    if (t == pos) {  // the new token's key: from shared memory, not from the cache
+#pragma unroll
+      for (int c = 0; c < kDh / 8; ++c) ku[c] = reinterpret_cast<const uint4*>(s_knew)[c];
+    }
+    float s[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) s[g] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kDh / 8; ++c) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ku[c]);
+      float kf[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = __bfloat1622float2(h2[j]);
+        kf[2 * j] = f2.x;
+        kf[2 * j + 1] = f2.y;
+      }
+#pragma unroll
+      for (int g = 0; g < kG; ++g) {
+        const float4 q0 = *reinterpret_cast<const float4*>(&s_q[g][c * 8]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&s_q[g][c * 8 + 4]);
+        s[g] += kf[0] * q0.x + kf[1] * q0.y + kf[2] * q0.z + kf[3] * q0.w + kf[4] * q1.x + kf[5] * q1.y + kf[6] * q1.z +
+                kf[7] * q1.w;
+      }
+    }
+    float p[kG];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      if (t >= T) s[g] = -INFINITY;
+      const float mx = fmaxf(m[g], wmax(s[g]));  // lane 0 of every group is a valid key: mx is finite
+      const float corr = __expf(m[g] - mx);
+      p[g] = (t < T) ? __expf(s[g] - mx) : 0.f;
+      l[g] = l[g] * corr + wsum(p[g]);
+#pragma unroll
+      for (int i = 0; i < kEpl; ++i) acc[g][i] *= corr;
+      m[g] = mx;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      float vf[kEpl];
+      if (t0 + jj == pos) {  // warp-uniform
+#pragma unroll
+        for (int i = 0; i < kEpl; ++i) vf[i] = __bfloat162float(s_vnew[lane * kEpl + i]);
+      } else if constexpr (kEpl == 4) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[jj][0]));
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[jj][1]));
+        vf[0] = x.x; vf[1] = x.y; vf[2] = y.x; vf[3] = y.y;
+      } else if constexpr (kEpl == 2) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vw[jj][0]));
+        vf[0] = x.x; vf[1] = x.y;
+      } else {
+        vf[0] = __uint_as_float(vw[jj][0] << 16);
+      }
+#pragma unroll
+      for (int g = 0; g < kG; ++g) {
+        const float pj = __shfl_sync(0xffffffffu, p[g], jj);  // rows past T carry probability 0
+#pragma unroll
+        for (int i = 0; i < kEpl; ++i) acc[g][i] += pj * vf[i];
+      }
+    }
+    t0 += S * kW * 32;
+    if (t0 < T) request(t0);
+  }
+  // ---- merge the warps of this CTA
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    if (lane == 0) {
+      s_m[warp][g] = m[g];
+      s_l[warp][g] = l[g];
+    }
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) s_acc[warp][g][lane * kEpl + i] = acc[g][i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kG * kDh; idx += blockDim.x) {
+    const int g = idx / kDh, e = idx - g * kDh;
+    float gm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) gm = fmaxf(gm, s_m[w][g]);
+    float gl = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      if (s_m[w][g] != -INFINITY) {
+        const float f = __expf(s_m[w][g] - gm);
+        gl += s_l[w][g] * f;
+        o += s_acc[w][g][e] * f;
+      }
+    }
+    c_o[g][e] = o;
+    if (e == 0) {
+      c_m[g] = gm;
+      c_l[g] = gl;
+    }
+  }
+  // ---- merge the CTAs of the cluster on rank 0 (distributed shared memory)
+  cluster.sync();
+  if (rank == 0) {
+    for (int idx = threadIdx.x; idx < kG * kDh; idx += blockDim.x) {
+      const int g = idx / kDh, e = idx - g * kDh;
+      float gm = -INFINITY;
+      for (int r = 0; r < S; ++r) gm = fmaxf(gm, *cluster.map_shared_rank(&c_m[g], r));
+      float gl = 0.f, o = 0.f;
+      for (int r = 0; r < S; ++r) {
+        const float mr = *cluster.map_shared_rank(&c_m[g], r);
+        if (mr != -INFINITY) {
+          const float f = __expf(mr - gm);
+          gl += *cluster.map_shared_rank(&c_l[g], r) * f;
+          o += *cluster.map_shared_rank(&c_o[g][e], r) * f;
+        }
+      }
+      a.out[(long long)b * a.ldo + (long long)(hk * kG + g) * kDh + e] = __float2bfloat16(o / gl);
+    }
+  }
+  cluster.sync();  // the other ranks' shared memory must outlive rank 0's reads
+}
+
+template <int kDh, int kG>
+static int launch_fused_decode_split(const FusedDecodeArgs& a, dim3 grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = grid.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fused_decode_attention_split_kernel<kDh, kG>, a);
+  if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "decode_attention_fused (split-KV) launch: %s", cudaGetErrorString(e));
+  return U2_OK;
+}
+
 template <int kDh>
 static int launch_fused_decode(const FusedDecodeArgs& a, int G, dim3 grid, cudaStream_t st) {
+  if (grid.z > 1) {
+    switch (G) {
+      case 1: return launch_fused_decode_split<kDh, 1>(a, grid, st);
+      case 2: return launch_fused_decode_split<kDh, 2>(a, grid, st);
+      case 4: return launch_fused_decode_split<kDh, 4>(a, grid, st);
+      case 8: return launch_fused_decode_split<kDh, 8>(a, grid, st);
+      default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: Hq/Hkv = %d (supported 1, 2, 4, 8)", G);
+    }
+  }
   switch (G) {
     case 1: fused_decode_attention_kernel<kDh, 1><<<grid, FaCfg<kDh, 1>::kWarps * 32, 0, st>>>(a); break;
     case 2: fused_decode_attention_kernel<kDh, 2><<<grid, FaCfg<kDh, 2>::kWarps * 32, 0, st>>>(a); break;
@@ -554,7 +790,10 @@ extern "C" U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_ca
   a.pos_dev = d->pos_dev; a.pos_host = d->pos;
   a.q_norm_w = d->q_norm_w; a.k_norm_w = d->k_norm_w; a.eps = d->eps;
   a.inv_freq = d->inv_freq; a.scale = d->scale;
-  dim3 grid((unsigned)d->Hkv, (unsigned)d->B);
+  const int splits = d->kv_splits > 1 ? d->kv_splits : 1;
+  if (splits != 1 && splits != 2 && splits != 4 && splits != 8)
+    return set_error(U2_ERR_ARG, "decode_attention_fused: kv_splits must be 0/1, 2, 4 or 8 (portable cluster sizes)");
+  dim3 grid((unsigned)d->Hkv, (unsigned)d->B, (unsigned)splits);
   const int G = d->Hq / d->Hkv;
   int rc;
   switch (d->dh) {

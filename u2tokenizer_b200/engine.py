@@ -88,6 +88,8 @@ class U2Engine:
         self.attn_ws = attn_workspace_bytes
         self.decode_impl = decode_impl  # "tcgen05" (stream-K tensor-core linears) or "gemv" (CUDA-core GEMV)
         import os
+        from . import _lib
+        self.num_sms = int(_lib.load().u2_device_sm_count())
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
@@ -551,6 +553,19 @@ class U2Engine:
             bufs[k].zero_()
         bufs["ws"].view(torch.int32).fill_(-1)  # "empty slot" sentinel
 
+    def _kv_splits(self, B: int) -> int:
+        """CTAs per (sequence, KV head) in the decode attention: fill the SMs when B * Hkv is small
+        (cfg 3: 4 * 8 = 32 pairs -> clusters of 4 = 128 CTAs). U2_ATTN_SPLIT=0/1 disables, 2/4/8 forces."""
+        import os
+        env = os.environ.get("U2_ATTN_SPLIT", "auto")
+        if env != "auto":
+            return max(1, int(env))
+        pairs = B * self.g.num_key_value_heads
+        s = 8
+        while s > 1 and pairs * s > max(self.num_sms, pairs):
+            s //= 2
+        return s
+
     def _use_tc_decode(self, B: int) -> bool:
         g = self.g
         dims = (g.hidden_size, g.intermediate_size, g.num_attention_heads * g.head_dim)
@@ -576,7 +591,7 @@ class U2Engine:
         for li, w in enumerate(self.layers):
             ops.decode_attention_fused(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
                                        inv_freq=self.inv_freq, scale=1.0 / math.sqrt(dh), pos_dev=cache.length_dev,
-                                       q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps)
+                                       q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps, kv_splits=self._kv_splits(B))
             last = li + 1 == nl
             g_next = self.final_norm if last else self.layers[li + 1]["ln1"]
             fl = flags[li] if (self.multi_op and self.fine_deps) else [None] * 4
