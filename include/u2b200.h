@@ -283,6 +283,8 @@ typedef struct u2_fused_decode_desc {
   float scale;
   int32_t kv_splits;   /* 0/1: one CTA per (sequence, KV head); 2/4/8: a cluster of that many CTAs splits the cached
                           keys and merges over distributed shared memory (fills the SMs when B * Hkv is small) */
+  int32_t pdl;         /* != 0 (split-KV variant only): launch with programmatic stream serialisation - position read
+                          and K/V prefetch overlap the tail of the preceding kernel, which must not write the cache */
 } u2_fused_decode_desc;
 U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_cache, void* v_cache, void* out,
                                           const u2_fused_decode_desc* desc, void* stream);

@@ -107,7 +107,7 @@ class FusedDecodeDesc(C.Structure):
         ("eps", C.c_float),
         ("inv_freq", C.c_void_p),
         ("scale", C.c_float),
-        ("kv_splits", C.c_int32),
+        ("kv_splits", C.c_int32), ("pdl", C.c_int32),
     ]
 
 

@@ -545,6 +545,10 @@ fused_decode_attention_split_kernel(const FusedDecodeArgs a) {
   const int S = (int)gridDim.z, rank = (int)blockIdx.z;  // the cluster spans the grid's z extent
   const int hk = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PDL: the kernel behind us (the next chained decode-linear launch) may start its prologue and weight prefetch
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // the position is advanced at the end of the previous decode step, several fully serialised launches ago: safe to
+  // read before the dependency wait, like the cache rows below the new position
   const int pos = a.pos_dev ? *a.pos_dev : a.pos_host;
   const int T = min(pos + 1, a.Tmax);
   __shared__ __align__(16) float s_q[kG][kDh];
@@ -584,6 +588,8 @@ fused_decode_attention_split_kernel(const FusedDecodeArgs a) {
     }
   };
   if (t0 < T) request(t0);
+  // PDL: everything above overlaps the tail of the kernel in front of us; the QKV projection must have landed now
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- phase A: G query heads (norm + rope -> smem), new k (norm + rope) and new v -> smem (+ cache on rank 0)
   for (int job = warp; job < kG + 2; job += kW) {
@@ -734,32 +740,34 @@ fused_decode_attention_split_kernel(const FusedDecodeArgs a) {
 }
 
 template <int kDh, int kG>
-static int launch_fused_decode_split(const FusedDecodeArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_fused_decode_split(const FusedDecodeArgs& a, dim3 grid, bool pdl, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = grid.z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, fused_decode_attention_split_kernel<kDh, kG>, a);
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "decode_attention_fused (split-KV) launch: %s", cudaGetErrorString(e));
   return U2_OK;
 }
 
 template <int kDh>
-static int launch_fused_decode(const FusedDecodeArgs& a, int G, dim3 grid, cudaStream_t st) {
+static int launch_fused_decode(const FusedDecodeArgs& a, int G, dim3 grid, bool pdl, cudaStream_t st) {
   if (grid.z > 1) {
     switch (G) {
-      case 1: return launch_fused_decode_split<kDh, 1>(a, grid, st);
-      case 2: return launch_fused_decode_split<kDh, 2>(a, grid, st);
-      case 4: return launch_fused_decode_split<kDh, 4>(a, grid, st);
-      case 8: return launch_fused_decode_split<kDh, 8>(a, grid, st);
+      case 1: return launch_fused_decode_split<kDh, 1>(a, grid, pdl, st);
+      case 2: return launch_fused_decode_split<kDh, 2>(a, grid, pdl, st);
+      case 4: return launch_fused_decode_split<kDh, 4>(a, grid, pdl, st);
+      case 8: return launch_fused_decode_split<kDh, 8>(a, grid, pdl, st);
       default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: Hq/Hkv = %d (supported 1, 2, 4, 8)", G);
     }
   }
@@ -797,9 +805,9 @@ extern "C" U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_ca
   const int G = d->Hq / d->Hkv;
   int rc;
   switch (d->dh) {
-    case 32: rc = launch_fused_decode<32>(a, G, grid, ST(stream)); break;
-    case 64: rc = launch_fused_decode<64>(a, G, grid, ST(stream)); break;
-    case 128: rc = launch_fused_decode<128>(a, G, grid, ST(stream)); break;
+    case 32: rc = launch_fused_decode<32>(a, G, grid, d->pdl != 0, ST(stream)); break;
+    case 64: rc = launch_fused_decode<64>(a, G, grid, d->pdl != 0, ST(stream)); break;
+    case 128: rc = launch_fused_decode<128>(a, G, grid, d->pdl != 0, ST(stream)); break;
     default: return set_error(U2_ERR_UNSUPPORTED, "decode_attention_fused: head_dim %d (supported 32/64/128)", d->dh);
   }
   if (rc) return rc;

@@ -249,8 +249,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mx = nm;
           if (hit) p.lab_logit[row] = pick;
         }
-        if (row_ok && n_blk * kBlockN + half * (kBlockN / 2) < p.N)
-          p.part[(long long)(n_blk * 2 + half) * p.part_ld + row] = make_float4(mx, se, sx, 0.f);
+        // always written, also for a half tile that lies entirely past N: (-inf, 0, 0) is the merge's neutral element
+        if (row_ok) p.part[(long long)(n_blk * 2 + half) * p.part_ld + row] = make_float4(mx, se, sx, 0.f);
       } else {
 #pragma unroll 1
       for (int c0 = half * (kBlockN / 2); c0 < (half + 1) * (kBlockN / 2); c0 += 32) {
@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(256) logprob_merge_kernel(const float4* __rest
   if (r < R) {
     for (int pi = grp; pi < P; pi += 8) {
       const float4 v = __ldcs(part + (long long)pi * part_ld + r);
+      if (v.x == -INFINITY) continue;  // a half tile without valid columns
       const float nm = fmaxf(m, v.x);
       s = s * __expf(m - nm) + v.y * __expf(v.x - nm);
       x += v.z;

@@ -90,6 +90,7 @@ class U2Engine:
         import os
         from . import _lib
         self.num_sms = int(_lib.load().u2_device_sm_count())
+        self.attn_pdl = os.environ.get("U2_ATTN_PDL", "1") != "0"  # PDL launch of the split-KV decode attention
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
@@ -591,7 +592,8 @@ class U2Engine:
         for li, w in enumerate(self.layers):
             ops.decode_attention_fused(qkv, cache.k[li], cache.v[li], ctx, B=B, Hq=hq, Hkv=hkv, dh=dh, Tmax=cache.max_len,
                                        inv_freq=self.inv_freq, scale=1.0 / math.sqrt(dh), pos_dev=cache.length_dev,
-                                       q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps, kv_splits=self._kv_splits(B))
+                                       q_norm_w=w["qn"], k_norm_w=w["kn"], eps=eps, kv_splits=self._kv_splits(B),
+                                       pdl=self.pdl and self.attn_pdl)
             last = li + 1 == nl
             g_next = self.final_norm if last else self.layers[li + 1]["ln1"]
             fl = flags[li] if (self.multi_op and self.fine_deps) else [None] * 4

@@ -409,7 +409,8 @@ def decode_embed(ids: torch.Tensor, table: torch.Tensor, gamma: torch.Tensor, x:
 
 def decode_attention_fused(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, *,
                            B: int, Hq: int, Hkv: int, dh: int, Tmax: int, inv_freq: torch.Tensor, scale: float,
-                           pos: int = 0, pos_dev=None, q_norm_w=None, k_norm_w=None, eps: float = 1e-6, kv_splits: int = 1):
+                           pos: int = 0, pos_dev=None, q_norm_w=None, k_norm_w=None, eps: float = 1e-6, kv_splits: int = 1,
+                           pdl: bool = False):
     """q/k norm + RoPE + KV-cache append + GQA attention for one new token per sequence (one launch).
     kv_splits in {2, 4, 8}: a cluster of that many CTAs per (sequence, KV head) splits the cached keys."""
     _need_cuda(qkv, k_cache, v_cache, out, inv_freq, pos_dev, q_norm_w, k_norm_w)
@@ -421,6 +422,7 @@ def decode_attention_fused(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: to
     d.inv_freq = inv_freq.data_ptr()
     d.scale = scale
     d.kv_splits = int(kv_splits)
+    d.pdl = 1 if pdl else 0
     _lib.check(_lib.load().u2_decode_attention_fused_bf16(qkv.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
                                                           out.data_ptr(), C.byref(d), _stream()),
                "u2_decode_attention_fused_bf16")
