@@ -173,3 +173,62 @@ def test_u2tokenizer_hard_selection():
     assert (picked >= kth - 3e-2 * scores.abs().max()).all()
     if torch.equal(sel, ref_idx):
         check(got, ref, what="hard-selection tokenizer")
+
+
+def test_reference_smoke_shape_svr():
+    """The reference's own SVR smoke run (src/model/u2tokenizer/svr.py:190-205): attn_type "rope", E = 512, 8 heads,
+    4 layers, top_k 1024, multi-scale, input [1, 64, 256, 512] -> (1, 1792, 512) - one of the only two "known answers"
+    the reference holds. 64 frames -> temporal attention over 64 positions and a 16384-token
+    DiffTS softmax; the rest of the tokenizer runs on top with a short question."""
+    g = tiny_geometry(hidden_size=512, attn_type="rope", u2t_num_heads=8, u2t_num_layers=4, u2t_top_k=1024,
+                      use_multi_scale=True, num_3d_query_token=8)
+    eng, sd = build(g, 11)
+    gen = torch.Generator().manual_seed(5)
+    v = torch.randn(1, 64, 256, 512, generator=gen).bfloat16()
+    t = torch.randn(1, 6, 512, generator=gen).bfloat16()
+    with torch.no_grad():
+        vis = O.svr(sd, "model.u2tokenizer.svt_module.", v.float(), g)
+        assert tuple(vis.shape) == (1, 1792, 512)          # the reference's printed shape
+        ref = O.u2tokenizer(sd, "model.u2tokenizer.", v.float(), t.float(), g)
+    check(eng.u2tokenizer(v.cuda(), t.cuda()), ref, what="svr smoke shape")
+
+
+def test_reference_smoke_shape_tta():
+    """The reference's own TTA smoke run (src/model/u2tokenizer/tta.py:142-151): attn_type "rope", E = 896 (head_dim
+    112), 4 layers, query [1, 64, 896], visual [1, 1792, 896], text [1, 755, 896] -> (1, 64, 896)."""
+    g = tiny_geometry(hidden_size=896, attn_type="rope", u2t_num_heads=8, u2t_num_layers=4, u2t_top_k=1024,
+                      use_multi_scale=True, num_3d_query_token=64)
+    eng, sd = build(g, 12)
+    gen = torch.Generator().manual_seed(6)
+    v = torch.randn(1, 2, 24, 896, generator=gen).bfloat16()   # DiffTS makes 1024 -> multi-scale 1792 visual tokens
+    t = torch.randn(1, 755, 896, generator=gen).bfloat16()
+    with torch.no_grad():
+        assert tuple(O.svr(sd, "model.u2tokenizer.svt_module.", v.float(), g).shape) == (1, 1792, 896)
+        ref = O.u2tokenizer(sd, "model.u2tokenizer.", v.float(), t.float(), g)
+        assert tuple(ref.shape) == (1, 64, 896)              # the reference's printed shape
+    check(eng.u2tokenizer(v.cuda(), t.cuda()), ref, what="tta smoke shape")
+
+
+def test_cfg1_single_32cube_volume():
+    """BASELINE.json configs[0] / SURVEY.md section 8d "cfg 1": ONE 32 x 32 x 32 volume -> images [1, 1, 32, 32, 32],
+    image_size (32, 32, 32) -> 32 patches -> 4 tokens per chunk, u2t_top_k = 4, num_3d_query_token = 4, a 2-layer
+    Qwen3-shaped stub: the smallest shape the reference path accepts (TokenSelection needs top_k <= C * tokens)."""
+    for diffts in (True, False):
+        g = tiny_geometry(image_size=[32, 32, 32], u2t_top_k=4, num_3d_query_token=4, enable_diffts=diffts)
+        assert g.n_patches == 32 and g.tokens_per_frame == 4
+        eng, sd = build(g, 13)
+        images, ids, qids = synthetic_inputs(g, batch=1, frames=1, n_question=5, lt=8)
+        assert tuple(images.shape) == (1, 1, 32, 32, 32)
+        with torch.no_grad():
+            ref_emb = O.multimodal_embeds(sd, ids, images, qids, g)
+            ref_logits = O.decoder_forward(sd, ref_emb, g)[0]
+            ref_ids, margins = O.greedy_generate(sd, ids, images, qids, g, max_new_tokens=6)
+        emb = eng.multimodal_embeds(ids.cuda(), images.cuda(), qids.cuda())
+        check(emb, ref_emb, what="cfg1 multimodal_embeds")
+        logits = eng.lm_logits(eng.prefill(emb))
+        check(logits, ref_logits, what="cfg1 logits")
+        thr = 4.0 * (logits.float().cpu() - ref_logits).abs().max().item()
+        got = eng.generate_greedy(emb, max_new_tokens=6).cpu()
+        low = (margins[0] < thr).nonzero()
+        upto = int(low[0]) if len(low) else got.shape[1]
+        assert torch.equal(got[0, :upto], ref_ids[0, :upto]), (got, ref_ids, margins)

@@ -39,7 +39,7 @@ def test_layernorm_rmsnorm(E, with_res):
     close(y, gamma * xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + 1e-6))
 
 
-@pytest.mark.parametrize("S,n", [(7, 7), (256, 256), (40, 1792), (33, 2049), (64, 300)])
+@pytest.mark.parametrize("S,n", [(7, 7), (256, 256), (40, 1792), (33, 2049), (64, 300), (5, 8200), (3, 16384)])
 @pytest.mark.parametrize("mode", ["plain", "rel", "causal"])
 def test_softmax(S, n, mode):
     from u2tokenizer_b200 import ops
@@ -156,7 +156,7 @@ def test_embed_splice():
     assert torch.equal(ops.embed_splice(ids, table, None), emb)
 
 
-@pytest.mark.parametrize("C_,dh", [(8, 512), (3, 32), (1, 64), (16, 256)])
+@pytest.mark.parametrize("C_,dh", [(8, 512), (3, 32), (1, 64), (16, 256), (32, 64), (33, 64), (64, 64), (100, 32)])
 @pytest.mark.parametrize("rel", [True, False])
 def test_temporal_attention(C_, dh, rel):
     from u2tokenizer_b200 import ops

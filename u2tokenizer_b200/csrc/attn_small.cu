@@ -1,5 +1,5 @@
 // Small-sequence attention pieces that do not belong on the tensor cores:
-//   temporal_attention  RMA / RoPE attention across the <= 32 frames of one spatial token
+//   temporal_attention  RMA / RoPE attention across the <= 128 frames of one spatial token
 //                       (reference svr.py:33-36 + rma.py:60-73); one CTA per (batch, token, head)
 //   rope / qk_norm_rope rotate-half RoPE (optionally per-head RMSNorm first: Qwen3) applied in place
 //                       on a fused QKV buffer, and the KV-cache append of the decoder
@@ -50,33 +50,48 @@ temporal_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
   for (int c = warp; c < C; c += (blockDim.x >> 5)) {
     const long long row = ((long long)b * C + c) * N + n;
     const __nv_bfloat16* q = qkv + row * ld_qkv + h * dh;
-    // scores: lane j keeps the score of key frame j
-    float my = -INFINITY;
-    for (int j = 0; j < C; ++j) {
-      float d = 0.f;
-      for (int e = lane * 2; e < dh; e += 64) {
-        const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + e));
-        const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * dh + e));
-        d += qq.x * kk.x + qq.y * kk.y;
+    // scores: lane l keeps the scores of key frames l, l + 32, l + 64, l + 96
+    float my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      if (jb * 32 >= C) break;
+      const int jn = min(32, C - jb * 32);
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = jb * 32 + jj;
+        float d = 0.f;
+        for (int e = lane * 2; e < dh; e += 64) {
+          const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + e));
+          const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sK + (size_t)j * dh + e));
+          d += qq.x * kk.x + qq.y * kk.y;
+        }
+        d = wsum(d) * scale;
+        if (rel_bias) d += __ldg(rel_bias + (long long)(j - c + rel_max - 1) * H + h);
+        if (lane == jj) my[jb] = d;
       }
-      d = wsum(d) * scale;
-      if (rel_bias) d += __ldg(rel_bias + (long long)(j - c + rel_max - 1) * H + h);
-      if (lane == j) my = d;
     }
-    const float m = wmax(my);
-    const float e = (lane < C) ? __expf(my - m) : 0.f;
-    const float s = wsum(e);
-    const float p = e / s;
+    const float m = wmax(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])));
+    float pr[4], ssum = 0.f;
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      pr[jb] = (jb * 32 + lane < C) ? __expf(my[jb] - m) : 0.f;
+      ssum += pr[jb];
+    }
+    const float inv = 1.f / wsum(ssum);
     __nv_bfloat16* o = out + row * ld_out + h * dh;
     for (int e0 = lane * 2; e0 < dh; e0 += 64) {
       float ax = 0.f, ay = 0.f;
-      for (int j = 0; j < C; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, p, j);
-        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)j * dh + e0));
-        ax += pj * vv.x;
-        ay += pj * vv.y;
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        if (jb * 32 >= C) break;
+        const int jn = min(32, C - jb * 32);
+        for (int jj = 0; jj < jn; ++jj) {
+          const float pj = __shfl_sync(0xffffffffu, pr[jb], jj);
+          const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)(jb * 32 + jj) * dh + e0));
+          ax += pj * vv.x;
+          ay += pj * vv.y;
+        }
       }
-      *reinterpret_cast<__nv_bfloat162*>(o + e0) = __floats2bfloat162_rn(ax, ay);
+      *reinterpret_cast<__nv_bfloat162*>(o + e0) = __floats2bfloat162_rn(ax * inv, ay * inv);
     }
   }
 }
@@ -255,7 +270,9 @@ extern "C" U2_API int u2_temporal_attention_bf16(const void* qkv, void* out, int
                                                  float scale, const float* rel_bias, int32_t rel_max,
                                                  void* stream) {
   if (!qkv || !out) return set_error(U2_ERR_ARG, "temporal_attention: null pointer");
-  if (C <= 0 || C > 32) return set_error(U2_ERR_UNSUPPORTED, "temporal_attention: 1 <= frames <= 32 (got %d)", C);
+  if (C <= 0 || C > 128) return set_error(U2_ERR_UNSUPPORTED, "temporal_attention: 1 <= frames <= 128 (got %d)", C);
+  if ((size_t)2 * C * dh * sizeof(__nv_bfloat16) > 200 * 1024)
+    return set_error(U2_ERR_UNSUPPORTED, "temporal_attention: frames * head_dim = %d exceeds the shared-memory staging (51200)", C * dh);
   if ((dh & 7) || (ld_qkv & 7) || (ld_out & 1)) return set_error(U2_ERR_ARG, "temporal_attention: dh/ld alignment");
   if (rel_bias && C > rel_max) return set_error(U2_ERR_ARG, "temporal_attention: frames exceed relative-bias table");
   if (B <= 0 || N <= 0) return U2_OK;

@@ -233,6 +233,44 @@ softmax_rows_kernel(const SoftmaxArgs a) {
   }
 }
 
+// Rows longer than the register-resident variants hold (> 8192 keys, e.g. DiffTS over 64 frames x 256 tokens, the
+// reference's own smoke shape svr.py:190-205): one CTA per row, three passes over the (L2-resident) row.
+__global__ void __launch_bounds__(256)
+softmax_long_rows_kernel(const SoftmaxArgs a) {
+  const long long r = blockIdx.x;
+  const int i2 = (int)(r % a.S);
+  const int i1 = (int)((r / a.S) % a.H);
+  const long long i0 = r / ((long long)a.S * a.H);
+  const float* in = a.in + i0 * a.in_s0 + i1 * a.in_s1 + i2 * a.in_s2;
+  __nv_bfloat16* out = a.out + i0 * a.out_s0 + i1 * a.out_s1 + i2 * a.out_s2;
+  const int limit = a.causal ? min(a.n, i2 + a.causal_off + 1) : a.n;
+  __shared__ float red[8];
+  auto score = [&](int j) {
+    float t = in[j] * a.scale;
+    if (a.rel_bias) t += __ldg(a.rel_bias + (long long)(j - i2 + a.rel_max - 1) * a.H + i1);
+    return t;
+  };
+  auto block_reduce = [&](float v, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = red[0];
+    for (int w = 1; w < 8; ++w) t = is_max ? fmaxf(t, red[w]) : t + red[w];
+    return t;
+  };
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < limit; j += 256) m = fmaxf(m, score(j));
+  m = block_reduce(m, true);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < limit; j += 256) s += __expf(score(j) - m);
+  s = block_reduce(s, false);
+  const float inv = s > 0.f ? 1.f / s : 0.f;
+  const int span = max(a.n, a.zero_pad_to);
+  for (int j = threadIdx.x; j < span; j += 256)
+    out[j] = __float2bfloat16(j < limit ? __expf(score(j) - m) * inv : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // SiLU(gate) * up on a fused [rows, 2*I] gate|up buffer -> [rows, I]
 // ------------------------------------------------------------------------------------------------
@@ -315,7 +353,8 @@ extern "C" U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_s
   else if (span <= 2048) U2_SM_CASE(128, 16);
   else if (span <= 4096) U2_SM_CASE(256, 16);
   else if (span <= 8192) U2_SM_CASE(256, 32);
-  else return set_error(U2_ERR_UNSUPPORTED, "softmax: row length %d > 8192", span);
+  else if (rows <= 0x7fffffffLL) softmax_long_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(a);
+  else return set_error(U2_ERR_UNSUPPORTED, "softmax: %lld rows of length %d", rows, span);
 #undef U2_SM_CASE
   U2_CHECK_LAUNCH("softmax");
   return U2_OK;

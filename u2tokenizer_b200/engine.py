@@ -90,7 +90,7 @@ class U2Engine:
         import os
         from . import _lib
         self.num_sms = int(_lib.load().u2_device_sm_count())
-        self.attn_pdl = os.environ.get("U2_ATTN_PDL", "1") != "0"  # PDL launch of the split-KV decode attention
+        self.attn_pdl = os.environ.get("U2_ATTN_PDL", "0") != "0"  # PDL launch of the split-KV decode attention
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
