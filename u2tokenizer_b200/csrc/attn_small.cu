@@ -78,7 +78,9 @@ temporal_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     }
     const float inv = 1.f / wsum(ssum);
     __nv_bfloat16* o = out + row * ld_out + h * dh;
-    for (int e0 = lane * 2; e0 < dh; e0 += 64) {
+    for (int eb = 0; eb < dh; eb += 64) {  // warp-uniform trip count: the shuffles below need every lane
+      const int e0 = eb + lane * 2;
+      const bool own = e0 < dh;
       float ax = 0.f, ay = 0.f;
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
@@ -86,12 +88,14 @@ temporal_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
         const int jn = min(32, C - jb * 32);
         for (int jj = 0; jj < jn; ++jj) {
           const float pj = __shfl_sync(0xffffffffu, pr[jb], jj);
-          const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)(jb * 32 + jj) * dh + e0));
-          ax += pj * vv.x;
-          ay += pj * vv.y;
+          if (own) {
+            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (size_t)(jb * 32 + jj) * dh + e0));
+            ax += pj * vv.x;
+            ay += pj * vv.y;
+          }
         }
       }
-      *reinterpret_cast<__nv_bfloat162*>(o + e0) = __floats2bfloat162_rn(ax * inv, ay * inv);
+      if (own) *reinterpret_cast<__nv_bfloat162*>(o + e0) = __floats2bfloat162_rn(ax * inv, ay * inv);
     }
   }
 }
