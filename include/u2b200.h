@@ -343,6 +343,38 @@ U2_API int64_t u2_logprob_ws_bytes(int32_t R, int32_t V);
 U2_API int u2_lmhead_logprob_bf16(const void* hidden, const void* W, float* logp, const u2_logprob_desc* desc,
                                   void* stream);
 
+/* Volume preprocessing in front of the path ------------------------------------------------
+ * The reference's u2Transform.adaptive_resize (src/utils/u2Transform.py:62-122, validation pipeline :47-56) on a volume
+ * that is already on the device: ScaleIntensityRangePercentiles(lower, upper -> [0, 1], clip) -> CropForeground (> 0) ->
+ * anti-aliased trilinear resize (align_corners) so that the larger in-plane side becomes `target` (depth kept when it is
+ * <= pad_depth, resized to pad_depth otherwise) -> zero pad to [pad_depth, target, target].
+ * vol: fp32 [D, H, W] (the reference's data[0] after get_fdata().transpose(2, 0, 1)); out: fp32 [pad_depth, target,
+ * target] (viewed as [pad_depth / 32, 32, target, target] it is the `images` tensor of one study). info (device memory)
+ * receives the data-dependent quantities; nothing is synchronised with the host. status != 0 flags the inputs on which
+ * the reference itself fails or degenerates (the output is then all zeros, except U2_PP_FLAT_INTENSITY). */
+#define U2_PP_OK 0
+#define U2_PP_EMPTY_FOREGROUND 1  /* no voxel above the lower percentile */
+#define U2_PP_DEGENERATE_SHAPE 2  /* a resized extent of 0, or an anti-aliasing kernel wider than 129 taps */
+#define U2_PP_FLAT_INTENSITY 3    /* a_min == a_max: MONAI returns img - a_min unscaled */
+typedef struct u2_preprocess_info {
+  double a_min, a_max;      /* the two percentiles (np.percentile, linear interpolation, float64) */
+  int32_t lo[3], hi[3];     /* foreground box [lo, hi) on (D, H, W) */
+  int32_t out[3];           /* resized extents on (D, H, W) before padding */
+  float sigma[3];           /* anti-aliasing sigma per axis (0: none) */
+  int32_t tail[3];          /* Gaussian half width in taps */
+  int32_t status;           /* U2_PP_* */
+} u2_preprocess_info;
+typedef struct u2_preprocess_desc {
+  int32_t D, H, W;
+  int32_t target, pad_depth;
+  double lower_pct, upper_pct;
+  void* ws;                 /* u2_preprocess_ws_bytes(D, H, W) bytes, 256-byte aligned */
+  int64_t ws_bytes;
+} u2_preprocess_desc;
+U2_API int64_t u2_preprocess_ws_bytes(int32_t D, int32_t H, int32_t W);
+U2_API int u2_preprocess_volume_f32(const float* vol, float* out, u2_preprocess_info* info,
+                                    const u2_preprocess_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

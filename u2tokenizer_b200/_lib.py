@@ -144,6 +144,24 @@ class LogprobDesc(C.Structure):
     ]
 
 
+class PreprocessInfo(C.Structure):
+    """Mirror of ``u2_preprocess_info``."""
+    _fields_ = [
+        ("a_min", C.c_double), ("a_max", C.c_double),
+        ("lo", C.c_int32 * 3), ("hi", C.c_int32 * 3), ("out", C.c_int32 * 3),
+        ("sigma", C.c_float * 3), ("tail", C.c_int32 * 3), ("status", C.c_int32),
+    ]
+
+
+class PreprocessDesc(C.Structure):
+    """Mirror of ``u2_preprocess_desc``."""
+    _fields_ = [
+        ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("target", C.c_int32), ("pad_depth", C.c_int32),
+        ("lower_pct", C.c_double), ("upper_pct", C.c_double),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -175,6 +193,8 @@ SIGNATURES = {
     "u2_topk_rows_f32": (C.c_int, [_P, _P, _I, _I, _I, _L, _L, _P]),
     "u2_dlinear_ws_elems": (C.c_int64, [_I, _I]),
     "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "u2_preprocess_ws_bytes": (C.c_int64, [_I, _I, _I]),
+    "u2_preprocess_volume_f32": (C.c_int, [_P, _P, _P, C.POINTER(PreprocessDesc), _P]),
     "u2_logprob_ws_bytes": (C.c_int64, [_I, _I]),
     "u2_lmhead_logprob_bf16": (C.c_int, [_P, _P, _P, C.POINTER(LogprobDesc), _P]),
 }
@@ -203,7 +223,8 @@ def load():
 
 
 # kernels launched per entry point (u2_multiscale_pool_bf16: gate + write, counted at its maximum)
-KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2, "u2_lmhead_logprob_bf16": 2}
+KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2, "u2_lmhead_logprob_bf16": 2,
+                    "u2_preprocess_volume_f32": 14}
 _launches = 0
 
 

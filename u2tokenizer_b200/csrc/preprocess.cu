@@ -1,0 +1,350 @@
+// Volume preprocessing in front of the hot path: the reference's `u2Transform.adaptive_resize`
+// (src/utils/u2Transform.py:62-122; MONAI ScaleIntensityRangePercentiles -> CropForeground -> anti-aliased trilinear
+// resize -> zero pad -> 32-slice chunks) as a short sequence of HBM-bound kernels on a volume that is already on the
+// device. Everything data dependent (percentiles, foreground box, output extents, smoothing widths) stays on the device:
+// no host synchronisation between the steps.
+//
+//   1. exact percentiles: 3-pass radix select (11 + 11 + 10 key bits) of the 4 order statistics np.percentile's linear
+//      interpolation needs (one histogram pass over the volume per radix digit, shared by the 4 ranks)
+//   2. foreground box: min / max coordinates of the voxels above the lower percentile
+//   3. plan: crop extents -> output extents, per-axis anti-aliasing sigma (MONAI resize), one thread
+//   4. separable Gaussian (zero padded at the crop faces), H then W then D like MONAI's separable_filtering; the first
+//      pass also applies the intensity scaling + clip
+//   5. trilinear resample (align_corners) + zero pad, written in the (D, H, W) order the model consumes
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "host_util.h"
+#include "u2b200.h"
+
+namespace u2 {
+
+constexpr int kPpMaxTail = 64;
+
+struct PpState {                 // device-side working state (lives in the workspace)
+  unsigned int prefix[4];        // radix select: matched high key bits per rank
+  unsigned int rank[4];          // remaining rank inside the matched prefix
+  float order[4];                // the order statistics v[lo0], v[lo0 + 1], v[lo1], v[lo1 + 1]
+};
+
+__device__ __forceinline__ unsigned int pp_key(float x) {
+  const unsigned int u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pp_unkey(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// warp-aggregated shared-memory histogram increment (CT volumes hold huge runs of identical values)
+__device__ __forceinline__ void pp_hist_add(unsigned int* hist, unsigned int bin, bool pred) {
+  const unsigned int act = __ballot_sync(0xffffffffu, pred);
+  if (!pred) return;
+  const unsigned int peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + bin, (unsigned int)__popc(peers));
+}
+
+// kPass 0: digit = key[31:21], every element, one histogram.   kPass 1: digit = key[20:10] of the elements whose
+// key[31:21] matches rank r's prefix, 4 histograms.   kPass 2: digit = key[9:0], prefix key[31:10].
+template <int kPass>
+__global__ void __launch_bounds__(256) pp_hist_kernel(const float* __restrict__ vol, long long n,
+                                                      const PpState* __restrict__ st, unsigned int* __restrict__ hist) {
+  constexpr int kBins = (kPass == 2) ? 1024 : 2048;
+  constexpr int kHists = (kPass == 0) ? 1 : 4;
+  __shared__ unsigned int sh[kHists * kBins];
+  for (int i = threadIdx.x; i < kHists * kBins; i += 256) sh[i] = 0;
+  unsigned int pre[4] = {0, 0, 0, 0};
+  if (kPass > 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pre[r] = st->prefix[r];
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * 256;
+  const long long n_round = (n + 31) / 32 * 32;  // whole warps stay in the loop: the ballots need every lane
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_round; i += stride) {
+    const bool in = i < n;
+    const unsigned int k = in ? pp_key(__ldg(vol + i)) : 0u;
+    if (kPass == 0) {
+      pp_hist_add(sh, k >> 21, in);
+    } else if (kPass == 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) pp_hist_add(sh + r * kBins, (k >> 10) & 0x7ffu, in && (k >> 21) == (pre[r] >> 21));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) pp_hist_add(sh + r * kBins, k & 0x3ffu, in && (k >> 10) == (pre[r] >> 10));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHists * kBins; i += 256)
+    if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+
+// One block: per rank, find the digit whose cumulative count crosses the remaining rank.
+template <int kPass>
+__global__ void __launch_bounds__(128) pp_pick_kernel(PpState* st, const unsigned int* __restrict__ hist) {
+  constexpr int kBins = (kPass == 2) ? 1024 : 2048;
+  constexpr int kShift = (kPass == 0) ? 21 : (kPass == 1 ? 10 : 0);
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp r handles rank r
+  const unsigned int* h = hist + (kPass == 0 ? 0 : r * kBins);
+  unsigned int want = st->rank[r];
+  unsigned int base = 0;
+  int found = -1;
+  for (int b0 = 0; b0 < kBins && found < 0; b0 += 32) {
+    const unsigned int c = h[b0 + lane];
+    unsigned int inc = c;  // inclusive scan over the 32 bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const bool hit = want < base + inc;           // first lane whose inclusive count exceeds the rank
+    const unsigned int m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      const int l = __ffs(m) - 1;
+      const unsigned int before = base + __shfl_sync(0xffffffffu, inc - c, l);
+      found = b0 + l;
+      want -= before;
+    } else {
+      base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  if (lane == 0) {
+    if (found < 0) found = kBins - 1;  // cannot happen for ranks < n
+    const unsigned int p = (kPass == 0 ? 0u : st->prefix[r]) | ((unsigned int)found << kShift);
+    st->prefix[r] = p;
+    st->rank[r] = want;
+    if (kPass == 2) st->order[r] = pp_unkey(p);
+  }
+}
+
+__global__ void pp_init_kernel(PpState* st, u2_preprocess_info* info, unsigned int r0, unsigned int r1, unsigned int r2,
+                               unsigned int r3, int D, int H, int W) {
+  st->rank[0] = r0; st->rank[1] = r1; st->rank[2] = r2; st->rank[3] = r3;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) st->prefix[r] = 0;
+  info->lo[0] = D; info->lo[1] = H; info->lo[2] = W;
+  info->hi[0] = 0; info->hi[1] = 0; info->hi[2] = 0;
+  info->status = 0;
+}
+
+// numpy's _lerp (np.percentile, method "linear"), float64
+__device__ __forceinline__ double pp_lerp(double a, double b, double t) {
+  const double diff = b - a;
+  double v = a + diff * t;
+  if (t >= 0.5) v = b - diff * (1.0 - t);
+  return v;
+}
+
+__global__ void pp_percentile_kernel(const PpState* st, u2_preprocess_info* info, double g_lo, double g_hi) {
+  info->a_min = pp_lerp((double)st->order[0], (double)st->order[1], g_lo);
+  info->a_max = pp_lerp((double)st->order[2], (double)st->order[3], g_hi);
+}
+
+// Foreground box: voxels whose scaled intensity is positive  <=>  x > a_min.
+__global__ void __launch_bounds__(256) pp_bbox_kernel(const float* __restrict__ vol, int D, int H, int W,
+                                                      u2_preprocess_info* info) {
+  const double a_min = info->a_min;
+  const long long n = (long long)D * H * W;
+  int lo[3] = {D, H, W}, hi[3] = {0, 0, 0};
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    if ((double)__ldg(vol + i) > a_min) {
+      const int w = (int)(i % W);
+      const int h = (int)((i / W) % H);
+      const int d = (int)(i / ((long long)W * H));
+      lo[0] = min(lo[0], d); hi[0] = max(hi[0], d + 1);
+      lo[1] = min(lo[1], h); hi[1] = max(hi[1], h + 1);
+      lo[2] = min(lo[2], w); hi[2] = max(hi[2], w + 1);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (hi[a] > 0) {
+        atomicMin(&info->lo[a], lo[a]);
+        atomicMax(&info->hi[a], hi[a]);
+      }
+    }
+  }
+}
+
+// Output extents and smoothing widths (u2Transform.py:72-80,96-97 and MONAI resize's anti-aliasing rule).
+__global__ void pp_plan_kernel(u2_preprocess_info* info, int target, int pad_depth) {
+  const int Dc = info->hi[0] - info->lo[0], Hc = info->hi[1] - info->lo[1], Wc = info->hi[2] - info->lo[2];
+  if (Dc <= 0 || Hc <= 0 || Wc <= 0) {
+    info->status = U2_PP_EMPTY_FOREGROUND;
+    info->out[0] = info->out[1] = info->out[2] = 0;
+    return;
+  }
+  const double ratio = fmin((double)target / (double)Hc, (double)target / (double)Wc);
+  const int oh = (int)((double)Hc * ratio), ow = (int)((double)Wc * ratio);
+  const int od = (pad_depth >= Dc) ? Dc : pad_depth;
+  info->out[0] = od; info->out[1] = oh; info->out[2] = ow;
+  if (oh <= 0 || ow <= 0) {
+    info->status = U2_PP_DEGENERATE_SHAPE;
+    return;
+  }
+  const int in_sz[3] = {Dc, Hc, Wc}, out_sz[3] = {od, oh, ow};
+  const bool shrink = od < Dc || oh < Hc || ow < Wc;
+  for (int a = 0; a < 3; ++a) {
+    const float f = (float)in_sz[a] / (float)out_sz[a];
+    const float s = shrink ? fmaxf(0.f, (f - 1.f) / 2.f) : 0.f;
+    const int tail = (int)(fmax((double)s * 4.0, 0.5) + 0.5);
+    info->sigma[a] = s;
+    info->tail[a] = tail;
+    if (tail > kPpMaxTail) info->status = U2_PP_DEGENERATE_SHAPE;
+  }
+  if (info->a_max - info->a_min == 0.0 && info->status == 0) info->status = U2_PP_FLAT_INTENSITY;
+}
+
+// One separable pass along kAxis (0 = D, 1 = H, 2 = W in storage order) over the crop box; zero outside the box.
+// kFirst: the source is the raw volume and the intensity scaling + clip is applied on the fly.
+template <int kAxis, bool kFirst>
+__global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int H,
+                                                        int W, const u2_preprocess_info* __restrict__ info) {
+  __shared__ float taps[2 * kPpMaxTail + 1];
+  if (info->status == U2_PP_EMPTY_FOREGROUND || info->status == U2_PP_DEGENERATE_SHAPE) return;
+  const int tail = info->tail[kAxis];
+  if (threadIdx.x <= 2 * tail) {
+    // MONAI gaussian_1d(sigma, truncated=4, approx="erf", normalize=False); sigma == 0 gives the identity (0, 1, 0)
+    const float s = info->sigma[kAxis];
+    const float t = 0.70710678f / fabsf(s);
+    const float x = (float)((int)threadIdx.x - tail);
+    taps[threadIdx.x] = fmaxf(0.f, 0.5f * (erff(t * (x + 0.5f)) - erff(t * (x - 0.5f))));
+  }
+  __syncthreads();
+  const int lo0 = info->lo[0], lo1 = info->lo[1], lo2 = info->lo[2];
+  const int Dc = info->hi[0] - lo0, Hc = info->hi[1] - lo1, Wc = info->hi[2] - lo2;
+  const double a_min = info->a_min;
+  const double range = info->a_max - info->a_min;
+  const bool flat = range == 0.0;
+  const long long nc = (long long)Dc * Hc * Wc;
+  const int len = kAxis == 0 ? Dc : (kAxis == 1 ? Hc : Wc);
+  const long long step = kAxis == 0 ? (long long)H * W : (kAxis == 1 ? W : 1);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nc; i += (long long)gridDim.x * 256) {
+    const int w = (int)(i % Wc);
+    const int h = (int)((i / Wc) % Hc);
+    const int d = (int)(i / ((long long)Wc * Hc));
+    const long long at = ((long long)(lo0 + d) * H + (lo1 + h)) * W + (lo2 + w);
+    const int pos = kAxis == 0 ? d : (kAxis == 1 ? h : w);
+    const int k0 = max(-tail, -pos), k1 = min(tail, len - 1 - pos);
+    float acc = 0.f;
+    for (int k = k0; k <= k1; ++k) {
+      float v = __ldg(src + at + k * step);
+      if (kFirst) {
+        const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) / range, 0.0), 1.0);
+        v = (float)sc;
+      }
+      acc += taps[k + tail] * v;
+    }
+    dst[at] = acc;
+  }
+}
+
+// out[z][y][x] = trilinear(align_corners=True) sample of the smoothed crop, zero outside the resized extent.
+__global__ void __launch_bounds__(256) pp_resize_kernel(const float* __restrict__ src, float* __restrict__ out, int H, int W,
+                                                        int target, int pad_depth,
+                                                        const u2_preprocess_info* __restrict__ info) {
+  const long long total = (long long)pad_depth * target * target;
+  const bool ok = info->status == 0 || info->status == U2_PP_FLAT_INTENSITY;
+  const int od = info->out[0], oh = info->out[1], ow = info->out[2];
+  const int lo0 = info->lo[0], lo1 = info->lo[1], lo2 = info->lo[2];
+  const int Dc = info->hi[0] - lo0, Hc = info->hi[1] - lo1, Wc = info->hi[2] - lo2;
+  // torch area_pixel_compute_scale<float>(align_corners=true)
+  const float sd = od > 1 ? (float)(Dc - 1) / (float)(od - 1) : 0.f;
+  const float sh = oh > 1 ? (float)(Hc - 1) / (float)(oh - 1) : 0.f;
+  const float sw = ow > 1 ? (float)(Wc - 1) / (float)(ow - 1) : 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % target);
+    const int y = (int)((i / target) % target);
+    const int z = (int)(i / ((long long)target * target));
+    float v = 0.f;
+    if (ok && z < od && y < oh && x < ow) {
+      const float fh = sh * y, fw = sw * x, fd = sd * z;
+      const int h0 = (int)fh, w0 = (int)fw, d0 = (int)fd;
+      const int h1 = h0 + (h0 < Hc - 1), w1 = w0 + (w0 < Wc - 1), d1 = d0 + (d0 < Dc - 1);
+      const float lh1 = fh - h0, lw1 = fw - w0, ld1 = fd - d0;
+      const float lh0 = 1.f - lh1, lw0 = 1.f - lw1, ld0 = 1.f - ld1;
+      auto at = [&](int d, int h, int w) { return __ldg(src + ((long long)(lo0 + d) * H + (lo1 + h)) * W + (lo2 + w)); };
+      // nesting of torch's upsample_trilinear3d on the reference's (H, W, D) tensor: t = H, h = W, w = D
+      v = lh0 * (lw0 * (ld0 * at(d0, h0, w0) + ld1 * at(d1, h0, w0)) + lw1 * (ld0 * at(d0, h0, w1) + ld1 * at(d1, h0, w1))) +
+          lh1 * (lw0 * (ld0 * at(d0, h1, w0) + ld1 * at(d1, h1, w0)) + lw1 * (ld0 * at(d0, h1, w1) + ld1 * at(d1, h1, w1)));
+    }
+    out[i] = v;
+  }
+}
+
+static inline size_t pp_align(size_t x) { return (x + 255) / 256 * 256; }
+constexpr size_t kPpHistBytes = 4 * 2048 * sizeof(unsigned int);
+
+}  // namespace u2
+
+extern "C" U2_API int64_t u2_preprocess_ws_bytes(int32_t D, int32_t H, int32_t W) {
+  using namespace u2;
+  if (D <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t n = (size_t)D * H * W;
+  return (int64_t)(pp_align(sizeof(PpState)) + 3 * pp_align(kPpHistBytes) + 2 * pp_align(n * sizeof(float)));
+}
+
+extern "C" U2_API int u2_preprocess_volume_f32(const float* vol, float* out, u2_preprocess_info* info,
+                                               const u2_preprocess_desc* d, void* stream) {
+  using namespace u2;
+  if (!vol || !out || !info || !d || !d->ws) return set_error(U2_ERR_ARG, "preprocess: null pointer");
+  if (d->D <= 0 || d->H <= 0 || d->W <= 0 || d->target <= 0 || d->pad_depth <= 0)
+    return set_error(U2_ERR_ARG, "preprocess: extents must be > 0");
+  if (!(d->lower_pct >= 0.0 && d->lower_pct <= d->upper_pct && d->upper_pct <= 100.0))
+    return set_error(U2_ERR_ARG, "preprocess: need 0 <= lower_pct <= upper_pct <= 100");
+  if (d->ws_bytes < u2_preprocess_ws_bytes(d->D, d->H, d->W))
+    return set_error(U2_ERR_ARG, "preprocess: workspace too small (%lld < %lld bytes)", (long long)d->ws_bytes,
+                     (long long)u2_preprocess_ws_bytes(d->D, d->H, d->W));
+  if (reinterpret_cast<uintptr_t>(d->ws) & 255) return set_error(U2_ERR_ARG, "preprocess: workspace must be 256-byte aligned");
+  const long long n = (long long)d->D * d->H * d->W;
+  if (n >= (1LL << 32)) return set_error(U2_ERR_UNSUPPORTED, "preprocess: volumes of 2^32 voxels or more");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* w = reinterpret_cast<char*>(d->ws);
+  PpState* state = reinterpret_cast<PpState*>(w);
+  w += pp_align(sizeof(PpState));
+  unsigned int* hist[3];
+  for (int i = 0; i < 3; ++i) {
+    hist[i] = reinterpret_cast<unsigned int*>(w);
+    w += pp_align(kPpHistBytes);
+  }
+  float* buf_a = reinterpret_cast<float*>(w);
+  float* buf_b = reinterpret_cast<float*>(w + pp_align((size_t)n * sizeof(float)));
+
+  // np.percentile(method="linear"): virtual index (n - 1) * q, neighbours floor / floor + 1, weight = fraction
+  double vi[2], gam[2];
+  unsigned int ranks[4];
+  const double qs[2] = {d->lower_pct / 100.0, d->upper_pct / 100.0};
+  for (int i = 0; i < 2; ++i) {
+    vi[i] = (double)(n - 1) * qs[i];
+    double fl = floor(vi[i]);
+    if (fl > (double)(n - 1)) fl = (double)(n - 1);
+    gam[i] = vi[i] - fl;
+    ranks[2 * i] = (unsigned int)fl;
+    ranks[2 * i + 1] = (unsigned int)((fl + 1 <= (double)(n - 1)) ? fl + 1 : fl);
+  }
+  cudaMemsetAsync(hist[0], 0, 3 * pp_align(kPpHistBytes), st);
+  pp_init_kernel<<<1, 1, 0, st>>>(state, info, ranks[0], ranks[1], ranks[2], ranks[3], d->D, d->H, d->W);
+  const int blocks = num_sms() * 8;
+  pp_hist_kernel<0><<<blocks, 256, 0, st>>>(vol, n, state, hist[0]);
+  pp_pick_kernel<0><<<1, 128, 0, st>>>(state, hist[0]);
+  pp_hist_kernel<1><<<blocks, 256, 0, st>>>(vol, n, state, hist[1]);
+  pp_pick_kernel<1><<<1, 128, 0, st>>>(state, hist[1]);
+  pp_hist_kernel<2><<<blocks, 256, 0, st>>>(vol, n, state, hist[2]);
+  pp_pick_kernel<2><<<1, 128, 0, st>>>(state, hist[2]);
+  pp_percentile_kernel<<<1, 1, 0, st>>>(state, info, gam[0], gam[1]);
+  pp_bbox_kernel<<<blocks, 256, 0, st>>>(vol, d->D, d->H, d->W, info);
+  pp_plan_kernel<<<1, 1, 0, st>>>(info, d->target, d->pad_depth);
+  pp_smooth_kernel<1, true><<<blocks, 256, 0, st>>>(vol, buf_a, d->D, d->H, d->W, info);
+  pp_smooth_kernel<2, false><<<blocks, 256, 0, st>>>(buf_a, buf_b, d->D, d->H, d->W, info);
+  pp_smooth_kernel<0, false><<<blocks, 256, 0, st>>>(buf_b, buf_a, d->D, d->H, d->W, info);
+  pp_resize_kernel<<<blocks, 256, 0, st>>>(buf_a, out, d->H, d->W, d->target, d->pad_depth, info);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
+  return U2_OK;
+}

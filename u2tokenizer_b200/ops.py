@@ -501,3 +501,40 @@ def lmhead_logprob(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Ten
     _lib.check(lib.u2_lmhead_logprob_bf16(hidden.data_ptr(), weight.data_ptr(), logp.data_ptr(), C.byref(d), _stream()),
                "u2_lmhead_logprob_bf16")
     return logp, lse, lsum
+
+
+def preprocess_volume(vol: torch.Tensor, *, target: int = 256, pad_depth: int = 256, lower: float = 0.5, upper: float = 99.5,
+                      ws: Optional[torch.Tensor] = None):
+    """The reference's u2Transform.adaptive_resize on a device volume [D, H, W] fp32: percentile intensity scaling ->
+    foreground crop -> anti-aliased trilinear resize -> zero pad. Returns (images [pad_depth / 32, 32, target, target]
+    fp32, info) where info is a device byte tensor holding a ``u2_preprocess_info`` (decode with
+    ``preprocess_info``; nothing is synchronised here)."""
+    _need_cuda(vol, ws)
+    if vol.dtype != F32 or vol.dim() != 3 or not vol.is_contiguous():
+        raise TypeError("preprocess_volume expects a contiguous fp32 [D, H, W] volume")
+    if pad_depth % 32:
+        raise ValueError("pad_depth must be a multiple of 32 (the model consumes 32-slice chunks)")
+    D, H, W = vol.shape
+    lib = _lib.load()
+    need = int(lib.u2_preprocess_ws_bytes(D, H, W))
+    if ws is None:
+        ws = torch.empty(need, device=vol.device, dtype=torch.uint8)
+    elif ws.numel() * ws.element_size() < need:
+        raise ValueError(f"preprocess_volume: workspace of {need} bytes required")
+    out = torch.empty(pad_depth // 32, 32, target, target, device=vol.device, dtype=F32)
+    info = torch.zeros(C.sizeof(_lib.PreprocessInfo), device=vol.device, dtype=torch.uint8)
+    d = _lib.PreprocessDesc()
+    d.D, d.H, d.W, d.target, d.pad_depth = D, H, W, target, pad_depth
+    d.lower_pct, d.upper_pct = float(lower), float(upper)
+    d.ws, d.ws_bytes = ws.data_ptr(), ws.numel() * ws.element_size()
+    _lib.check(lib.u2_preprocess_volume_f32(vol.data_ptr(), out.data_ptr(), info.data_ptr(), C.byref(d), _stream()),
+               "u2_preprocess_volume_f32")
+    return out, info
+
+
+def preprocess_info(info: torch.Tensor) -> dict:
+    """Decode the device-side ``u2_preprocess_info`` (synchronises)."""
+    raw = bytes(info.cpu().numpy().tobytes())
+    s = _lib.PreprocessInfo.from_buffer_copy(raw)
+    return dict(a_min=s.a_min, a_max=s.a_max, lo=list(s.lo), hi=list(s.hi), out=list(s.out), sigma=list(s.sigma),
+                tail=list(s.tail), status=s.status)
