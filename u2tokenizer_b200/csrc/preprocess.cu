@@ -39,6 +39,13 @@ __device__ __forceinline__ float pp_unkey(unsigned int k) {
 // warp-aggregated shared-memory histogram increment (CT volumes hold huge runs of identical values)
 __device__ __forceinline__ void pp_hist_add(unsigned int* hist, unsigned int bin, bool pred) {
   const unsigned int act = __ballot_sync(0xffffffffu, pred);
+  if (act == 0) return;  // warp-uniform
+  const int leader = __ffs(act) - 1;
+  const unsigned int b0 = __shfl_sync(0xffffffffu, bin, leader);
+  if (__all_sync(0xffffffffu, !pred || bin == b0)) {  // the common case in air / saturated regions: one bin per warp
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(hist + b0, (unsigned int)__popc(act));
+    return;
+  }
   if (!pred) return;
   const unsigned int peers = __match_any_sync(act, bin);
   if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + bin, (unsigned int)__popc(peers));
@@ -53,10 +60,15 @@ __global__ void __launch_bounds__(256) pp_hist_kernel(const float* __restrict__ 
   constexpr int kHists = (kPass == 0) ? 1 : 4;
   __shared__ unsigned int sh[kHists * kBins];
   for (int i = threadIdx.x; i < kHists * kBins; i += 256) sh[i] = 0;
+  constexpr int kPreShift = (kPass == 1) ? 21 : 10;
   unsigned int pre[4] = {0, 0, 0, 0};
+  bool dup[4] = {false, false, false, false};  // same prefix as a lower rank: that rank's histogram serves both
   if (kPass > 0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) pre[r] = st->prefix[r];
+    for (int r = 0; r < 4; ++r) pre[r] = st->prefix[r] >> kPreShift;
+#pragma unroll
+    for (int r = 1; r < 4; ++r)
+      for (int q = 0; q < r; ++q) dup[r] = dup[r] || pre[q] == pre[r];
   }
   __syncthreads();
   const long long stride = (long long)gridDim.x * 256;
@@ -68,10 +80,12 @@ __global__ void __launch_bounds__(256) pp_hist_kernel(const float* __restrict__ 
       pp_hist_add(sh, k >> 21, in);
     } else if (kPass == 1) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) pp_hist_add(sh + r * kBins, (k >> 10) & 0x7ffu, in && (k >> 21) == (pre[r] >> 21));
+      for (int r = 0; r < 4; ++r)
+        if (!dup[r]) pp_hist_add(sh + r * kBins, (k >> 10) & 0x7ffu, in && (k >> 21) == pre[r]);
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) pp_hist_add(sh + r * kBins, k & 0x3ffu, in && (k >> 10) == (pre[r] >> 10));
+      for (int r = 0; r < 4; ++r)
+        if (!dup[r]) pp_hist_add(sh + r * kBins, k & 0x3ffu, in && (k >> 10) == pre[r]);
     }
   }
   __syncthreads();
@@ -85,7 +99,16 @@ __global__ void __launch_bounds__(128) pp_pick_kernel(PpState* st, const unsigne
   constexpr int kBins = (kPass == 2) ? 1024 : 2048;
   constexpr int kShift = (kPass == 0) ? 21 : (kPass == 1 ? 10 : 0);
   const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp r handles rank r
-  const unsigned int* h = hist + (kPass == 0 ? 0 : r * kBins);
+  constexpr int kPreShift = (kPass == 1) ? 21 : 10;
+  int src = r;  // histogram slot: the lowest rank with the same prefix (pp_hist_kernel filled only that one)
+  unsigned int my_prefix = 0;
+  if (kPass > 0) {
+    my_prefix = st->prefix[r];
+    for (int q = r - 1; q >= 0; --q)
+      if ((st->prefix[q] >> kPreShift) == (my_prefix >> kPreShift)) src = q;
+  }
+  __syncthreads();  // every warp has read the prefixes before any of them is updated
+  const unsigned int* h = hist + (kPass == 0 ? 0 : src * kBins);
   unsigned int want = st->rank[r];
   unsigned int base = 0;
   int found = -1;
@@ -110,7 +133,7 @@ __global__ void __launch_bounds__(128) pp_pick_kernel(PpState* st, const unsigne
   }
   if (lane == 0) {
     if (found < 0) found = kBins - 1;  // cannot happen for ranks < n
-    const unsigned int p = (kPass == 0 ? 0u : st->prefix[r]) | ((unsigned int)found << kShift);
+    const unsigned int p = my_prefix | ((unsigned int)found << kShift);
     st->prefix[r] = p;
     st->rank[r] = want;
     if (kPass == 2) st->order[r] = pp_unkey(p);
@@ -140,20 +163,20 @@ __global__ void pp_percentile_kernel(const PpState* st, u2_preprocess_info* info
   info->a_max = pp_lerp((double)st->order[2], (double)st->order[3], g_hi);
 }
 
-// Foreground box: voxels whose scaled intensity is positive  <=>  x > a_min.
+// Foreground box: voxels whose scaled intensity is positive  <=>  x > a_min. One block per (d, h) row at a time.
 __global__ void __launch_bounds__(256) pp_bbox_kernel(const float* __restrict__ vol, int D, int H, int W,
                                                       u2_preprocess_info* info) {
   const double a_min = info->a_min;
-  const long long n = (long long)D * H * W;
   int lo[3] = {D, H, W}, hi[3] = {0, 0, 0};
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    if ((double)__ldg(vol + i) > a_min) {
-      const int w = (int)(i % W);
-      const int h = (int)((i / W) % H);
-      const int d = (int)(i / ((long long)W * H));
-      lo[0] = min(lo[0], d); hi[0] = max(hi[0], d + 1);
-      lo[1] = min(lo[1], h); hi[1] = max(hi[1], h + 1);
-      lo[2] = min(lo[2], w); hi[2] = max(hi[2], w + 1);
+  for (unsigned int row = blockIdx.x; row < (unsigned int)(D * H); row += gridDim.x) {
+    const int d = (int)(row / (unsigned int)H), h = (int)(row - (unsigned int)d * H);
+    const float* p = vol + (size_t)row * W;
+    for (int w = threadIdx.x; w < W; w += 256) {
+      if ((double)__ldg(p + w) > a_min) {
+        lo[0] = min(lo[0], d); hi[0] = max(hi[0], d + 1);
+        lo[1] = min(lo[1], h); hi[1] = max(hi[1], h + 1);
+        lo[2] = min(lo[2], w); hi[2] = max(hi[2], w + 1);
+      }
     }
   }
 #pragma unroll
@@ -163,11 +186,9 @@ __global__ void __launch_bounds__(256) pp_bbox_kernel(const float* __restrict__ 
       lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
       hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
     }
-    if ((threadIdx.x & 31) == 0) {
-      if (hi[a] > 0) {
-        atomicMin(&info->lo[a], lo[a]);
-        atomicMax(&info->hi[a], hi[a]);
-      }
+    if ((threadIdx.x & 31) == 0 && hi[a] > 0) {
+      atomicMin(&info->lo[a], lo[a]);
+      atomicMax(&info->hi[a], hi[a]);
     }
   }
 }
@@ -222,26 +243,26 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
   const double a_min = info->a_min;
   const double range = info->a_max - info->a_min;
   const bool flat = range == 0.0;
-  const long long nc = (long long)Dc * Hc * Wc;
   const int len = kAxis == 0 ? Dc : (kAxis == 1 ? Hc : Wc);
   const long long step = kAxis == 0 ? (long long)H * W : (kAxis == 1 ? W : 1);
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nc; i += (long long)gridDim.x * 256) {
-    const int w = (int)(i % Wc);
-    const int h = (int)((i / Wc) % Hc);
-    const int d = (int)(i / ((long long)Wc * Hc));
-    const long long at = ((long long)(lo0 + d) * H + (lo1 + h)) * W + (lo2 + w);
-    const int pos = kAxis == 0 ? d : (kAxis == 1 ? h : w);
-    const int k0 = max(-tail, -pos), k1 = min(tail, len - 1 - pos);
-    float acc = 0.f;
-    for (int k = k0; k <= k1; ++k) {
-      float v = __ldg(src + at + k * step);
-      if (kFirst) {
-        const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) / range, 0.0), 1.0);
-        v = (float)sc;
+  for (unsigned int row = blockIdx.x; row < (unsigned int)(Dc * Hc); row += gridDim.x) {  // one (d, h) row of the crop
+    const int d = (int)(row / (unsigned int)Hc), h = (int)(row - (unsigned int)d * Hc);
+    const long long base = ((long long)(lo0 + d) * H + (lo1 + h)) * W + lo2;
+    for (int w = threadIdx.x; w < Wc; w += 256) {
+      const long long at = base + w;
+      const int pos = kAxis == 0 ? d : (kAxis == 1 ? h : w);
+      const int k0 = max(-tail, -pos), k1 = min(tail, len - 1 - pos);
+      float acc = 0.f;
+      for (int k = k0; k <= k1; ++k) {
+        float v = __ldg(src + at + k * step);
+        if (kFirst) {
+          const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) / range, 0.0), 1.0);
+          v = (float)sc;
+        }
+        acc += taps[k + tail] * v;
       }
-      acc += taps[k + tail] * v;
+      dst[at] = acc;
     }
-    dst[at] = acc;
   }
 }
 
@@ -249,7 +270,6 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) pp_resize_kernel(const float* __restrict__ src, float* __restrict__ out, int H, int W,
                                                         int target, int pad_depth,
                                                         const u2_preprocess_info* __restrict__ info) {
-  const long long total = (long long)pad_depth * target * target;
   const bool ok = info->status == 0 || info->status == U2_PP_FLAT_INTENSITY;
   const int od = info->out[0], oh = info->out[1], ow = info->out[2];
   const int lo0 = info->lo[0], lo1 = info->lo[1], lo2 = info->lo[2];
@@ -258,23 +278,32 @@ __global__ void __launch_bounds__(256) pp_resize_kernel(const float* __restrict_
   const float sd = od > 1 ? (float)(Dc - 1) / (float)(od - 1) : 0.f;
   const float sh = oh > 1 ? (float)(Hc - 1) / (float)(oh - 1) : 0.f;
   const float sw = ow > 1 ? (float)(Wc - 1) / (float)(ow - 1) : 0.f;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int x = (int)(i % target);
-    const int y = (int)((i / target) % target);
-    const int z = (int)(i / ((long long)target * target));
-    float v = 0.f;
-    if (ok && z < od && y < oh && x < ow) {
-      const float fh = sh * y, fw = sw * x, fd = sd * z;
-      const int h0 = (int)fh, w0 = (int)fw, d0 = (int)fd;
-      const int h1 = h0 + (h0 < Hc - 1), w1 = w0 + (w0 < Wc - 1), d1 = d0 + (d0 < Dc - 1);
-      const float lh1 = fh - h0, lw1 = fw - w0, ld1 = fd - d0;
-      const float lh0 = 1.f - lh1, lw0 = 1.f - lw1, ld0 = 1.f - ld1;
-      auto at = [&](int d, int h, int w) { return __ldg(src + ((long long)(lo0 + d) * H + (lo1 + h)) * W + (lo2 + w)); };
-      // nesting of torch's upsample_trilinear3d on the reference's (H, W, D) tensor: t = H, h = W, w = D
-      v = lh0 * (lw0 * (ld0 * at(d0, h0, w0) + ld1 * at(d1, h0, w0)) + lw1 * (ld0 * at(d0, h0, w1) + ld1 * at(d1, h0, w1))) +
-          lh1 * (lw0 * (ld0 * at(d0, h1, w0) + ld1 * at(d1, h1, w0)) + lw1 * (ld0 * at(d0, h1, w1) + ld1 * at(d1, h1, w1)));
+  for (unsigned int row = blockIdx.x; row < (unsigned int)(pad_depth * target); row += gridDim.x) {  // one (z, y) row
+    const int z = (int)(row / (unsigned int)target), y = (int)(row - (unsigned int)z * target);
+    float* orow = out + (size_t)row * target;
+    const bool row_in = ok && z < od && y < oh;
+    const float fh = sh * y, fd = sd * z;
+    const int h0 = (int)fh, d0 = (int)fd;
+    const int h1 = h0 + (h0 < Hc - 1), d1 = d0 + (d0 < Dc - 1);
+    const float lh1 = fh - h0, ld1 = fd - d0;
+    const float lh0 = 1.f - lh1, ld0 = 1.f - ld1;
+    const float* r00 = src + ((long long)(lo0 + d0) * H + (lo1 + h0)) * W + lo2;
+    const float* r10 = src + ((long long)(lo0 + d1) * H + (lo1 + h0)) * W + lo2;
+    const float* r01 = src + ((long long)(lo0 + d0) * H + (lo1 + h1)) * W + lo2;
+    const float* r11 = src + ((long long)(lo0 + d1) * H + (lo1 + h1)) * W + lo2;
+    for (int x = threadIdx.x; x < target; x += 256) {
+      float v = 0.f;
+      if (row_in && x < ow) {
+        const float fw = sw * x;
+        const int w0 = (int)fw;
+        const int w1 = w0 + (w0 < Wc - 1);
+        const float lw1 = fw - w0, lw0 = 1.f - lw1;
+        // nesting of torch's upsample_trilinear3d on the reference's (H, W, D) tensor: t = H, h = W, w = D
+        v = lh0 * (lw0 * (ld0 * __ldg(r00 + w0) + ld1 * __ldg(r10 + w0)) + lw1 * (ld0 * __ldg(r00 + w1) + ld1 * __ldg(r10 + w1))) +
+            lh1 * (lw0 * (ld0 * __ldg(r01 + w0) + ld1 * __ldg(r11 + w0)) + lw1 * (ld0 * __ldg(r01 + w1) + ld1 * __ldg(r11 + w1)));
+      }
+      orow[x] = v;
     }
-    out[i] = v;
   }
 }
 
