@@ -110,27 +110,39 @@ __global__ void __launch_bounds__(128) pp_pick_kernel(PpState* st, const unsigne
   __syncthreads();  // every warp has read the prefixes before any of them is updated
   const unsigned int* h = hist + (kPass == 0 ? 0 : src * kBins);
   unsigned int want = st->rank[r];
-  unsigned int base = 0;
-  int found = -1;
-  for (int b0 = 0; b0 < kBins && found < 0; b0 += 32) {
-    const unsigned int c = h[b0 + lane];
-    unsigned int inc = c;  // inclusive scan over the 32 bins
+  // lane l owns the contiguous segment [l * kSeg, (l + 1) * kSeg): independent loads, then one warp scan of the segment
+  // totals, then the owning lane walks its segment
+  constexpr int kSeg = kBins / 32;
+  unsigned int seg = 0;
+#pragma unroll 8
+  for (int i = 0; i < kSeg; ++i) seg += h[lane * kSeg + i];
+  unsigned int inc = seg;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    const bool hit = want < base + inc;           // first lane whose inclusive count exceeds the rank
-    const unsigned int m = __ballot_sync(0xffffffffu, hit);
-    if (m) {
-      const int l = __ffs(m) - 1;
-      const unsigned int before = base + __shfl_sync(0xffffffffu, inc - c, l);
-      found = b0 + l;
-      want -= before;
-    } else {
-      base += __shfl_sync(0xffffffffu, inc, 31);
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
+  const unsigned int m = __ballot_sync(0xffffffffu, want < inc);
+  const int owner = m ? __ffs(m) - 1 : 31;
+  int found = -1;
+  if (lane == owner) {
+    unsigned int before = inc - seg;
+    for (int i = 0; i < kSeg; ++i) {
+      const unsigned int c = h[lane * kSeg + i];
+      if (want < before + c) {
+        found = lane * kSeg + i;
+        break;
+      }
+      before += c;
+    }
+    if (found < 0) {  // cannot happen for ranks < n
+      found = lane * kSeg + kSeg - 1;
+      before = 0;
+    }
+    want -= before;
+  }
+  found = __shfl_sync(0xffffffffu, found, owner);
+  want = __shfl_sync(0xffffffffu, want, owner);
   if (lane == 0) {
     if (found < 0) found = kBins - 1;  // cannot happen for ranks < n
     const unsigned int p = my_prefix | ((unsigned int)found << kShift);
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
   const double a_min = info->a_min;
   const double range = info->a_max - info->a_min;
   const bool flat = range == 0.0;
+  const double inv_range = flat ? 0.0 : 1.0 / range;
   const int len = kAxis == 0 ? Dc : (kAxis == 1 ? Hc : Wc);
   const long long step = kAxis == 0 ? (long long)H * W : (kAxis == 1 ? W : 1);
   for (unsigned int row = blockIdx.x; row < (unsigned int)(Dc * Hc); row += gridDim.x) {  // one (d, h) row of the crop
@@ -256,7 +269,9 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
       for (int k = k0; k <= k1; ++k) {
         float v = __ldg(src + at + k * step);
         if (kFirst) {
-          const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) / range, 0.0), 1.0);
+          // (x - a_min) / range with the division replaced by a multiplication with 1 / range: at most one float64
+          // ulp away before the rounding to float32
+          const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) * inv_range, 0.0), 1.0);
           v = (float)sc;
         }
         acc += taps[k + tail] * v;
