@@ -25,8 +25,8 @@ i = ops.preprocess_info(info)
 crop = 1
 for a in range(3):
     crop *= i["hi"][a] - i["lo"][a]
-# algorithmic traffic: 3 histogram reads + 1 box read of the volume, 3 smoothing passes (read + write) over the crop,
+# algorithmic traffic: 3 histogram reads + 1 scale+box read and 1 write of the volume, 3 smoothing passes (read + write) over the crop,
 # the resize reading the crop once and writing the padded output
-by = 4 * n * 4 + 3 * 2 * crop * 4 + crop * 4 + out.numel() * 4
+by = 4 * n * 4 + n * 4 + 3 * 2 * crop * 4 + crop * 4 + out.numel() * 4
 print(f"preprocess {D}x{H}x{W}: {ms:.3f} ms per study; info {i}")
 print(f"algorithmic bytes {by / 1e6:.1f} MB -> {by / ms / 1e6:.1f} GB/s")

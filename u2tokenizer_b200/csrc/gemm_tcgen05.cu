@@ -63,8 +63,24 @@ struct GemmDev {
   long long part_ld;
 };
 
+// erf-based GELU (nn.GELU() default, MONAI MLPBlock / the projector MLP) with erf from Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the bf16 rounding of the result): 2 MUFU + ~12 FMA-class instructions instead of erff's
+// branchy ~30 - the epilogue of the K = 768 ViT GEMMs is instruction-issue bound, not tensor bound.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(erf_abs, x), hx);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == U2_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (act == U2_ACT_GELU) return gelu_erf(x);
   if (act == U2_ACT_SILU) return x / (1.0f + __expf(-x));
   return x;
 }

@@ -6,10 +6,10 @@
 //
 //   1. exact percentiles: 3-pass radix select (11 + 11 + 10 key bits) of the 4 order statistics np.percentile's linear
 //      interpolation needs (one histogram pass over the volume per radix digit, shared by the 4 ranks)
-//   2. foreground box: min / max coordinates of the voxels above the lower percentile
+//   2. intensity scaling + clip of every voxel and, in the same pass, the foreground box (min / max coordinates of the
+//      voxels above the lower percentile)
 //   3. plan: crop extents -> output extents, per-axis anti-aliasing sigma (MONAI resize), one thread
-//   4. separable Gaussian (zero padded at the crop faces), H then W then D like MONAI's separable_filtering; the first
-//      pass also applies the intensity scaling + clip
+//   4. separable Gaussian (zero padded at the crop faces), H then W then D like MONAI's separable_filtering
 //   5. trilinear resample (align_corners) + zero pad, written in the (D, H, W) order the model consumes
 #include <cuda_runtime.h>
 #include <math.h>
@@ -175,16 +175,25 @@ __global__ void pp_percentile_kernel(const PpState* st, u2_preprocess_info* info
   info->a_max = pp_lerp((double)st->order[2], (double)st->order[3], g_hi);
 }
 
-// Foreground box: voxels whose scaled intensity is positive  <=>  x > a_min. One block per (d, h) row at a time.
-__global__ void __launch_bounds__(256) pp_bbox_kernel(const float* __restrict__ vol, int D, int H, int W,
-                                                      u2_preprocess_info* info) {
+// Intensity scaling + clip of every voxel (MONAI ScaleIntensityRange: float64 arithmetic, float32 result; the division by
+// the range is a multiplication with its reciprocal, at most one float64 ulp away before the rounding to float32) and, in
+// the same pass, the foreground box: voxels whose scaled intensity is positive  <=>  x > a_min.
+// One block per (d, h) row at a time.
+__global__ void __launch_bounds__(256) pp_scale_bbox_kernel(const float* __restrict__ vol, float* __restrict__ scaled, int D,
+                                                            int H, int W, u2_preprocess_info* info) {
   const double a_min = info->a_min;
+  const double range = info->a_max - info->a_min;
+  const bool flat = range == 0.0;
+  const double inv_range = flat ? 0.0 : 1.0 / range;
   int lo[3] = {D, H, W}, hi[3] = {0, 0, 0};
   for (unsigned int row = blockIdx.x; row < (unsigned int)(D * H); row += gridDim.x) {
     const int d = (int)(row / (unsigned int)H), h = (int)(row - (unsigned int)d * H);
     const float* p = vol + (size_t)row * W;
+    float* q = scaled + (size_t)row * W;
     for (int w = threadIdx.x; w < W; w += 256) {
-      if ((double)__ldg(p + w) > a_min) {
+      const double v = (double)__ldg(p + w);
+      q[w] = (float)(flat ? v - a_min : fmin(fmax((v - a_min) * inv_range, 0.0), 1.0));
+      if (v > a_min) {
         lo[0] = min(lo[0], d); hi[0] = max(hi[0], d + 1);
         lo[1] = min(lo[1], h); hi[1] = max(hi[1], h + 1);
         lo[2] = min(lo[2], w); hi[2] = max(hi[2], w + 1);
@@ -235,8 +244,7 @@ __global__ void pp_plan_kernel(u2_preprocess_info* info, int target, int pad_dep
 }
 
 // One separable pass along kAxis (0 = D, 1 = H, 2 = W in storage order) over the crop box; zero outside the box.
-// kFirst: the source is the raw volume and the intensity scaling + clip is applied on the fly.
-template <int kAxis, bool kFirst>
+template <int kAxis>
 __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int H,
                                                         int W, const u2_preprocess_info* __restrict__ info) {
   __shared__ float taps[2 * kPpMaxTail + 1];
@@ -252,10 +260,6 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
   __syncthreads();
   const int lo0 = info->lo[0], lo1 = info->lo[1], lo2 = info->lo[2];
   const int Dc = info->hi[0] - lo0, Hc = info->hi[1] - lo1, Wc = info->hi[2] - lo2;
-  const double a_min = info->a_min;
-  const double range = info->a_max - info->a_min;
-  const bool flat = range == 0.0;
-  const double inv_range = flat ? 0.0 : 1.0 / range;
   const int len = kAxis == 0 ? Dc : (kAxis == 1 ? Hc : Wc);
   const long long step = kAxis == 0 ? (long long)H * W : (kAxis == 1 ? W : 1);
   for (unsigned int row = blockIdx.x; row < (unsigned int)(Dc * Hc); row += gridDim.x) {  // one (d, h) row of the crop
@@ -266,16 +270,7 @@ __global__ void __launch_bounds__(256) pp_smooth_kernel(const float* __restrict_
       const int pos = kAxis == 0 ? d : (kAxis == 1 ? h : w);
       const int k0 = max(-tail, -pos), k1 = min(tail, len - 1 - pos);
       float acc = 0.f;
-      for (int k = k0; k <= k1; ++k) {
-        float v = __ldg(src + at + k * step);
-        if (kFirst) {
-          // (x - a_min) / range with the division replaced by a multiplication with 1 / range: at most one float64
-          // ulp away before the rounding to float32
-          const double sc = flat ? ((double)v - a_min) : fmin(fmax(((double)v - a_min) * inv_range, 0.0), 1.0);
-          v = (float)sc;
-        }
-        acc += taps[k + tail] * v;
-      }
+      for (int k = k0; k <= k1; ++k) acc += taps[k + tail] * __ldg(src + at + k * step);
       dst[at] = acc;
     }
   }
@@ -382,11 +377,11 @@ extern "C" U2_API int u2_preprocess_volume_f32(const float* vol, float* out, u2_
   pp_hist_kernel<2><<<blocks, 256, 0, st>>>(vol, n, state, hist[2]);
   pp_pick_kernel<2><<<1, 128, 0, st>>>(state, hist[2]);
   pp_percentile_kernel<<<1, 1, 0, st>>>(state, info, gam[0], gam[1]);
-  pp_bbox_kernel<<<blocks, 256, 0, st>>>(vol, d->D, d->H, d->W, info);
+  pp_scale_bbox_kernel<<<blocks, 256, 0, st>>>(vol, buf_b, d->D, d->H, d->W, info);
   pp_plan_kernel<<<1, 1, 0, st>>>(info, d->target, d->pad_depth);
-  pp_smooth_kernel<1, true><<<blocks, 256, 0, st>>>(vol, buf_a, d->D, d->H, d->W, info);
-  pp_smooth_kernel<2, false><<<blocks, 256, 0, st>>>(buf_a, buf_b, d->D, d->H, d->W, info);
-  pp_smooth_kernel<0, false><<<blocks, 256, 0, st>>>(buf_b, buf_a, d->D, d->H, d->W, info);
+  pp_smooth_kernel<1><<<blocks, 256, 0, st>>>(buf_b, buf_a, d->D, d->H, d->W, info);
+  pp_smooth_kernel<2><<<blocks, 256, 0, st>>>(buf_a, buf_b, d->D, d->H, d->W, info);
+  pp_smooth_kernel<0><<<blocks, 256, 0, st>>>(buf_b, buf_a, d->D, d->H, d->W, info);
   pp_resize_kernel<<<blocks, 256, 0, st>>>(buf_a, out, d->H, d->W, d->target, d->pad_depth, info);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
