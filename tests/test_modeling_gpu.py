@@ -127,3 +127,21 @@ def test_multi_sample_generate_shares_the_prefill():
     assert int(a.min()) >= 0 and int(a.max()) < g.vocab_size
     with pytest.raises(ValueError):
         model.generate(*args, question_ids=qids.cuda(), max_new_tokens=4, do_sample=False, num_return_sequences=2)
+
+
+def test_forward_graph_replay_matches_eager():
+    """Repeated same-shape forwards replay one CUDA graph over static buffers (engine.forward_logits): every replay must
+    give what the eager launch sequence gives on the same inputs, for inputs that change from call to call."""
+    model, g, sd = make("qwen3")
+    eng = model.engine()
+    for seed in (1, 2, 3, 4):
+        images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12, seed=seed)
+        got = model(images=images.cuda(), input_ids=ids.cuda(), question_ids=qids.cuda()).logits
+        ref = eng.forward_logits(ids.cuda(), images.cuda(), qids.cuda(), use_graph=False)
+        assert got.shape == ref.shape and rel_err(got, ref) < 1e-3, seed
+    assert eng._fwd_state["graph"] is not None and eng._fwd_state["n"] > 50
+    # a different shape drops the graph and starts over
+    images, ids, qids = synthetic_inputs(g, batch=1, frames=2, n_question=6, lt=12, seed=9)
+    a = model(images=images.cuda(), input_ids=ids.cuda(), question_ids=qids.cuda()).logits
+    b = model(images=images.cuda(), input_ids=ids.cuda(), question_ids=qids.cuda()).logits
+    assert a.shape[0] == 1 and rel_err(a, b) < 1e-3

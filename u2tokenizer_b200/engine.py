@@ -90,6 +90,7 @@ class U2Engine:
         import os
         from . import _lib
         self.num_sms = int(_lib.load().u2_device_sm_count())
+        self.fwd_graph = os.environ.get("U2_FWD_GRAPH", "1") != "0"  # replay repeated same-shape forwards as one CUDA graph
         self.attn_pdl = os.environ.get("U2_ATTN_PDL", "0") != "0"  # PDL launch of the split-KV decode attention
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
@@ -110,6 +111,7 @@ class U2Engine:
             self._prep_tokenizer(t)
         self._prep_decoder(t)
         self._gen_state = None
+        self._fwd_state = None
         self._sampling = None
 
     # =========================================================================================
@@ -457,6 +459,50 @@ class U2Engine:
 
     def embed_tokens(self, input_ids: torch.Tensor) -> torch.Tensor:
         return ops.embed_splice(input_ids.to(self.dev), self.embed, None)
+
+    def forward_logits(self, input_ids: torch.Tensor, images: torch.Tensor, question_ids: Optional[torch.Tensor],
+                       use_graph: Optional[bool] = None) -> torch.Tensor:
+        """Teacher-forced forward with images: vision tower -> mu2-tokenizer -> splice -> decoder prefill -> lm_head,
+        [B, L, V] fp32 logits. The ~600 launches of one forward are short (a 256x256x128 study is ~6 ms of kernels), so
+        from the second call with the same shapes on the whole sequence replays as ONE CUDA graph over static buffers
+        (U2_FWD_GRAPH=0 keeps it eager)."""
+        from . import _lib
+        if use_graph is None:
+            use_graph = self.fwd_graph
+        key = (tuple(images.shape), images.dtype, tuple(input_ids.shape),
+               None if question_ids is None else tuple(question_ids.shape))
+        st = self._fwd_state if (self._fwd_state is not None and self._fwd_state["key"] == key) else None
+        if st is None:
+            self._fwd_state = None  # drop the previous graph (and its memory pool) first
+            st = dict(key=key, calls=0, graph=None)
+            self._fwd_state = st
+        st["calls"] += 1
+
+        def run(ids, im, q):
+            emb = self.multimodal_embeds(ids, im, q)
+            return self.lm_logits(self.prefill(emb))
+
+        if not use_graph or st["calls"] < 2:  # the first call runs eagerly (it also configures the kernels' attributes)
+            return run(input_ids, images, question_ids)
+        if st["graph"] is None:
+            st["ids"] = input_ids.to(self.dev).clone()
+            st["images"] = images.to(self.dev).clone()
+            st["q"] = None if question_ids is None else question_ids.to(self.dev).clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launches()
+            with torch.cuda.graph(graph):
+                st["logits"] = run(st["ids"], st["images"], st["q"])
+            st["n"] = _lib.launches() - n0
+            _lib.add_launches(-st["n"])  # capture records, it does not execute
+            st["graph"] = graph
+        st["ids"].copy_(input_ids, non_blocking=True)
+        st["images"].copy_(images, non_blocking=True)
+        if st["q"] is not None:
+            st["q"].copy_(question_ids, non_blocking=True)
+        st["graph"].replay()
+        _lib.add_launches(st["n"])
+        return st["logits"].clone()
 
     # =========================================================================================
     # decoder: prefill

@@ -249,6 +249,13 @@ class U2MetaForCausalLM(ABC):
             raise NotImplementedError("HF-driven cached decoding is not supported; call generate() "
                                       "(greedy decode runs inside the engine with its own static KV cache)")
         eng = self.engine()
+        if (inputs_embeds is None and labels is None and images is not None and self.get_vision_tower() is not None
+                and input_ids is not None and input_ids.shape[1] != 1):
+            # inference-style forward with images: one call into the engine, replayed as a CUDA graph when the shapes repeat
+            logits = eng.forward_logits(input_ids, images, question_ids)
+            if return_dict is False:
+                return (logits,)
+            return CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=None)
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels
              ) = self.prepare_inputs_for_multimodal(input_ids, position_ids, attention_mask, past_key_values, labels,
