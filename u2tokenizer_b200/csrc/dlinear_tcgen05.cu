@@ -553,7 +553,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
                 const float me = __bfloat162float(__float2bfloat16(val));
                 const float other = __shfl_down_sync(0xffffffffu, me, 1);
                 if (row_ok && (trow & 1) == 0) {
-                  const float o = me / (1.f + __expf(-me)) * other;
+                  const float o = __fdividef(me, 1.f + __expf(-me)) * other;
                   reinterpret_cast<__nv_bfloat16*>(p.y)[(long long)b * p.ldy + (row >> 1)] = __float2bfloat16(o);
                 }
               } else if (row_ok) {

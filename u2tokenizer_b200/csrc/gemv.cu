@@ -167,7 +167,7 @@ gemv_kernel(const GemvArgs a) {
             // unfused path rounds gate/up to bf16 before the activation: keep the same rounding points
             const float g = __bfloat162float(__float2bfloat16(v));
             const float u = __bfloat162float(__float2bfloat16(acc[1][r][b]));
-            v = g / (1.f + __expf(-g)) * u;
+            v = __fdividef(g, 1.f + __expf(-g)) * u;
           }
           if (a.residual) v += __bfloat162float(a.residual[b * a.ldr + n]);
           if (a.y_dtype == U2_DT_BF16) reinterpret_cast<__nv_bfloat16*>(a.y)[b * a.ldy + n] = __float2bfloat16(v);

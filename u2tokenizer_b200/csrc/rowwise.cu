@@ -298,7 +298,7 @@ silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict_
       unpack8(reinterpret_cast<const uint4*>(gu + r * ldg + I)[c], u);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = g[j] / (1.f + __expf(-g[j])) * u[j];
+    for (int j = 0; j < 8; ++j) o[j] = __fdividef(g[j], 1.f + __expf(-g[j])) * u[j];
     reinterpret_cast<uint4*>(out + r * ldo)[c] = pack8(o);
   }
 }
