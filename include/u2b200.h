@@ -290,7 +290,7 @@ U2_API int u2_decode_attention_fused_bf16(const void* qkv, void* k_cache, void* 
                                           const u2_fused_decode_desc* desc, void* stream);
 
 /* Row-wise top-k of fp32 scores, sorted descending (ties: lower index first), as torch.topk in the hard
- * TokenSelection (reference svr.py:75-91). out_idx[r, i] = index + r * idx_offset_per_row (int64). T <= 8192. */
+ * TokenSelection (reference svr.py:75-91). out_idx[r, i] = index + r * idx_offset_per_row (int64). T <= 16384. */
 U2_API int u2_topk_rows_f32(const float* scores, int64_t* out_idx, int32_t rows, int32_t T, int32_t K, int64_t ld,
                             int64_t idx_offset_per_row, void* stream);
 

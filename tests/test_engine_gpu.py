@@ -175,13 +175,15 @@ def test_u2tokenizer_hard_selection():
         check(got, ref, what="hard-selection tokenizer")
 
 
-def test_reference_smoke_shape_svr():
+@pytest.mark.parametrize("diffts,dmtp", [(True, True), (False, False)])
+def test_reference_smoke_shape_svr(diffts, dmtp):
     """The reference's own SVR smoke run (src/model/u2tokenizer/svr.py:190-205): attn_type "rope", E = 512, 8 heads,
     4 layers, top_k 1024, multi-scale, input [1, 64, 256, 512] -> (1, 1792, 512) - one of the only two "known answers"
-    the reference holds. 64 frames -> temporal attention over 64 positions and a 16384-token
-    DiffTS softmax; the rest of the tokenizer runs on top with a short question."""
+    the reference holds. 64 frames -> temporal attention over 64 positions; (False, False) is the
+    smoke block's own configuration (hard top-k over 16384 tokens, plain multi-scale pooling), (True, True) the
+    canonical one (a 16384-token DiffTS softmax). The rest of the tokenizer runs on top with a short question."""
     g = tiny_geometry(hidden_size=512, attn_type="rope", u2t_num_heads=8, u2t_num_layers=4, u2t_top_k=1024,
-                      use_multi_scale=True, num_3d_query_token=8)
+                      use_multi_scale=True, num_3d_query_token=8, enable_diffts=diffts, enable_dmtp=dmtp)
     eng, sd = build(g, 11)
     gen = torch.Generator().manual_seed(5)
     v = torch.randn(1, 64, 256, 512, generator=gen).bfloat16()

@@ -448,7 +448,7 @@ def test_dlinear_multi_chain(B, E, I, NQ, sched, fine):
             close(outs[it][2], a, 3e-2)
 
 
-@pytest.mark.parametrize("T,K", [(2048, 1024), (24, 8), (8192, 1024), (100, 100), (5, 1)])
+@pytest.mark.parametrize("T,K", [(2048, 1024), (24, 8), (8192, 1024), (100, 100), (5, 1), (16384, 1024), (9000, 3)])
 def test_topk_rows(T, K):
     """Index work: bit-exact against torch.topk (sorted descending) on the same fp32 scores, ties included."""
     from u2tokenizer_b200 import ops

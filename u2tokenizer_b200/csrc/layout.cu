@@ -511,14 +511,14 @@ extern "C" U2_API int u2_topk_rows_f32(const float* scores, int64_t* out_idx, in
   using namespace u2;
   if (!scores || !out_idx) return set_error(U2_ERR_ARG, "topk: null pointer");
   if (K <= 0 || K > T) return set_error(U2_ERR_ARG, "topk: need 0 < K <= T (reference torch.topk raises too)");
-  if (T > 8192) return set_error(U2_ERR_UNSUPPORTED, "topk: T=%d > 8192", T);
+  if (T > 16384) return set_error(U2_ERR_UNSUPPORTED, "topk: T=%d > 16384 (keys are sorted in shared memory)", T);
   if (rows <= 0) return U2_OK;
   int n_pad = 1;
   while (n_pad < T) n_pad <<= 1;
   const size_t smem = (size_t)n_pad * sizeof(unsigned long long);
   static bool cfgd = false;
   if (!cfgd) {
-    cudaError_t e = cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+    cudaError_t e = cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "topk smem: %s", cudaGetErrorString(e));
     cfgd = true;
   }
