@@ -147,3 +147,51 @@ def test_decoder_matches_hf(family):
         want2 = hf(inputs_embeds=nxt, past_key_values=want.past_key_values, use_cache=True).logits
         got2, _ = O.decoder_forward(sd, nxt, g, past)
         assert rel_err(got2, want2) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own two smoke runs (the only "known answers" it holds)
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("diffts,dmtp", [(False, False), (True, True)])
+def test_reference_smoke_run_svr(diffts, dmtp):
+    """src/model/u2tokenizer/svr.py:190-205: SpatioTemporalVisualTokenRefinerModel(512, 8 heads, 4 layers, top_k 1024,
+    multi-scale, "rope") on [1, 64, 256, 512] prints (1, 1792, 512). (False, False) is that block's own configuration,
+    (True, True) the canonical DiffTS + DMTP one."""
+    refshim.install()
+    from src.model.u2tokenizer.svr import SpatioTemporalVisualTokenRefinerModel
+    g = tiny_geometry(hidden_size=512, attn_type="rope", u2t_num_heads=8, u2t_num_layers=4, u2t_top_k=1024,
+                      use_multi_scale=True, enable_diffts=diffts, enable_dmtp=dmtp)
+    sd = fp32_sd(g, seed=11)
+    ref = SpatioTemporalVisualTokenRefinerModel(embed_size=512, num_heads=8, num_layers=4, top_k=1024, use_multi_scale=True,
+                                                attn_type="rope", enable_diffts=diffts, enable_dmtp=dmtp)
+    ref.load_state_dict(_sub(sd, "model.u2tokenizer.svt_module."), strict=True)
+    x = torch.randn(1, 64, 256, 512, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = ref(x)
+        got = O.svr(sd, "model.u2tokenizer.svt_module.", x, g)
+    assert tuple(want.shape) == (1, 1792, 512) == tuple(got.shape)     # the shape the reference prints
+    # hard selection over 16384 near-identical scores is decided by the last float bits: the selected SET may differ
+    # between two fp32 evaluations, the selected VALUES (and everything downstream) may not
+    assert rel_err(got, want) < (TOL if diffts else 1e-3)
+
+
+@needs_ref
+def test_reference_smoke_run_tta():
+    """src/model/u2tokenizer/tta.py:142-151: TextConditionTokenAggregatorModel(896, 4 layers, 8 heads, "rope") on query
+    [1, 64, 896], visual [1, 1792, 896], text [1, 755, 896] prints (1, 64, 896)."""
+    refshim.install()
+    from src.model.u2tokenizer.tta import TextConditionTokenAggregatorModel
+    g = tiny_geometry(hidden_size=896, attn_type="rope", u2t_num_heads=8, u2t_num_layers=4)
+    sd = fp32_sd(g, seed=12)
+    ref = TextConditionTokenAggregatorModel(896, 4, 8, attn_type="rope")
+    ref.load_state_dict(_sub(sd, "model.u2tokenizer.tta_module."), strict=True)
+    gen = torch.Generator().manual_seed(6)
+    q = torch.randn(1, 64, 896, generator=gen)
+    vis = torch.randn(1, 1792, 896, generator=gen)
+    txt = torch.randn(1, 755, 896, generator=gen)
+    with torch.no_grad():
+        want = ref(q, vis, txt)
+        got = O.tta(sd, "model.u2tokenizer.tta_module.", q, vis, txt, g)
+    assert tuple(want.shape) == (1, 64, 896) == tuple(got.shape)       # the shape the reference prints
+    assert rel_err(got, want) < TOL
