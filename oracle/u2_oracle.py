@@ -128,7 +128,7 @@ def rma(sd: SD, pre: str, x: torch.Tensor, h: int, max_seq_len: int = 512) -> to
     k = _split_heads(_lin(x, sd, pre + "wk"), h)
     v = _split_heads(_lin(x, sd, pre + "wv"), h)
     scores = q @ k.transpose(-2, -1) / math.sqrt(dh)
-    pos = torch.arange(s)
+    pos = torch.arange(s, device=x.device)
     idx = pos[None, :] - pos[:, None] + max_seq_len - 1
     scores = scores + sd[pre + "relative_bias"][idx].permute(2, 0, 1).unsqueeze(0)
     ctx = torch.softmax(scores, dim=-1) @ v
@@ -149,10 +149,10 @@ def rope_mha(sd: SD, pre: str, x: torch.Tensor, h: int) -> torch.Tensor:
     q = _split_heads(_lin(x, sd, pre + "wq"), h)
     k = _split_heads(_lin(x, sd, pre + "wk"), h)
     v = _split_heads(_lin(x, sd, pre + "wv"), h)
-    inv = 1.0 / (10000 ** (torch.arange(0, dh, 2, dtype=torch.float32) / dh))
-    fr = torch.outer(torch.arange(s, dtype=torch.float32), inv)
+    inv = 1.0 / (10000 ** (torch.arange(0, dh, 2, dtype=torch.float32, device=x.device) / dh))
+    fr = torch.outer(torch.arange(s, dtype=torch.float32, device=x.device), inv)
     emb = torch.cat((fr, fr), dim=-1)
-    cos, sin = emb.cos()[None, None], emb.sin()[None, None]
+    cos, sin = emb.cos()[None, None].to(x.dtype), emb.sin()[None, None].to(x.dtype)
     q = q * cos + _rotate_half(q) * sin
     k = k * cos + _rotate_half(k) * sin
     ctx = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dh), dim=-1) @ v
@@ -199,7 +199,7 @@ def token_selection_hard(sd: SD, pre: str, x: torch.Tensor, top_k: int) -> torch
     b, t, n, e = x.shape
     scores = _lin(x, sd, pre + "score_net").squeeze(-1).view(b, -1)
     _, idx = torch.topk(scores, top_k, dim=1)
-    return x.view(b, t * n, e)[torch.arange(b).unsqueeze(1), idx]
+    return x.view(b, t * n, e)[torch.arange(b, device=x.device).unsqueeze(1), idx]
 
 
 def token_selection_diff(sd: SD, pre: str, x: torch.Tensor, tau: float = 1.0) -> torch.Tensor:
@@ -325,14 +325,15 @@ def decoder_forward(sd: SD, inputs_embeds: torch.Tensor, cfg, past=None, return_
     hq, hkv, dh = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
     eps = cfg.rms_norm_eps
     past_len = 0 if past is None else past[0][0].shape[2]
-    pos = torch.arange(past_len, past_len + s, dtype=torch.float32)
-    fr = torch.outer(pos, rope_inv_freq(cfg))
+    dev = inputs_embeds.device
+    pos = torch.arange(past_len, past_len + s, dtype=torch.float32, device=dev)
+    fr = torch.outer(pos, rope_inv_freq(cfg).to(dev))
     emb = torch.cat((fr, fr), dim=-1)
-    cos, sin = emb.cos()[None, None], emb.sin()[None, None]
+    cos, sin = emb.cos()[None, None].to(inputs_embeds.dtype), emb.sin()[None, None].to(inputs_embeds.dtype)
     x = inputs_embeds
     new_past = []
     total = past_len + s
-    mask = torch.full((s, total), float("-inf")).triu(diagonal=past_len + 1)
+    mask = torch.full((s, total), float("-inf"), device=dev, dtype=inputs_embeds.dtype).triu(diagonal=past_len + 1)
     for i in range(cfg.num_hidden_layers):
         lp = f"model.layers.{i}."
         y = _rms(x, sd[lp + "input_layernorm.weight"], eps)
@@ -379,7 +380,7 @@ def greedy_generate(sd: SD, input_ids, images, question_ids, cfg, max_new_tokens
     logits, past = decoder_forward(sd, emb, cfg)
     out, margins = [], []
     b = emb.shape[0]
-    done = torch.zeros(b, dtype=torch.bool)
+    done = torch.zeros(b, dtype=torch.bool, device=emb.device)
     for _ in range(max_new_tokens):
         last = logits[:, -1]
         top2 = last.topk(2, dim=-1).values

@@ -1,0 +1,153 @@
+"""Full-depth parity at the BENCHMARKED configurations.
+
+The fp32 oracle (oracle/u2_oracle.py, pure functional torch) runs ON THE GPU as the checker - it finishes the
+whole mu2-Qwen3-1.7B / -8B forward in seconds there - against the CUDA engine at
+
+  * cfg 2 dimensions: E = 2048, ViT-B/12, 4 + 4 tokenizer layers, 28 decoder layers, C = 4 frames of 32 x 256 x 256,
+    Lt = 512, prompt L = 288, vocabulary 151 936 (tied head);
+  * cfg 3 dimensions: E = 4096 (tokenizer head_dim 512), 36 decoder layers, C = 8 frames, batch 4, 256 greedy steps.
+
+Checked: every module boundary (vision tower + projector, mu2-tokenizer, spliced embeddings, final hidden states,
+logits) and the greedy decode. Tolerances (bf16 product path vs fp32 oracle on the same bf16-rounded weights):
+
+  per boundary   max|out - ref| / max|ref| <= max(3e-2, 1.5 x the error of STOCK bf16 eager PyTorch running the same
+                 oracle functions on the same GPU) and cosine >= 0.999 - i.e. the hand-written path may not be worse
+                 than cuBLAS / ATen bf16 eager by more than 1.5 x;
+  greedy ids     teacher-forced on the oracle's ids (a near-tie cannot derail the rest of the sequence), the engine's
+                 own pick must EQUAL the oracle's at every step whose oracle top-1 / top-2 margin exceeds
+                 thr = 4 x max|logit error| measured on the prompt logits; the test prints compared / total and, for
+                 cfg 3 (decisive "bigram" head, synthetic.py), asserts that >= 95 % of the 4 x 256 tokens are compared.
+"""
+import gc
+import os
+
+import pytest
+import torch
+
+from common import cosine, rel_err
+from oracle import u2_oracle as O
+from u2tokenizer_b200.synthetic import synthetic_inputs, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+TOL, COS = 3e-2, 0.999
+
+
+def _geom(which: str):
+    from u2tokenizer_b200.configuration import QWEN3_1P7B, QWEN3_8B, U2Qwen3Config
+    from u2tokenizer_b200.geometry import Geometry
+    return Geometry.from_hf(U2Qwen3Config(**(QWEN3_1P7B if which == "cfg2" else QWEN3_8B)))
+
+
+def _oracle_stages(sd, g, images, ids, qids, frame_chunk=8):
+    """fp32 (or bf16-eager) oracle outputs at every module boundary; frames in chunks to bound the materialised
+    [frames, 12, 2049, 2049] ViT attention."""
+    B, C = images.shape[:2]
+    fr = images.view(B * C, 1, *images.shape[2:]).to(next(iter(sd.values())).dtype)
+    feats = torch.cat([O.encode_images(sd, fr[i:i + frame_chunk], g) for i in range(0, B * C, frame_chunk)])
+    v_tokens = feats.view(B, C, feats.shape[-2], feats.shape[-1])
+    t_tokens = torch.nn.functional.embedding(qids, sd["model.embed_tokens.weight"])
+    vis = O.u2tokenizer(sd, "model.u2tokenizer.", v_tokens, t_tokens, g)
+    emb = torch.nn.functional.embedding(ids, sd["model.embed_tokens.weight"])
+    emb = torch.cat((emb[:, :1], vis, emb[:, vis.shape[1] + 1:]), dim=1)
+    hidden, past = O.decoder_forward(sd, emb, g, return_hidden=True)
+    head = sd["lm_head.weight"] if "lm_head.weight" in sd else sd["model.embed_tokens.weight"]
+    logits = torch.nn.functional.linear(hidden, head)
+    return dict(encode_images=feats, u2tokenizer=vis, multimodal_embeds=emb, final_hidden=hidden, logits=logits), past
+
+
+@torch.no_grad()
+def _oracle_greedy(sd, g, logits, past, n_new):
+    out, margins = [], []
+    for _ in range(n_new):
+        last = logits[:, -1]
+        top2 = last.topk(2, dim=-1).values
+        margins.append(top2[:, 0] - top2[:, 1])
+        nxt = last.argmax(-1)
+        out.append(nxt)
+        logits, past = O.decoder_forward(sd, torch.nn.functional.embedding(nxt[:, None], sd["model.embed_tokens.weight"]), g, past)
+    return torch.stack(out, 1), torch.stack(margins, 1)
+
+
+def _run(which, batch, frames, n_new, lt, head_kw, min_compared):
+    from u2tokenizer_b200.engine import U2Engine
+    g = _geom(which)
+    dev = "cuda"
+    sd16 = synthetic_state_dict(g, seed=0, device=dev, dtype=torch.bfloat16, **head_kw)
+    eng = U2Engine(g, sd16, device=dev)
+    images, ids, qids = synthetic_inputs(g, batch=batch, frames=frames, n_question=32, lt=lt, device=dev)
+    report = {}
+    with torch.no_grad():
+        # ---- stock bf16 eager PyTorch on the same functions: the yardstick for "bf16 error at this depth"
+        eager, _ = _oracle_stages(sd16, g, images, ids, qids)
+        eager = {k: v.float() for k, v in eager.items()}
+        sd32 = {k: v.float() for k, v in sd16.items()}
+        del sd16
+        ref, past = _oracle_stages(sd32, g, images, ids, qids)
+        # ---- the CUDA engine, boundary by boundary (each stage fed by the ENGINE's previous stage: errors accumulate
+        # exactly as they do in production)
+        B, C = images.shape[:2]
+        got = {}
+        got["encode_images"] = eng.encode_images(images.view(B * C, 1, *images.shape[2:]))
+        t_tokens = eng.embed_tokens(qids)
+        got["u2tokenizer"] = eng.u2tokenizer(got["encode_images"].view(B, C, -1, g.hidden_size), t_tokens)
+        got["multimodal_embeds"] = eng.multimodal_embeds(ids, images, qids)
+        got["final_hidden"] = eng.prefill(got["multimodal_embeds"])
+        got["logits"] = eng.lm_logits(got["final_hidden"])
+        bad = []
+        for k in ("encode_images", "u2tokenizer", "multimodal_embeds", "final_hidden", "logits"):
+            e, c = rel_err(got[k], ref[k]), cosine(got[k], ref[k])
+            ee, ce = rel_err(eager[k], ref[k]), cosine(eager[k], ref[k])
+            report[k] = dict(rel_err=e, cosine=c, eager_bf16_rel_err=ee, eager_bf16_cosine=ce)
+            print(f"[{which}] {k:18s} engine rel_err {e:.4g} cos {c:.6f} | stock bf16 eager rel_err {ee:.4g} cos {ce:.6f}")
+            if not (e <= max(TOL, 1.5 * ee) and c >= min(COS, ce - 1e-4)):
+                bad.append(k)
+        thr = 4.0 * (got["logits"].float() - ref["logits"]).abs().max().item()
+        max_logit = ref["logits"].abs().max().item()
+        # ---- greedy decode: the oracle free-runs, the engine is teacher-forced on the oracle's ids
+        ref_ids, margins = _oracle_greedy(sd32, g, ref["logits"], past, n_new)
+        del past, sd32, eager
+        gc.collect()
+        torch.cuda.empty_cache()
+        step_logits = []
+        own = eng.generate_greedy(got["multimodal_embeds"], n_new, use_graph=True, force_ids=ref_ids, logits_out=step_logits)
+        free = eng.generate_greedy(got["multimodal_embeds"], n_new, use_graph=True)
+    decisive = margins >= thr
+    agree = own == ref_ids
+    n_cmp, n_tot = int(decisive.sum()), decisive.numel()
+    n_bad = int((decisive & ~agree).sum())
+    # free-running: identical up to (excluding) each sequence's first low-margin step
+    free_ok, free_cmp = True, 0
+    for b in range(batch):
+        low = (~decisive[b]).nonzero()
+        upto = int(low[0]) if len(low) else n_new
+        free_cmp += upto
+        free_ok &= bool(torch.equal(free[b, :upto], ref_ids[b, :upto]))
+    print(f"[{which}] greedy: thr {thr:.4g} (max|logit| {max_logit:.4g}, median margin {margins.median().item():.4g}); "
+          f"teacher-forced compared {n_cmp}/{n_tot} tokens, mismatches {n_bad}; all-steps agreement "
+          f"{int(agree.sum())}/{n_tot}; free-running identical prefix {free_cmp}/{n_tot} ok={free_ok}; "
+          f"distinct ids per sequence {[len(set(r.tolist())) for r in ref_ids]}")
+    os.makedirs(os.path.join(os.path.dirname(__file__), "..", "gpurun_out"), exist_ok=True)
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", f"fulldepth_{which}.json"), "w") as f:
+        json.dump(dict(stages=report, thr=thr, max_logit=max_logit, compared=n_cmp, total=n_tot, mismatches=n_bad,
+                       agree_all=int(agree.sum()), free_prefix=free_cmp, free_ok=free_ok), f, indent=1)
+    assert not bad, f"stages out of tolerance: {bad} {report}"
+    assert n_bad == 0, f"{n_bad} decisive-margin tokens differ"
+    assert free_ok
+    assert n_cmp >= min_compared * n_tot, f"only {n_cmp}/{n_tot} tokens had a decisive margin"
+    del eng
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def test_cfg2_full_depth_forward_and_greedy():
+    """BASELINE cfg 2: mu2-Qwen3-1.7B (tied head), ONE 256 x 256 x 128 volume (4 frames), prompt 288, Lt 512; plus 64
+    greedy steps. The head is tied, so only the log-normal row-norm profile is available to sharpen the margins
+    (compared / total is reported, not bounded)."""
+    _run("cfg2", batch=1, frames=4, n_new=64, lt=512, head_kw=dict(head_tail=1.5), min_compared=0.0)
+
+
+def test_cfg3_full_depth_generate():
+    """BASELINE cfg 3: mu2-Qwen3-8B, batch 4, 256^3 volumes (8 frames), 256 greedy tokens, bigram-structured head:
+    >= 95 % of the 4 x 256 tokens must have a decisive margin and every one of them must be identical."""
+    _run("cfg3", batch=4, frames=8, n_new=256, lt=512, head_kw=dict(bigram=1.0), min_compared=0.95)

@@ -722,7 +722,16 @@ class U2Engine:
         try:
             if num_return_sequences > 1:
                 return self._generate_multi(embeds, max_new_tokens, eos_token_id, use_graph, int(num_return_sequences))
-            return self.generate_greedy(embeds, max_new_tokens, eos_token_id=eos_token_id, use_graph=use_graph)
+            cap = 16 if self._use_tc_decode(16) else 8  # sequences one decode step can carry (dlinear N / gemv batch)
+            if embeds.shape[0] <= cap:
+                return self.generate_greedy(embeds, max_new_tokens, eos_token_id=eos_token_id, use_graph=use_graph)
+            outs = [self.generate_greedy(embeds[b0:b0 + cap].contiguous(), max_new_tokens, eos_token_id=eos_token_id,
+                                         use_graph=use_graph) for b0 in range(0, embeds.shape[0], cap)]
+            width = max(o.shape[1] for o in outs)
+            if any(o.shape[1] != width for o in outs):  # chunks that hit EOS early: pad with EOS (masked by the caller)
+                fill = eos_token_id[0] if isinstance(eos_token_id, (list, tuple)) else eos_token_id
+                outs = [torch.nn.functional.pad(o, (0, width - o.shape[1]), value=int(fill)) for o in outs]
+            return torch.cat(outs, dim=0)
         finally:
             self._sampling = None
 
@@ -739,17 +748,22 @@ class U2Engine:
         return st
 
     def generate_greedy(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id=None,
-                        use_graph: bool = True, return_margins: bool = False):
+                        use_graph: bool = True, return_margins: bool = False, force_ids: Optional[torch.Tensor] = None,
+                        logits_out: Optional[list] = None):
         """Prefill on `embeds` [B, L, E], then max_new_tokens decode steps (greedy unless a sampling configuration
         was installed by generate()). Returns new ids [B, n] (and the per-step top-1/top-2 logit margins when
-        asked, for margin-aware parity checks)."""
+        asked, for margin-aware parity checks).
+        force_ids [B, n] (parity tests): teacher forcing - the returned ids are still this engine's own picks, but the
+        token fed to the next step is force_ids[:, step], so one near-tie cannot derail the rest of the comparison.
+        logits_out: a list that receives a copy of every step's fp32 logits [B, V]."""
         B, L, _ = embeds.shape
         st = self._gen_state_for(B, L + max_new_tokens)
         cache = st["cache"]
         cache.set_length(0)
         hidden = self.prefill(embeds, cache)
         logits0 = self.lm_logits(hidden[:, -1].contiguous())
-        return self._decode_loop(st, logits0, max_new_tokens, eos_token_id, use_graph, return_margins)
+        return self._decode_loop(st, logits0, max_new_tokens, eos_token_id, use_graph, return_margins,
+                                 force_ids=force_ids, logits_out=logits_out)
 
     def _generate_multi(self, embeds: torch.Tensor, max_new_tokens: int, eos_token_id, use_graph: bool, n: int):
         B, L, _ = embeds.shape
@@ -777,7 +791,7 @@ class U2Engine:
         return torch.cat(outs, dim=0)
 
     def _decode_loop(self, st, logits0: torch.Tensor, max_new_tokens: int, eos_token_id, use_graph: bool,
-                     return_margins: bool):
+                     return_margins: bool, force_ids: Optional[torch.Tensor] = None, logits_out: Optional[list] = None):
         """Pick the first token from `logits0`, then run max_new_tokens - 1 decode steps on st['cache'] (whose length
         is the prompt length); the steps after the first replay one captured CUDA graph."""
         from . import _lib
@@ -789,6 +803,11 @@ class U2Engine:
         margins = []
         self._pick_next(logits0, bufs["ids"].view(B), None, step=0)
         out[:, 0] = bufs["ids"].view(B)
+        if logits_out is not None:
+            logits_out.append(logits0.float().clone())
+        if force_ids is not None:
+            force_ids = force_ids.to(self.dev, torch.int64)
+            bufs["ids"].view(B).copy_(force_ids[:, 0])
         if return_margins:
             t2 = logits0.topk(2, dim=-1).values
             margins.append(t2[:, 0] - t2[:, 1])
@@ -825,6 +844,10 @@ class U2Engine:
                     t2 = lg.topk(2, dim=-1).values
                     margins.append(t2[:, 0] - t2[:, 1])
             out[:, step] = bufs["ids"].view(B)
+            if logits_out is not None:
+                logits_out.append(bufs["logits"].clone())
+            if force_ids is not None:
+                bufs["ids"].view(B).copy_(force_ids[:, step])
             n_done += 1
         res = out[:, :n_done]
         if return_margins:

@@ -178,6 +178,11 @@ class U2MetaForCausalLM(ABC):
     def engine(self):
         """Build (once) the CUDA engine from this module's current parameters."""
         eng = self.__dict__.get("_u2_engine")
+        if eng is not None and self.__dict__.get("_u2_engine_stamp") != self._param_stamp():
+            # some parameter changed in place since the engine copied / fused the weights (optimizer step, p.copy_, a
+            # re-pointed p.data, a submodule load_state_dict): the fused copies are stale -> rebuild, never serve them
+            self.invalidate_engine()
+            eng = None
         if eng is None:
             from .engine import U2Engine
             p = next(self.parameters())
@@ -187,10 +192,23 @@ class U2MetaForCausalLM(ABC):
             sd = {k: v for k, v in self.state_dict().items()}
             eng = U2Engine(Geometry.from_hf(self.config), sd, device=p.device)
             self.__dict__["_u2_engine"] = eng
+            self.__dict__["_u2_engine_stamp"] = self._param_stamp()
+            if not self.__dict__.get("_u2_hooks"):
+                # submodule.load_state_dict(...) does not pass through this module's load_state_dict override
+                for m in self.modules():
+                    m.register_load_state_dict_post_hook(lambda mod, keys, root=self: root.invalidate_engine())
+                self.__dict__["_u2_hooks"] = True
         return eng
+
+    def _param_stamp(self):
+        """(storage address, autograd version counter) of every parameter: in-place updates through the parameter bump
+        the counter, `p.data = ...` changes the address. Writers that go through `p.data` IN PLACE (which torch does
+        not track) must call invalidate_engine() themselves - parallel.Zero1Step and the training engine do."""
+        return tuple((q.data_ptr(), q._version) for q in self.parameters())
 
     def invalidate_engine(self):
         self.__dict__.pop("_u2_engine", None)
+        self.__dict__.pop("_u2_engine_stamp", None)
 
     def load_state_dict(self, *a, **k):
         self.invalidate_engine()
@@ -239,6 +257,17 @@ class U2MetaForCausalLM(ABC):
                 raise ValueError(f"Unexpected embed_tokens_weight shape. Pretrained: {etw.shape}. Current: {inp.shape}. "
                                  f"Numer of new tokens: {num_new_tokens}.")
 
+    @staticmethod
+    def _check_right_padded(attention_mask):
+        """The fused path has no padding mask: a RIGHT-padded batch is exact under the causal mask (real tokens never
+        attend to the pads on their right), anything else (left padding, holes) would silently change the result."""
+        if attention_mask is None:
+            return
+        m = attention_mask.to(torch.bool)
+        if m.dim() != 2 or bool((m[:, 1:] & ~m[:, :-1]).any()) or not bool(m[:, 0].all()):
+            raise NotImplementedError("attention_mask must be all ones or right-padded (left-padded / sparse masks are "
+                                      "not supported by the fused CUDA path)")
+
     # ---- forward / generate shared by the Llama and Qwen3 wrappers (reference u2llama.py:41-138) ----
     def _u2_forward(self, images=None, input_ids=None, labels=None, attention_mask=None, question_ids=None,
                     position_ids=None, past_key_values=None, inputs_embeds=None, use_cache=None,
@@ -248,6 +277,7 @@ class U2MetaForCausalLM(ABC):
         if past_key_values is not None:
             raise NotImplementedError("HF-driven cached decoding is not supported; call generate() "
                                       "(greedy decode runs inside the engine with its own static KV cache)")
+        self._check_right_padded(attention_mask)
         eng = self.engine()
         if (inputs_embeds is None and labels is None and images is not None and self.get_vision_tower() is not None
                 and input_ids is not None and input_ids.shape[1] != 1):
@@ -284,6 +314,7 @@ class U2MetaForCausalLM(ABC):
         343-350) without the [B, L, V] logits: labels are `input_ids` rolled left by one, positions whose rolled
         `loss_mask` is 0 contribute 0, the result is rolled back right by one. Returns a dict with `per_token_logps`
         [B, L] fp32, `all_logps` [B] and `mean_logits` (mean of the masked rows' logits, as the trainer logs it)."""
+        self._check_right_padded(attention_mask)
         eng = self.engine()
         (_, _, _, _, inputs_embeds, _) = self.prepare_inputs_for_multimodal(input_ids, None, attention_mask, None, None,
                                                                             images, question_ids)
@@ -347,6 +378,28 @@ class U2MetaForCausalLM(ABC):
         if pad is None and gc is not None:
             pad = gc.pad_token_id
         n_ret = int(opt("num_return_sequences", 1))
+        # options that would change the generated ids and are not implemented on the CUDA path must not be dropped
+        # silently; pure output-format / cache switches are accepted
+        neutral = {"repetition_penalty": 1.0, "no_repeat_ngram_size": 0, "min_new_tokens": 0, "min_length": 0,
+                   "length_penalty": 1.0, "encoder_repetition_penalty": 1.0, "typical_p": 1.0, "epsilon_cutoff": 0.0,
+                   "eta_cutoff": 0.0, "min_p": None, "bad_words_ids": None, "force_words_ids": None,
+                   "suppress_tokens": None, "begin_suppress_tokens": None, "logits_processor": None,
+                   "stopping_criteria": None, "prefix_allowed_tokens_fn": None, "penalty_alpha": None,
+                   "num_beam_groups": 1, "diversity_penalty": 0.0}
+        for k in list(kwargs):
+            if k in neutral:
+                v = kwargs.pop(k)
+                if v is not None and v != neutral[k] and v != [] and v != 0:
+                    raise NotImplementedError(f"generate({k}={v!r}) is not implemented on the CUDA path")
+            elif k in ("use_cache", "return_dict_in_generate", "output_scores", "output_logits", "output_attentions",
+                       "output_hidden_states", "synced_gpus", "streamer", "generation_config", "bos_token_id",
+                       "cache_implementation", "tokenizer"):
+                v = kwargs.pop(k)
+                if k in ("return_dict_in_generate", "output_scores", "output_logits", "output_attentions",
+                         "output_hidden_states") and v:
+                    raise NotImplementedError(f"generate({k}=True) is not implemented on the CUDA path")
+        if kwargs:
+            raise TypeError(f"generate() got unsupported arguments {sorted(kwargs)}")
         if n_ret > 1 and not do_sample:
             raise ValueError("num_return_sequences > 1 needs do_sample=True (greedy decoding is deterministic; HF raises too)")
         ids = eng.generate(inputs_embeds.to(torch.bfloat16), max_new_tokens=max_new, eos_token_id=eos,

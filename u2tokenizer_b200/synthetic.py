@@ -112,10 +112,24 @@ def _std_for(name: str, shape) -> Tuple[float, float]:
 
 
 @torch.no_grad()
-def synthetic_state_dict(g: Geometry, seed: int = 0, device="cpu", dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+def synthetic_state_dict(g: Geometry, seed: int = 0, device="cpu", dtype=torch.bfloat16,
+                         head_tail: float = 0.0, bigram: float = 0.0) -> Dict[str, torch.Tensor]:
     """Every parameter drawn from its own seeded generator (name-hashed), so a CPU oracle copy and a
     GPU product copy built from the same (geometry, seed) hold bit-identical bf16 values when both
-    are generated on the CPU; for the big benchmark models generation happens on the device."""
+    are generated on the CPU; for the big benchmark models generation happens on the device.
+
+    head_tail > 0 gives the output head a "trained-like" peaky structure: row v of lm_head (of embed_tokens when the
+    head is tied) is scaled by exp(head_tail * n_v), n_v ~ N(0, 1). An i.i.d. Gaussian head makes the top-1 / top-2
+    logit gap ~ 1 / (2 ln V) of the top logit, i.e. comparable to the bf16 error, so greedy token ids could not be
+    compared at all; with log-normal row norms the leading candidates are separated by a finite fraction of the top
+    logit and greedy parity becomes a real check.
+
+    bigram > 0 (untied heads only) gives the decoder "trained-like" bigram statistics instead: embed_tokens rows are
+    N(0, s^2) with s = bigram * 0.7 * sqrt(2 * layers) (so the token's own embedding is `bigram` times the random-walk
+    norm of the 2 * layers residual-branch outputs) and lm_head row pi(v) is the direction of embed_tokens row v for a
+    seeded permutation pi: the preferred next token of v is pi(v) with a margin that is a finite fraction of the top
+    logit, the layers' contribution perturbs (and sometimes overrides) it. Greedy ids then walk through the vocabulary
+    instead of repeating one id, and nearly every step has a decisive top-1 / top-2 margin."""
     out = {}
     dev = torch.device(device)
     for i, (name, shape) in enumerate(param_shapes(g).items()):
@@ -129,6 +143,23 @@ def synthetic_state_dict(g: Geometry, seed: int = 0, device="cpu", dtype=torch.b
         else:
             t = (torch.randn(shape, device=dev, generator=gen) * std + mean).to(dtype)
         out[name] = t
+    if head_tail > 0:
+        name = "lm_head.weight" if "lm_head.weight" in out else "model.embed_tokens.weight"
+        gen = torch.Generator(device=dev).manual_seed(seed * 1000003 + 999331)
+        scale = torch.exp(head_tail * torch.randn(out[name].shape[0], 1, device=dev, generator=gen))
+        out[name] = (out[name].float() * scale).to(dtype)
+    if bigram > 0:
+        if "lm_head.weight" not in out:
+            raise ValueError("bigram structure needs an untied output head")
+        V, E = out["lm_head.weight"].shape
+        gen = torch.Generator(device=dev).manual_seed(seed * 1000003 + 999332)
+        perm = torch.randperm(V, device=dev, generator=gen)
+        s_e = bigram * 0.7 * (2 * g.num_hidden_layers) ** 0.5
+        emb = torch.empty(V, E, device=dev, dtype=dtype).normal_(0.0, 1.0, generator=gen)
+        head = torch.empty_like(emb)
+        head[perm] = (emb.float() * 0.05).to(dtype) if V * E <= (1 << 26) else emb.mul(0.05)
+        out["lm_head.weight"] = head
+        out["model.embed_tokens.weight"] = emb.mul_(s_e)
     return out
 
 
