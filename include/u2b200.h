@@ -50,7 +50,8 @@ U2_API int u2_device_sm_count(void);         /* SMs of the current device (148 o
 /* GEMM --------------------------------------------------------------------------------------------
  * For every batch z = (zo, zi):
  *     C[z] (M x N) = act( alpha * A[z] (M x K) * B[z'] (N x K)^T + bias[n] ) + residual
- * A, B are bf16, K-major (row stride lda/ldb elements, multiples of 8); fp32 accumulation in TMEM.
+ * A, B are bf16, K-major (row stride lda/ldb elements, multiples of 8) unless a_mn / b_mn say otherwise;
+ * fp32 accumulation in TMEM. residual == C (same ld) accumulates into a bf16 C (gradient accumulation).
  * Batch offsets (elements): A: zi*a_stride_zi + zo*a_stride_zo; B: (zi / b_zi_div)*b_stride_zi +
  * zo*b_stride_zo (b_zi_div > 1 shares one B among consecutive inner batches: GQA);
  * C: zi*c_stride_zi + zo*c_stride_zo.
@@ -76,6 +77,10 @@ typedef struct u2_gemm_desc {
   int32_t res_row_mod;
   int32_t row_div, row_stride, row_off;
   int32_t block_n;    /* 0 = auto, else 64/128/256 */
+  /* transposed operands (training: dgrad = dY * W, wgrad = dY^T * X, P^T dO ...): a_mn != 0 -> A is stored
+   * [K][M] (element (m, k) at A[k * lda + m]); b_mn != 0 -> B is stored [K][N]. lda / ldb are then the strides
+   * between consecutive contraction indices. No transposed copy is made: the tile is loaded MN-major. */
+  int32_t a_mn, b_mn;
 } u2_gemm_desc;
 
 U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const u2_gemm_desc* desc, void* stream);

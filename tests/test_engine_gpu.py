@@ -81,7 +81,7 @@ def test_forward_logits_and_generate(family):
         g = tiny_geometry(qk_norm=False, rope_theta=500000.0, rope_scaling=rs, tie_word_embeddings=True, head_dim=32)
     # untied head (qwen3 variant): bigram-structured weights give decisive top-1 / top-2 margins, so (nearly) every
     # greedy token is actually compared; the tied Llama variant can only use the log-normal row-norm profile
-    eng, sd = build(g, 3, **(dict(bigram=1.0) if family == "qwen3" else dict(head_tail=1.5)))
+    eng, sd = build(g, 3, **(dict(bigram=1.0) if family == "qwen3" else dict(head_tail=1.0)))
     images, ids, qids = synthetic_inputs(g, batch=2, frames=2, n_question=6, lt=12)
     n_new = 24
     with torch.no_grad():

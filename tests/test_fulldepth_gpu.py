@@ -144,10 +144,13 @@ def test_cfg2_full_depth_forward_and_greedy():
     """BASELINE cfg 2: mu2-Qwen3-1.7B (tied head), ONE 256 x 256 x 128 volume (4 frames), prompt 288, Lt 512; plus 64
     greedy steps. The head is tied, so only the log-normal row-norm profile is available to sharpen the margins
     (compared / total is reported, not bounded)."""
-    _run("cfg2", batch=1, frames=4, n_new=64, lt=512, head_kw=dict(head_tail=1.5), min_compared=0.0)
+    _run("cfg2", batch=1, frames=4, n_new=64, lt=512, head_kw=dict(head_tail=1.0), min_compared=0.0)
 
 
 def test_cfg3_full_depth_generate():
     """BASELINE cfg 3: mu2-Qwen3-8B, batch 4, 256^3 volumes (8 frames), 256 greedy tokens, bigram-structured head:
-    >= 95 % of the 4 x 256 tokens must have a decisive margin and every one of them must be identical."""
-    _run("cfg3", batch=4, frames=8, n_new=256, lt=512, head_kw=dict(bigram=1.0), min_compared=0.95)
+    >= 95 % of the 4 x 256 tokens must have a decisive margin and every one of them must be identical.
+    bigram = 0.35: the token's own embedding is ~1/3 of the random-walk norm of the 72 residual-branch outputs, so the
+    layers' contribution is the larger part of the final hidden state (with bigram = 1.0 the first run of this test
+    compared 1024/1024 tokens, but with a median margin of 94 % of the top logit: too easy)."""
+    _run("cfg3", batch=4, frames=8, n_new=256, lt=512, head_kw=dict(bigram=0.35), min_compared=0.95)

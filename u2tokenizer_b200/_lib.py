@@ -28,6 +28,7 @@ class GemmDesc(C.Structure):
         ("res_row_mod", C.c_int32),
         ("row_div", C.c_int32), ("row_stride", C.c_int32), ("row_off", C.c_int32),
         ("block_n", C.c_int32),
+        ("a_mn", C.c_int32), ("b_mn", C.c_int32),
     ]
 
 

@@ -86,7 +86,12 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int kBlockN, int kMode = 0>
+// kMajor bit 0: A is MN-major (stored [K][M], the contraction index is the slow one), bit 1: same for B. An MN-major
+// operand tile is loaded as 64-wide MN chunks x 64 k-rows (one TMA box each, 8 KB, 128-byte swizzle): exactly the
+// canonical UMMA "MN-major, SWIZZLE_128B" layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = 8192 B
+// between chunks and SBO = 1024 B between groups of 8 k-rows. dgrad (dY * W) and wgrad (dY^T * X) of every Linear,
+// P^T dO / dS^T Q of the attention backward and the DiffTS products run through this without transposed copies.
+template <int kBlockN, int kMode = 0, int kMajor = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
@@ -154,10 +159,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBlockK,
-                      m_blk * kBlockM, zi_i, zo_i);
-          tma_load_4d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK,
-                      n_blk * kBlockN, zi_b, zo_i);
+          if constexpr (kMajor & 1) {
+#pragma unroll
+            for (int c = 0; c < kBlockM / 64; ++c)
+              tma_load_4d(smem_a + stage * Cfg::kABytes + c * (64 * kBlockK * 2), &tmap_a, &full_bar[stage],
+                          m_blk * kBlockM + c * 64, kb * kBlockK, zi_i, zo_i);
+          } else {
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBlockK,
+                        m_blk * kBlockM, zi_i, zo_i);
+          }
+          if constexpr (kMajor & 2) {
+#pragma unroll
+            for (int c = 0; c < kBlockN / 64; ++c)
+              tma_load_4d(smem_b + stage * Cfg::kBBytes + c * (64 * kBlockK * 2), &tmap_b, &full_bar[stage],
+                          n_blk * kBlockN + c * 64, kb * kBlockK, zi_b, zo_i);
+          } else {
+            tma_load_4d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBlockK,
+                        n_blk * kBlockN, zi_b, zo_i);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -168,7 +187,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN) | ((kMajor & 1) ? (1u << 15) : 0u) |
+                                 ((kMajor & 2) ? (1u << 16) : 0u);
+      // descriptor start-address step (16-byte units) per UMMA_K = 16 contraction indices: 32 B inside the swizzle
+      // row for a K-major tile, two 1024-byte groups of 8 k-rows for an MN-major one
+      constexpr uint32_t a_kstep = (kMajor & 1) ? 128 : 2, b_kstep = (kMajor & 2) ? 128 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -180,12 +203,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes), b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t a_desc = (kMajor & 1) ? umma_desc_mnmajor_sw128(a_addr, 64 * kBlockK * 2) : umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = (kMajor & 2) ? umma_desc_mnmajor_sw128(b_addr, 64 * kBlockK * 2) : umma_desc_kmajor_sw128(b_addr);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance the start address by k * 16 elements * 2 B = 32 B (>>4 -> +2) inside the swizzle row
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a_desc + a_kstep * k, b_desc + b_kstep * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem slot when the MMAs have read it
           if (++stage == kStages) {
@@ -361,13 +384,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kBlockN, int kMode = 0>
+template <int kBlockN, int kMode = 0, int kMajor = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int num_sms,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kBlockN, kMode>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kBlockN, kMode, kMajor>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
@@ -376,7 +399,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   const int num_n = (p.N + kBlockN - 1) / kBlockN;
   const long long tiles = (long long)num_m * num_n * p.zi * p.zo;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<kBlockN, kMode><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<kBlockN, kMode, kMajor><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return U2_OK;
@@ -503,9 +526,17 @@ extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const 
 
   CUtensorMap ta, tb;
   const int zi_b = (zi + bdiv - 1) / bdiv;
-  int rc = make_tmap_bf16_4d(&ta, A, d->K, d->M, zi, zo, d->lda, zi > 1 ? d->a_stride_zi : 0, zo > 1 ? d->a_stride_zo : 0, kBlockK, kBlockM);
+  const int major = (d->a_mn ? 1 : 0) | (d->b_mn ? 2 : 0);
+  int rc;
+  if (d->a_mn)  // stored [K][M]: inner dim = M, rows = K, boxes of 64 (M) x 64 (K)
+    rc = make_tmap_bf16_4d(&ta, A, d->M, d->K, zi, zo, d->lda, zi > 1 ? d->a_stride_zi : 0, zo > 1 ? d->a_stride_zo : 0, 64, kBlockK);
+  else
+    rc = make_tmap_bf16_4d(&ta, A, d->K, d->M, zi, zo, d->lda, zi > 1 ? d->a_stride_zi : 0, zo > 1 ? d->a_stride_zo : 0, kBlockK, kBlockM);
   if (rc) return rc;
-  rc = make_tmap_bf16_4d(&tb, B, d->K, d->N, zi_b, zo, d->ldb, zi_b > 1 ? d->b_stride_zi : 0, zo > 1 ? d->b_stride_zo : 0, kBlockK, block_n);
+  if (d->b_mn)
+    rc = make_tmap_bf16_4d(&tb, B, d->N, d->K, zi_b, zo, d->ldb, zi_b > 1 ? d->b_stride_zi : 0, zo > 1 ? d->b_stride_zo : 0, 64, kBlockK);
+  else
+    rc = make_tmap_bf16_4d(&tb, B, d->K, d->N, zi_b, zo, d->ldb, zi_b > 1 ? d->b_stride_zi : 0, zo > 1 ? d->b_stride_zo : 0, kBlockK, block_n);
   if (rc) return rc;
 
   GemmDev p = {};
@@ -522,9 +553,17 @@ extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const 
   p.row_div = d->row_div; p.row_stride = d->row_stride; p.row_off = d->row_off;
   p.C = C;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (block_n) {
-    case 64: return launch_gemm<64>(ta, tb, p, num_sms(), s);
-    case 128: return launch_gemm<128>(ta, tb, p, num_sms(), s);
-    default: return launch_gemm<256>(ta, tb, p, num_sms(), s);
+#define U2_GEMM_BN(MAJ)                                                    \
+  switch (block_n) {                                                      \
+    case 64: return launch_gemm<64, 0, MAJ>(ta, tb, p, num_sms(), s);     \
+    case 128: return launch_gemm<128, 0, MAJ>(ta, tb, p, num_sms(), s);   \
+    default: return launch_gemm<256, 0, MAJ>(ta, tb, p, num_sms(), s);    \
   }
+  switch (major) {
+    case 0: U2_GEMM_BN(0)
+    case 1: U2_GEMM_BN(1)
+    case 2: U2_GEMM_BN(2)
+    default: U2_GEMM_BN(3)
+  }
+#undef U2_GEMM_BN
 }

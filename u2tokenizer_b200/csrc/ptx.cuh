@@ -184,6 +184,19 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the contraction index is the slow, row index of the stored matrix): 64-element (128-byte)
+// MN chunks of 8-row (k) groups, 128-byte swizzle. LBO = byte distance between consecutive 64-wide MN chunks,
+// SBO = 1024 B between consecutive groups of 8 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;         // leading byte offset, bits [16,30)
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                      // layout type: SWIZZLE_128B
+  return d;
+}
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4)           // accumulator format: F32

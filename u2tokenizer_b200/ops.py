@@ -40,8 +40,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K
          a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0),
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, ldr: int = 0, res_row_mod: int = 0,
-         row_remap=(0, 0, 0), block_n: int = 0) -> torch.Tensor:
-    """Raw (batched, strided) GEMM: C[z] = act(alpha * A[z] @ B[z']^T + bias) + residual."""
+         row_remap=(0, 0, 0), block_n: int = 0, a_mn: bool = False, b_mn: bool = False) -> torch.Tensor:
+    """Raw (batched, strided) GEMM: C[z] = act(alpha * A[z] @ B[z']^T + bias) + residual.
+    a_mn / b_mn: the operand is stored transposed ([K][M] / [K][N], lda / ldb = stride between contraction indices)."""
     _need_cuda(a, b, c, bias, residual)
     if a.dtype != BF16 or b.dtype != BF16:
         raise TypeError("gemm operands must be bf16")
@@ -66,6 +67,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K
     d.res_row_mod = res_row_mod
     d.row_div, d.row_stride, d.row_off = row_remap
     d.block_n = block_n
+    d.a_mn, d.b_mn = int(a_mn), int(b_mn)
     lib = _lib.load()
     _lib.check(lib.u2_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), C.byref(d), _stream()),
                "u2_gemm_bf16")
