@@ -102,22 +102,22 @@ U2_API int u2_multiscale_pool_bwd_bf16(const void* x, const void* dy, void* dx, 
  * (reference u2_arch.py:114,118-121 backward). ids int64 [B, L]. */
 U2_API int u2_embed_scatter_add_bf16(const int64_t* ids, const void* drows, void* dtable, void* dvis, int32_t B,
                                      int32_t L, int32_t E, int32_t n_vis, int64_t vocab, void* stream);
-/* out[r, :] (+)= sum_{g < G} in[(r / inner) * G * inner + g * inner + r % inner, :]: sum of the G query-head
- * gradients that share one KV head (GQA dK / dV). rows = number of OUTPUT rows, E % 8 == 0. */
-U2_API int u2_group_sum_bf16(const void* in, void* out, int64_t rows, int32_t G, int64_t inner, int32_t E,
-                             void* stream);
+/* out[r * ld_out + h * dh + e] = sum_{g < G} in[r * ld_in + (h * G + g) * dh + e]: sum of the G query-head
+ * gradients that share one KV head (GQA dK / dV written per query head by the batched GEMMs). dh % 8 == 0. */
+U2_API int u2_group_sum_bf16(const void* in, void* out, int64_t rows, int32_t heads, int32_t G, int32_t dh,
+                             int64_t ld_in, int64_t ld_out, void* stream);
 
-/* Cross-entropy / log-probability head backward, in place on bf16 logits [R, V] (row stride ld):
- *   logits[r, v] <- coef[r] * (exp(logits[r, v] - lse[r]) - [v == labels[r]])
+/* Cross-entropy / log-probability head backward: fp32 logits [R, V] (row stride ld_in) -> bf16 dlogits (ld_out):
+ *   dlogits[r, v] = coef[r] * (exp(logits[r, v] - lse[r]) - [v == labels[r]])
  * coef fp32 [R] (0 for rows without a label): 1 / #labelled rows for the mean-NLL loss of forward(labels=...)
- * (u2llama.py:76-87), -dLoss/dlogp[r] for the DPO loss (dpo_u2trainer.py:296 and trl's sigmoid loss). */
-U2_API int u2_ce_bwd_bf16(void* logits, const float* lse, const int64_t* labels, const float* coef, int64_t R,
-                          int32_t V, int64_t ld, void* stream);
+ * (u2llama.py:76-87), -dLoss/dlogp[r] for the DPO loss (dpo_u2trainer.py:296 and trl's sigmoid loss). V % 8 == 0. */
+U2_API int u2_ce_bwd_f32_bf16(const float* logits, void* dlogits, const float* lse, const int64_t* labels,
+                              const float* coef, int64_t R, int32_t V, int64_t ld_in, int64_t ld_out, void* stream);
 /* Sigmoid DPO loss head (trl DPOTrainer.dpo_loss, loss_type "sigmoid", reference_free False; beta from
  * train_stage2.py:83): per_tok fp32 [2P, L] policy log-probs (chosen rows first, then rejected), ref_sum fp32 [2P]
  * summed reference log-probs, mask [2P, L] (uint8).  loss = mean_p -logsigmoid(beta * ((pc - pr) - (rc - rr)));
  * out[0] = loss, out[1] = mean reward accuracy, out[2] = mean reward margin;
- * coef[r, l] = -dloss/dlogp[r, l] (feeds u2_ce_bwd_bf16). One block, P <= 1024. */
+ * coef[r, l] = -dloss/dlogp[r, l] (feeds u2_ce_bwd_f32_bf16). One block, P <= 1024. */
 U2_API int u2_dpo_loss_f32(const float* per_tok, const float* ref_sum, const uint8_t* mask, float* out, float* coef,
                            int32_t P, int32_t L, float beta, void* stream);
 
@@ -137,6 +137,9 @@ U2_API int u2_adamw_f32grad(float* master, float* m, float* v, const float* grad
                             float* param_out_f32, int64_t n, const u2_adamw_desc* desc, void* stream);
 U2_API int u2_sumsq_bf16(const void* x, float* out, int64_t n, void* stream);
 U2_API int u2_sumsq_f32(const float* x, float* out, int64_t n, void* stream);
+/* dst += src (bf16, n % 8 == 0): gradient accumulation where two branches meet (residual connections, the visual /
+ * text tokens that feed every TTA layer). */
+U2_API int u2_add_bf16(void* dst, const void* src, int64_t n, void* stream);
 /* dtype plumbing between the flat buffers: fp32 -> bf16 and bf16 -> fp32 (n elements). */
 U2_API int u2_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 U2_API int u2_cast_bf16_f32(const void* in, float* out, int64_t n, void* stream);

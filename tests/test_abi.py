@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_symbols():
-    src = open(os.path.join(ROOT, "include", "u2b200.h")).read()
+    src = open(os.path.join(ROOT, "include", "u2b200.h")).read() + open(os.path.join(ROOT, "include", "u2b200_train.h")).read()
     return sorted(set(re.findall(r"U2_API\s+[\w\s\*]+?\b(u2_\w+)\s*\(", src)))
 
 

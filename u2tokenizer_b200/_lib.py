@@ -163,7 +163,27 @@ class PreprocessDesc(C.Structure):
     ]
 
 
-# name -> (restype, argtypes); every symbol include/u2b200.h declares must be listed here
+class SoftmaxBwdDesc(C.Structure):
+    """Mirror of ``u2_softmax_bwd_desc`` (include/u2b200_train.h)."""
+    _fields_ = [
+        ("p_s0", C.c_int64), ("p_s1", C.c_int64), ("p_s2", C.c_int64),
+        ("dp_s0", C.c_int64), ("dp_s1", C.c_int64), ("dp_s2", C.c_int64),
+        ("ds_s0", C.c_int64), ("ds_s1", C.c_int64), ("ds_s2", C.c_int64),
+        ("n0", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("n", C.c_int32),
+        ("zero_pad_to", C.c_int32),
+    ]
+
+
+class AdamWDesc(C.Structure):
+    """Mirror of ``u2_adamw_desc``."""
+    _fields_ = [
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("step", C.c_int32),
+        ("grad_scale", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/u2b200.h / u2b200_train.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -198,6 +218,31 @@ SIGNATURES = {
     "u2_preprocess_volume_f32": (C.c_int, [_P, _P, _P, C.POINTER(PreprocessDesc), _P]),
     "u2_logprob_ws_bytes": (C.c_int64, [_I, _I]),
     "u2_lmhead_logprob_bf16": (C.c_int, [_P, _P, _P, C.POINTER(LogprobDesc), _P]),
+    # ---- training side (include/u2b200_train.h)
+    "u2_transpose_bf16": (C.c_int, [_P, _P, _I, _I, _L, _L, _I, _L, _L, _P]),
+    "u2_colsum_bf16": (C.c_int, [_P, _P, _L, _L, _L, _P]),
+    "u2_gelu_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "u2_gelu_bwd_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
+    "u2_silu_mul_bwd_bf16": (C.c_int, [_P, _P, _P, _L, _I, _L, _L, _P]),
+    "u2_layernorm_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _L, _F, _P]),
+    "u2_rmsnorm_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _L, _F, _P]),
+    "u2_softmax_bwd_bf16": (C.c_int, [_P, _P, _P, C.POINTER(SoftmaxBwdDesc), _P]),
+    "u2_relbias_grad_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _P]),
+    "u2_temporal_attention_bwd_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _F, _P, _P, _I, _P]),
+    "u2_rope_bwd_bf16": (C.c_int, [_P, _P, C.POINTER(RopeDesc), _P, _P, _P]),
+    "u2_spp_pool_bwd_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),
+    "u2_multiscale_pool_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "u2_embed_scatter_add_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _L, _P]),
+    "u2_group_sum_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _L, _L, _P]),
+    "u2_ce_bwd_f32_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _L, _L, _P]),
+    "u2_dpo_loss_f32": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "u2_adamw_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(AdamWDesc), _P]),
+    "u2_adamw_f32grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(AdamWDesc), _P]),
+    "u2_sumsq_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "u2_sumsq_f32": (C.c_int, [_P, _P, _L, _P]),
+    "u2_add_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "u2_cast_f32_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "u2_cast_bf16_f32": (C.c_int, [_P, _P, _L, _P]),
 }
 
 
@@ -225,7 +270,7 @@ def load():
 
 # kernels launched per entry point (u2_multiscale_pool_bf16: gate + write, counted at its maximum)
 KERNELS_PER_CALL = {"u2_multiscale_pool_bf16": 2, "u2_argmax_f32": 2, "u2_lmhead_logprob_bf16": 2,
-                    "u2_preprocess_volume_f32": 14}
+                    "u2_preprocess_volume_f32": 14, "u2_multiscale_pool_bwd_bf16": 2}
 _launches = 0
 
 

@@ -210,6 +210,32 @@ class U2MetaForCausalLM(ABC):
         self.__dict__.pop("_u2_engine", None)
         self.__dict__.pop("_u2_engine_stamp", None)
 
+    # ---- training ---------------------------------------------------------------------------------
+    def train_engine(self, **kw):
+        """Build (once) the training engine: the parameters move into its flat training-layout buffer and this module's
+        nn.Parameters are re-pointed at slices of it (no second copy; the optimizer's in-place updates ARE the engine's
+        weights). Group-level requires_grad flags are read from the parameters (freeze_vision_tower / freeze_backbone /
+        tune_mm_mlp_adapter of the reference, train_stage1.py:313-332, u2_arch.py:58)."""
+        te = self.__dict__.get("_u2_train_engine")
+        if te is None:
+            from .train import TrainEngine
+            p = next(self.parameters())
+            if not p.is_cuda:
+                raise RuntimeError("the training path runs on CUDA only (model.cuda()); there is no CPU fallback")
+
+            def any_rg(prefix):
+                ps = [q for n, q in self.named_parameters() if n.startswith(prefix)]
+                return any(q.requires_grad for q in ps) if ps else False
+            flags = dict(vit=any_rg("model.vision_tower."), proj=any_rg("model.mm_projector."), u2t=any_rg("model.u2tokenizer."),
+                         dec=any_rg("model.layers.") or any_rg("model.norm."), embed=any_rg("model.embed_tokens."),
+                         head=any_rg("lm_head."))
+            kw.setdefault("trainable", flags)
+            te = TrainEngine(Geometry.from_hf(self.config), self.state_dict(), device=p.device, **kw)
+            te.bind_module(self)
+            self.__dict__["_u2_train_engine"] = te
+            self.invalidate_engine()
+        return te
+
     def load_state_dict(self, *a, **k):
         self.invalidate_engine()
         return super().load_state_dict(*a, **k)
@@ -278,6 +304,17 @@ class U2MetaForCausalLM(ABC):
             raise NotImplementedError("HF-driven cached decoding is not supported; call generate() "
                                       "(greedy decode runs inside the engine with its own static KV cache)")
         self._check_right_padded(attention_mask)
+        if (labels is not None and torch.is_grad_enabled() and inputs_embeds is None and input_ids is not None
+                and any(p.requires_grad for p in self.parameters())):
+            # training step (reference train_stage1.py:244-250: batch -> model(**batch) -> loss.backward()): forward with
+            # saved activations on the training engine, backward through ONE autograd node that hands every parameter its
+            # gradient (computed by the hand-written backward pass, not by torch autograd)
+            te = self.train_engine()
+            names, params = zip(*[(n, p) for n, p in self.named_parameters() if p.requires_grad])
+            loss = _U2TrainLoss.apply(te, (images, input_ids, question_ids, labels), names, *params)
+            if return_dict is False:
+                return (loss, None)
+            return CausalLMOutputWithPast(loss=loss, logits=None, past_key_values=None)
         eng = self.engine()
         if (inputs_embeds is None and labels is None and images is not None and self.get_vision_tower() is not None
                 and input_ids is not None and input_ids.shape[1] != 1):
@@ -415,6 +452,39 @@ class U2MetaForCausalLM(ABC):
             keep = int((~after).any(dim=0).sum())
             ids = ids[:, :max(keep, 1)]
         return ids  # new tokens only, like HF generate() on inputs_embeds (reference u2llama.py:123-127)
+
+
+class _U2TrainLoss(torch.autograd.Function):
+    """loss = TrainEngine.forward_loss(batch); backward() = TrainEngine.backward(): the bridge that lets
+    `model(**batch).loss.backward()` (HF Trainer / accelerate) drive the hand-written backward pass."""
+
+    @staticmethod
+    def forward(ctx, te, batch, names, *params):
+        images, input_ids, question_ids, labels = batch
+        ctx.te, ctx.names = te, names
+        with torch.no_grad():
+            return te.forward_loss(images, input_ids, question_ids, labels)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        te = ctx.te
+        te.zero_grad()
+        te.backward(grad_out.to(torch.float32))
+        L = te.lay
+        gvb = torch.empty(L.vec_total, device=te.dev, dtype=torch.bfloat16)
+        from . import train_ops as T
+        T.cast(te.Gv, gvb)
+        grads = []
+        for n in ctx.names:
+            if n == "lm_head.weight" and te.tied:
+                grads.append(None)   # the tied head's gradient is delivered through embed_tokens
+            elif n in L.mat_off:
+                grads.append(te.Gm[L.mat_off[n]:L.mat_off[n] + L._numel(n)].view(L.shapes[n]))
+            elif n in L.vec_off:
+                grads.append(gvb[L.vec_off[n]:L.vec_off[n] + L._numel(n)].view(L.shapes[n]))
+            else:
+                grads.append(None)
+        return (None, None, None, *grads)
 
 
 # ------------------------------------------------------------------------------------------------
