@@ -133,6 +133,10 @@ typedef struct u2_adamw_desc {
 } u2_adamw_desc;
 U2_API int u2_adamw_bf16(float* master, float* m, float* v, const void* grad, void* param_out, int64_t n,
                          const u2_adamw_desc* desc, void* stream);
+/* same update with bf16 first / second moments (8 instead of 12 bytes of state per parameter: the mode a single GPU
+ * needs to hold the whole optimizer state of the 8B model; the sharded multi-GPU step keeps fp32 moments) */
+U2_API int u2_adamw_bf16_mom16(float* master, void* m, void* v, const void* grad, void* param_out, int64_t n,
+                               const u2_adamw_desc* desc, void* stream);
 U2_API int u2_adamw_f32grad(float* master, float* m, float* v, const float* grad, void* param_out_bf16,
                             float* param_out_f32, int64_t n, const u2_adamw_desc* desc, void* stream);
 U2_API int u2_sumsq_bf16(const void* x, float* out, int64_t n, void* stream);

@@ -389,7 +389,9 @@ def test_forward_backward_matches_oracle_autograd(case):
     from u2tokenizer_b200.train import TrainEngine
     g = tiny_geometry(**CASES[case])
     sd16 = synthetic_state_dict(g, seed=21, device="cpu", dtype=BF)
-    # non-trivial relative-bias tables / gate so that their gradients are exercised
+    # N(0, 0.02) query tokens make every TTA attention uniform (scores ~ 0) and its gradients pure cancellation noise:
+    # give them O(1) entries so that the TTA / linear-aggregation backward is actually exercised
+    sd16["model.u2tokenizer.query_tokens"] = (sd16["model.u2tokenizer.query_tokens"].float() * 50).to(BF)
     images, ids, qids = synthetic_inputs(g, batch=2, frames=3, n_question=7, lt=12)
     labels = _labels(ids, g.num_3d_query_token)
     ref_loss, ref_g = _oracle_loss_and_grads(sd16, g, images, ids, qids, labels)
@@ -400,7 +402,11 @@ def test_forward_backward_matches_oracle_autograd(case):
     assert abs(float(loss) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
     L = te.lay
     bad, worst = [], (0.0, "")
-    skip_zero = 0
+    skip_zero = n_noise = 0
+    # gradients that are mathematically (near) zero - k-projection biases under the softmax shift invariance, gates that
+    # see identical inputs, score nets behind a nearly uniform softmax - are cancellation noise in ANY bf16 pipeline: a
+    # tensor also passes when its absolute error is below 2e-3 of the largest gradient entry of the whole model
+    gmax = max(v.abs().max().item() for v in ref_g.values())
     for n in L.mat_names + L.vec_names:
         if n in L.mat_off:
             got = te.Gm[L.mat_off[n]:L.mat_off[n] + L._numel(n)].view(L.shapes[n]).float().cpu()
@@ -417,13 +423,20 @@ def test_forward_backward_matches_oracle_autograd(case):
             assert got.abs().max().item() < 1e-4, f"{n}: oracle gradient is zero, got {got.abs().max().item()}"
             continue
         e, c = rel_err(got, want), cosine(got, want)
-        if e > worst[0]:
-            worst = (e, n)
-        if not (e < 4e-2 and c > 0.995):
-            bad.append((n, round(e, 4), round(c, 5)))
-    print(f"[{case}] loss {float(loss):.5f} (oracle {ref_loss:.5f}); worst gradient rel_err {worst[0]:.4g} at {worst[1]}; "
-          f"{len(L.mat_names + L.vec_names)} parameters, {skip_zero} with an identically zero gradient")
-    assert not bad, bad
+        if e < 4e-2 and c > 0.995:
+            if e > worst[0]:
+                worst = (e, n)
+            continue
+        if (got - want).abs().max().item() < 2e-3 * gmax:
+            n_noise += 1
+            continue
+        bad.append((n, round(e, 4), round(c, 5), got.abs().max().item(), scale))
+    print(f"[{case}] loss {float(loss):.5f} (oracle {ref_loss:.5f}); {len(L.mat_names + L.vec_names)} parameters: worst rel_err "
+          f"among the directly compared {worst[0]:.4g} at {worst[1]}; {n_noise} below the noise floor (|err| < 2e-3 * {gmax:.3g}), "
+          f"{skip_zero} identically zero")
+    for b_ in bad:
+        print("   BAD", b_)
+    assert not bad, bad[:6]
 
 
 def test_frozen_vision_tower_and_module_backward():
@@ -438,6 +451,7 @@ def test_frozen_vision_tower_and_module_backward():
                         tie_word_embeddings=False, rope_theta=1e6)
     g = Geometry.from_hf(cfg)
     sd16 = synthetic_state_dict(g, seed=5, device="cpu", dtype=BF)
+    sd16["model.u2tokenizer.query_tokens"] = (sd16["model.u2tokenizer.query_tokens"].float() * 50).to(BF)
     prev = torch.get_default_dtype()
     torch.set_default_dtype(BF)
     try:
@@ -456,6 +470,7 @@ def test_frozen_vision_tower_and_module_backward():
     out.loss.backward()
     assert abs(float(out.loss) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
     bad = []
+    gmax = max(v.abs().max().item() for v in ref_g.values())
     for n, p in model.named_parameters():
         if n.startswith("model.vision_tower."):
             assert p.grad is None
@@ -464,10 +479,13 @@ def test_frozen_vision_tower_and_module_backward():
         if want.abs().max().item() < 1e-9:
             continue
         assert p.grad is not None, n
-        e, c = rel_err(p.grad.float().cpu(), want), cosine(p.grad.float().cpu(), want)
-        if not (e < 5e-2 and c > 0.99):
+        got = p.grad.float().cpu()
+        e, c = rel_err(got, want), cosine(got, want)
+        if not (e < 5e-2 and c > 0.99) and (got - want).abs().max().item() >= 2e-3 * gmax:
             bad.append((n, round(e, 4), round(c, 5)))
-    assert not bad, bad
+    for b_ in bad:
+        print("   BAD", b_)
+    assert not bad, bad[:6]
     # an optimizer step through torch (in place on the flat buffer) is seen by the next forward
     before = float(out.loss)
     torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.05).step()

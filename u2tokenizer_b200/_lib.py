@@ -237,6 +237,7 @@ SIGNATURES = {
     "u2_ce_bwd_f32_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _L, _L, _P]),
     "u2_dpo_loss_f32": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "u2_adamw_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(AdamWDesc), _P]),
+    "u2_adamw_bf16_mom16": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(AdamWDesc), _P]),
     "u2_adamw_f32grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, C.POINTER(AdamWDesc), _P]),
     "u2_sumsq_bf16": (C.c_int, [_P, _P, _L, _P]),
     "u2_sumsq_f32": (C.c_int, [_P, _P, _L, _P]),

@@ -864,6 +864,48 @@ struct AdamArgs {
   const float* grad_scale;
 };
 
+__device__ __forceinline__ void ld4(const float* p, long long i, float (&o)[4]) {
+  const float4 t = reinterpret_cast<const float4*>(p)[i];
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, long long i, float (&o)[4]) {
+  const uint2 t = reinterpret_cast<const uint2*>(p)[i];
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
+}
+__device__ __forceinline__ void st4(float* p, long long i, const float (&o)[4]) {
+  reinterpret_cast<float4*>(p)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, long long i, const float (&o)[4]) {
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(o[0], o[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(o[2], o[3]);
+  reinterpret_cast<uint2*>(p)[i] = t;
+}
+
+// fp32 master + bf16 moments (the single-GPU memory mode: 8 instead of 12 bytes of optimizer state per parameter)
+__global__ void __launch_bounds__(256)
+adamw_mom16_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
+                   const __nv_bfloat16* __restrict__ grad, __nv_bfloat16* __restrict__ p_bf16, long long n, const AdamArgs a) {
+  const float gs = a.grad_scale ? *a.grad_scale : 1.f;
+  const long long nvec = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float g[4], w[4], mm[4], vv[4];
+    ld4(grad, i, g); ld4(master, i, w); ld4(m, i, mm); ld4(v, i, vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = g[j] * gs;
+      mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gj;
+      vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * gj * gj;
+      const float denom = sqrtf(vv[j]) * a.bc2_rsqrt + a.eps;
+      w[j] = w[j] * (1.f - a.lr * a.wd) - (a.lr / a.bc1) * (mm[j] / denom);
+    }
+    st4(master, i, w); st4(m, i, mm); st4(v, i, vv);
+    if (p_bf16) st4(p_bf16, i, w);
+  }
+}
+
 template <bool kGradF32>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v, const void* __restrict__ grad,
@@ -1216,6 +1258,19 @@ extern "C" U2_API int u2_adamw_bf16(float* master, float* m, float* v, const voi
   if (rc) return rc;
   if (n <= 0) return U2_OK;
   adamw_kernel<false><<<t_grid(n / 4, 256, 148LL * 16), 256, 0, ST(stream)>>>(master, m, v, grad, BF(param_out), nullptr, n, a);
+  U2_CHECK_LAUNCH("adamw");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_adamw_bf16_mom16(float* master, void* m, void* v, const void* grad, void* param_out, int64_t n,
+                                          const u2_adamw_desc* desc, void* stream) {
+  if (!master || !m || !v || !grad) return set_error(U2_ERR_ARG, "adamw: null pointer");
+  if (n & 3) return set_error(U2_ERR_ARG, "adamw: n must be a multiple of 4");
+  AdamArgs a;
+  int rc = adam_args(desc, &a);
+  if (rc) return rc;
+  if (n <= 0) return U2_OK;
+  adamw_mom16_kernel<<<t_grid(n / 4, 256, 148LL * 16), 256, 0, ST(stream)>>>(master, BF(m), BF(v), CBF(grad), BF(param_out), n, a);
   U2_CHECK_LAUNCH("adamw");
   return U2_OK;
 }

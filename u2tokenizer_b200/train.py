@@ -432,19 +432,20 @@ class TrainEngine:
         ops.gemm(rows, pe_w, x0, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd, bias=pe_b,
                  residual=pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
         ops.set_rows(x0, self.w(v + "cls_token").view(Hd), Fr, Sp, 0)
-        x = Var(x0.view(Fr * Sp, Hd), trv)
+        x_emb = Var(x0.view(Fr * Sp, Hd), trv)   # NOT `x`: that name is rebound by the layer loop below
 
         def bwd_embed():
-            if x.g is None or not trv:
+            if x_emb.g is None or not trv:
                 return
-            dx = x.g.view(Fr, Sp, Hd)
+            dx = x_emb.g.view(Fr, Sp, Hd)
             dy = dx[:, 1:1 + P].contiguous().view(Fr * P, Hd)
             T.linear_wgrad(dy, rows, self.gm(v + "patch_embedding.patch_embeddings.1.weight"), accumulate=True)
             T.colsum(dy, self.gv(v + "patch_embedding.patch_embeddings.1.bias"))
             T.colsum(dy, self.gv(v + "patch_embedding.position_embeddings"), rows=Fr, cols=P * Hd, ld=P * Hd)
             T.colsum(dx, self.gv(v + "cls_token"), rows=Fr, cols=Hd, ld=Sp * Hd)
-            x.g = None
+            x_emb.g = None
         self.tape.append(bwd_embed)
+        x = x_emb
 
         nh = g.vit_heads
         dh = Hd // nh
@@ -477,17 +478,19 @@ class TrainEngine:
         seq = g.proj_pooling_type == "sequence"
         ops.spp_pool(y.v, pooled, frames=Fr, grid=g.grid, ps=g.proj_pooling_size, E=Hd, in_frame_stride=Sp, in_off=1, ldx=Hd,
                      sequence=seq)
-        z = Var(pooled.view(Fr * npf, Hd), y.ng)
+        z_pool = Var(pooled.view(Fr * npf, Hd), y.ng)   # `z` is rebound by the projector loop
+        y_ln = y
 
         def bwd_pool():
-            if z.g is None or not y.ng:
+            if z_pool.g is None or not y_ln.ng:
                 return
             dy = torch.empty(Fr * Sp, Hd, device=self.dev, dtype=BF16)
-            T.spp_pool_bwd(z.g, dy, frames=Fr, grid=g.grid, ps=g.proj_pooling_size, E=Hd, in_frame_stride=Sp, in_off=1, ldx=Hd,
+            T.spp_pool_bwd(z_pool.g, dy, frames=Fr, grid=g.grid, ps=g.proj_pooling_size, E=Hd, in_frame_stride=Sp, in_off=1, ldx=Hd,
                            rows_per_frame=Sp, sequence=seq)
-            self._acc(y, dy, owned=True)
-            z.g = None
+            self._acc(y_ln, dy, owned=True)
+            z_pool.g = None
         self.tape.append(bwd_pool)
+        z = z_pool
         # projector MLP
         trp = self._tr("proj")
         p = "model.mm_projector.projector."
@@ -711,13 +714,14 @@ class TrainEngine:
         self._alias(vis, vis3)
         tr = self._tr("u2t")
         qtok = self.w(u + "query_tokens").view(Q, E)
-        q = Var(qtok.unsqueeze(0).expand(B, Q, E).contiguous().view(B * Q, E), tr)
+        q_tok = Var(qtok.unsqueeze(0).expand(B, Q, E).contiguous().view(B * Q, E), tr)   # `q` is rebound per TTA layer
 
         def bwd_q():
-            if q.g is not None and tr:
-                T.colsum(q.g, self.gv(u + "query_tokens"), rows=B, cols=Q * E, ld=Q * E)
-            q.g = None
+            if q_tok.g is not None and tr:
+                T.colsum(q_tok.g, self.gv(u + "query_tokens"), rows=B, cols=Q * E, ld=Q * E)
+            q_tok.g = None
         self.tape.append(bwd_q)
+        q = q_tok
         for i in range(g.u2t_num_layers):
             l = f"{u}tta_module.layers_vt.{i}."
             s = self._self_attention(q, B, Q, l + "self_attention.")
@@ -952,10 +956,13 @@ class TrainEngine:
     # =========================================================================================
     # optimizer: ZeRO-1 over the data-parallel group
     # =========================================================================================
-    def init_optimizer(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm: Optional[float] = 1.0):
+    def init_optimizer(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm: Optional[float] = 1.0,
+                       moment_dtype=F32):
         """AdamW state for this rank: fp32 master / m / v of the local 1/W slice of every bucket of the matrix region and of
         the whole (replicated) vector region. Defaults follow the reference's TrainingArguments (train_stage1.py:113-131:
-        adamw_torch, lr 1e-4, weight_decay 0) and HF Trainer's max_grad_norm 1.0."""
+        adamw_torch, lr 1e-4, weight_decay 0) and HF Trainer's max_grad_norm 1.0. moment_dtype=torch.bfloat16 stores the
+        matrix region's moments in bf16 (8 instead of 12 bytes of state per parameter): what ONE GPU needs to hold the
+        unsharded state of the 8B model; the sharded multi-GPU step keeps fp32."""
         L = self.lay
         pc, nb = L.piece, L.n_buckets
         mm = torch.empty(nb * pc, device=self.dev, dtype=F32)
@@ -965,7 +972,8 @@ class TrainEngine:
         vm = torch.empty(L.vec_total, device=self.dev, dtype=F32)
         T.cast(self.W[L.mat_total:], vm)
         self.opt = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay, clip=max_grad_norm, step=0,
-                        m_master=mm, m_m=torch.zeros_like(mm), m_v=torch.zeros_like(mm),
+                        m_master=mm, m_m=torch.zeros(nb * pc, device=self.dev, dtype=moment_dtype),
+                        m_v=torch.zeros(nb * pc, device=self.dev, dtype=moment_dtype),
                         v_master=vm, v_m=torch.zeros_like(vm), v_v=torch.zeros_like(vm),
                         gshard=torch.empty(nb * pc, device=self.dev, dtype=BF16) if self.world > 1 else None,
                         norm=torch.zeros(2, device=self.dev, dtype=F32), scale=torch.ones(1, device=self.dev, dtype=F32),

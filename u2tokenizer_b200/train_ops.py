@@ -253,7 +253,10 @@ def adamw(master, m, v, grad, param_out, *, lr, beta1=0.9, beta2=0.999, eps=1e-8
     n = master.numel()
     d = _adam_desc(lr, beta1, beta2, eps, weight_decay, step, grad_scale)
     lib = _lib.load()
-    if grad.dtype == BF16:
+    if grad.dtype == BF16 and m.dtype == BF16:
+        _lib.check(lib.u2_adamw_bf16_mom16(master.data_ptr(), m.data_ptr(), v.data_ptr(), grad.data_ptr(), _ptr(param_out), n,
+                                           C.byref(d), _stream()), "u2_adamw_bf16_mom16")
+    elif grad.dtype == BF16:
         _lib.check(lib.u2_adamw_bf16(master.data_ptr(), m.data_ptr(), v.data_ptr(), grad.data_ptr(), _ptr(param_out), n,
                                      C.byref(d), _stream()), "u2_adamw_bf16")
     else:
