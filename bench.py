@@ -50,6 +50,23 @@ def make_geometry(workload: str):
     elif workload == "cfg2":
         cfg = U2Qwen3Config(**QWEN3_1P7B)
         spec = dict(model="mu2-Qwen3-1.7B", batch=1, frames=4, new_tokens=0, n_question=32, lt=512, mode="forward")
+    elif workload == "cfg4":
+        # BASELINE configs[3]: mu2-Qwen3-8B, global batch 16 on 8 GPUs = 2 volumes / GPU, three raw scales (64 / 128 / 256)^3
+        # brought to [8, 32, 256, 256] by the reference's resize-and-pad rule (u2Transform.py:74-94,120: zero frames behind the
+        # real depth), teacher-forced sequences of 512 tokens (train_stage1.py:104), forward + backward + ZeRO-1 AdamW step
+        cfg = U2Qwen3Config(**QWEN3_8B)
+        spec = dict(model="mu2-Qwen3-8B", batch=2, frames=8, new_tokens=0, n_question=32, lt=512, seq=512, mode="train")
+    elif workload == "cfg5":
+        # BASELINE configs[4]: stage-2 DPO step, one preference pair / GPU (chosen + rejected = 2 sequences of 1024 tokens
+        # over the same study), policy forward + backward and frozen-reference forward (dpo_u2trainer.py:185-359)
+        cfg = U2Qwen3Config(**QWEN3_8B)
+        spec = dict(model="mu2-Qwen3-8B", batch=2, frames=8, new_tokens=0, n_question=32, lt=1024, seq=1024, mode="dpo")
+    elif workload == "tiny_train":
+        cfg = U2Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                            num_key_value_heads=2, head_dim=64, vocab_size=1024, image_size=[16, 64, 64],
+                            vit_hidden_size=128, vit_mlp_dim=256, vit_num_layers=2, vit_num_heads=2, u2t_num_layers=2,
+                            u2t_top_k=16, num_3d_query_token=16, tie_word_embeddings=False)
+        spec = dict(model="tiny", batch=2, frames=2, new_tokens=0, n_question=8, lt=16, seq=48, mode="train")
     elif workload == "tiny":  # plumbing check only
         cfg = U2Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
                             num_key_value_heads=2, head_dim=64, vocab_size=1024, image_size=[16, 64, 64],
@@ -286,9 +303,10 @@ def extra_rooflines(model, spec, geom):
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline(geom, spec, budget_note=True):
     """Times the fp32 oracle (a restatement of the reference's PyTorch forward) on the host cores.
-    Bounded sample: ONE volume with one layer of each stack (ViT block, SVR layer, TTA layer, decoder
-    layer at prefill and for a few cached decode tokens); the per-layer times are scaled by the real
-    layer counts to estimate one full step of the workload."""
+    Bounded sample (about 10-30 s of CPU work): ONE volume through the WHOLE vision path at full depth (patch embedding,
+    all ViT blocks, projector, all SVR / TTA layers, DiffTS, DMTP, linear aggregation - measured, not extrapolated), then
+    two decoder layers at the prompt length and for 8 cached decode tokens plus a 32k-row slice of the lm_head, scaled
+    by the decoder's layer count / vocabulary (the extrapolated share is reported)."""
     import copy
     from oracle import u2_oracle as O
     from u2tokenizer_b200.synthetic import synthetic_inputs, synthetic_state_dict
@@ -298,27 +316,32 @@ def cpu_baseline(geom, spec, budget_note=True):
         avail = os.cpu_count() or 1
 
     def best_threads(fn):
-        """The box may report far more logical CPUs than it can run well: pick the fastest thread count."""
+        """The box may report far more logical CPUs than it can run well: pick the fastest thread count (median of 3)."""
         best, best_t = avail, float("inf")
-        for n in sorted({min(avail, c) for c in (4, 8, 16, 32, 64, avail)}):
+        for n in sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)}):
             torch.set_num_threads(n)
             fn()
-            t0 = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t0
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            dt = statistics.median(ts)
             if dt < best_t:
                 best, best_t = n, dt
         return best
 
-    a_big, b_big = torch.randn(2048, 768), torch.randn(768, 3072)
-    a_vec, b_vec = torch.randn(1, geom.hidden_size), torch.randn(geom.hidden_size, geom.intermediate_size)
+    E, I = geom.hidden_size, geom.intermediate_size
+    a_big, b_big = torch.randn(2056 * 2, 768), torch.randn(768, 3072)          # one ViT MLP GEMM over two frames
+    a_vec, b_vec = torch.randn(1, E), torch.randn(E, 2 * I)                     # one decode-step gate|up GEMV
     n_big = best_threads(lambda: a_big @ b_big)
     n_vec = best_threads(lambda: a_vec @ b_vec)
     cores = max(n_big, n_vec)
     torch.set_num_threads(n_big)
     g1 = copy.deepcopy(geom)
-    g1.vit_layers, g1.u2t_num_layers, g1.num_hidden_layers = 1, 1, 1
-    g1.vocab_size = min(geom.vocab_size, 8192)  # lm_head timed separately below at its real size per token
+    n_dec = 2
+    g1.num_hidden_layers = n_dec
+    g1.vocab_size = min(geom.vocab_size, 8192)  # lm_head timed separately below on a 32k-row slice of the real width
     sd = {k: v.float() for k, v in synthetic_state_dict(g1, seed=0, device="cpu", dtype=torch.bfloat16).items()}
     images, ids, qids = synthetic_inputs(g1, batch=1, frames=spec["frames"], n_question=spec["n_question"], lt=spec["lt"])
     t = {}
@@ -330,53 +353,245 @@ def cpu_baseline(geom, spec, budget_note=True):
         return r
 
     with torch.no_grad():
-        fr = images.view(spec["frames"], 1, *g1.image_size)
-        x = timed("patch_embed", lambda: O.patch_embed(sd, "model.vision_tower.vision_tower.", fr, g1.patch_size))
-        x = torch.cat((sd["model.vision_tower.vision_tower.cls_token"].expand(x.shape[0], -1, -1), x), 1)
-        x = timed("vit_block", lambda: O.vit_block(sd, "model.vision_tower.vision_tower.blocks.0.", x, g1.vit_heads))
-        feats = timed("projector", lambda: O.spatial_pooling_projector(sd, "model.mm_projector.", x[:, 1:], g1))
-        v = feats.view(1, spec["frames"], -1, g1.hidden_size)
-        txt = torch.nn.functional.embedding(qids, sd["model.embed_tokens.weight"])
-        v1 = timed("svr_layer", lambda: O.svr_layer(sd, "model.u2tokenizer.svt_module.attention_network.layers.0.", v,
-                                                     g1.u2t_num_heads, g1.attn_type))
-        g_sel = copy.deepcopy(g1)
-        g_sel.u2t_num_layers = 0
-        vis = timed("select_pool", lambda: O.svr(sd, "model.u2tokenizer.svt_module.", v1, g_sel))
-        q = sd["model.u2tokenizer.query_tokens"]
-        g_t0 = copy.deepcopy(g1)
-        timed("tta_layer_plus_linagg", lambda: O.tta(sd, "model.u2tokenizer.tta_module.", q, vis, txt, g_t0))
-        g_t0.u2t_num_layers = 0
-        timed("linagg", lambda: O.tta(sd, "model.u2tokenizer.tta_module.", q, vis, txt, g_t0))
+        O.vit_block(sd, "model.vision_tower.vision_tower.blocks.0.", torch.randn(1, 2049, geom.vit_hidden), g1.vit_heads)  # warm
+        timed("vision_tokenizer_full_depth", lambda: O.visual_tokens(sd, images, qids, g1))
         L = ids.shape[1]
-        emb = torch.randn(1, L, g1.hidden_size) * 0.02
-        (_, past) = timed("dec_layer_prefill", lambda: O.decoder_forward(sd, emb, g1, return_hidden=True))
-        n_tok = 4
+        emb = torch.randn(1, L, E) * 0.02
+        (_, past) = timed("dec_prefill_%d_layers" % n_dec, lambda: O.decoder_forward(sd, emb, g1, return_hidden=True))
+        n_tok = 8
         torch.set_num_threads(n_vec)
+
         def dec():
             p = past
             for _ in range(n_tok):
-                _, p = O.decoder_forward(sd, torch.randn(1, 1, g1.hidden_size) * 0.02, g1, p, return_hidden=True)
-        timed("dec_layer_decode4", dec)
-        head = torch.randn(min(geom.vocab_size, 32768), g1.hidden_size)
-        hx = torch.randn(1, g1.hidden_size)
+                _, p = O.decoder_forward(sd, torch.randn(1, 1, E) * 0.02, g1, p, return_hidden=True)
+        dec()
+        timed("dec_decode_%d_tokens_%d_layers" % (n_tok, n_dec), dec)
+        head = torch.randn(min(geom.vocab_size, 32768), E)
+        hx = torch.randn(1, E)
+        hx @ head.t()
         timed("lm_head_32k_rows", lambda: hx @ head.t())
     log("[cpu_baseline] parts (s):", {k: round(v, 4) for k, v in t.items()}, "threads gemm/gemv", n_big, n_vec, "of", avail)
-    nl_v, nl_u, nl_d = geom.vit_layers, geom.u2t_num_layers, geom.num_hidden_layers
-    tta_layer = max(t["tta_layer_plus_linagg"] - t["linagg"], 0.0)
-    vision = t["patch_embed"] + nl_v * t["vit_block"] + t["projector"] + nl_u * t["svr_layer"] + t["select_pool"] \
-        + nl_u * tta_layer + t["linagg"]
-    prefill = nl_d * t["dec_layer_prefill"]
+    nl_d = geom.num_hidden_layers
+    vision = t["vision_tokenizer_full_depth"]
+    prefill = nl_d / n_dec * t["dec_prefill_%d_layers" % n_dec]
     head_tok = t["lm_head_32k_rows"] * geom.vocab_size / head.shape[0]
-    per_tok = nl_d * t["dec_layer_decode4"] / n_tok + head_tok
+    per_tok = nl_d / n_dec * t["dec_decode_%d_tokens_%d_layers" % (n_tok, n_dec)] / n_tok + head_tok
     per_volume = vision + prefill + spec["new_tokens"] * per_tok + (head_tok if spec["new_tokens"] else head_tok * L)
     vols = 1.0 / per_volume
-    sample = (f"oracle port (fp32 torch, {n_big} threads for GEMM phases / {n_vec} for decode, best of a sweep over "
-              f"{avail} logical CPUs): 1 volume x {spec['frames']} frames; timed 1 ViT block, 1 SVR layer, "
-              f"1 TTA layer, 1 decoder layer (prefill L={L} + {n_tok} cached tokens), lm_head slice; scaled by layer counts "
-              f"({nl_v}/{nl_u}/{nl_d}) and {spec['new_tokens']} new tokens; measured {sum(t.values()):.1f} s of CPU work")
+    measured = sum(t.values())
+    sample = (f"oracle port (fp32 torch eager, {n_big} threads for the GEMM phases / {n_vec} for decode, best of a sweep over "
+              f"{avail} logical CPUs): ONE volume x {spec['frames']} frames through the whole vision + mu2-tokenizer path at full "
+              f"depth (measured: {vision:.1f} s), {n_dec} of {nl_d} decoder layers at prefill L={L} and for {n_tok} cached tokens, "
+              f"a 32k-row lm_head slice; decoder scaled by {nl_d}/{n_dec} layers, {spec['new_tokens']} new tokens per volume; "
+              f"{measured:.1f} s of CPU work measured, vision share of the estimated step {vision / per_volume:.1%} measured "
+              f"directly, the remaining {1 - vision / per_volume:.1%} extrapolated from the decoder sample")
     return {"value": vols, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample,
             "per_volume_s": per_volume, "tokens_per_s": (1.0 / per_tok) if spec["new_tokens"] else None,
             "parts_s": {k: round(v, 4) for k, v in t.items()}}
+
+
+def gpu_eager_baseline(model, geom, spec, inputs, steps=2):
+    """Same-box GPU comparator ("the kernel to beat on the same box"): the reference modules'
+    arithmetic (the oracle functions) in bf16 under STOCK PyTorch eager - cuBLAS GEMMs, torch SDPA / flash attention,
+    ATen elementwise kernels - on the same GPU, same weights, same inputs, same timed region as `value`."""
+    from oracle import u2_oracle as O
+    images, ids, qids = inputs
+    sd = {k: v for k, v in model.state_dict().items()}
+    if "lm_head.weight" not in sd:
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    O.USE_SDPA = True
+    try:
+        def run():
+            with torch.no_grad():
+                if spec["mode"] == "generate":
+                    return O.greedy_generate(sd, ids, images.to(torch.bfloat16), qids, geom, spec["new_tokens"])[0]
+                return O.forward_logits(sd, ids, images.to(torch.bfloat16), qids, geom)[:, -1].float().argmax(-1)
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = run()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        O.USE_SDPA = False
+    ms = e0.elapsed_time(e1) / steps
+    B = spec["batch"]
+    return {"value": round(B / (ms / 1e3), 4), "unit": "volumes/s", "ms_per_step": round(ms, 2),
+            "tokens_per_s": round(B * spec["new_tokens"] / (ms / 1e3), 1) if spec["new_tokens"] else None,
+            "kind": "oracle functions (the reference modules' arithmetic) in bf16 under stock PyTorch eager: cuBLAS + torch SDPA, "
+                    "same GPU / weights / inputs / timed region; HF-style Python decode loop with a concatenated KV cache",
+            "steps": steps}
+
+
+# ------------------------------------------------------------------------------------------------
+# training workloads (cfg 4: SFT step, cfg 5: DPO step): forward + backward + ZeRO-1 gradient exchange + fused AdamW
+# ------------------------------------------------------------------------------------------------
+def train_flops(g, B, C, L, Lt):
+    """Forward FLOPs of one training sample batch (2 * M * N * K over every contraction on the path) and the step total:
+    backward = dgrad + wgrad of every Linear (2x forward) + the attention backward (2.5x its forward, incl. the recomputed
+    ViT scores); patch embedding has no dgrad."""
+    Hd, P, E, H = g.vit_hidden, g.n_patches, g.hidden_size, g.u2t_num_heads
+    S = P + 1
+    F_ = B * C
+    N, Q, K = g.tokens_per_frame, g.num_3d_query_token, g.u2t_top_k
+    lin = att = 0.0
+    pe = 2.0 * F_ * P * g.patch_dim * Hd
+    lin += g.vit_layers * 2.0 * F_ * S * (3 * Hd * Hd + Hd * Hd + 2 * Hd * g.vit_mlp)
+    att += g.vit_layers * 4.0 * F_ * S * S * Hd
+    lin += 2.0 * F_ * N * (Hd * E + E * E)                                         # projector
+    rows = F_ * N
+    lin += g.u2t_num_layers * 2 * 2.0 * rows * 4 * E * E                            # SVR: spatial + temporal, qkv + dense
+    att += g.u2t_num_layers * (4.0 * F_ * N * N * E + 4.0 * B * N * C * C * E)
+    T_ = C * N
+    if g.enable_diffts:
+        lin += 2.0 * B * T_ * K * E * 2
+    Mv = K + K // 2 + K // 4 if g.use_multi_scale else K
+    lin += g.u2t_num_layers * 2.0 * B * (Q * 4 * E * E + Q * 2 * E * E + Mv * 2 * E * E + Q * 2 * E * E + Lt * 2 * E * E)
+    att += g.u2t_num_layers * 4.0 * B * Q * (Q + Mv + Lt) * E
+    lin += 2.0 * B * (Q + Mv) * E * E
+    att += 4.0 * B * Q * Mv * E
+    hq, hkv, dh, I = g.num_attention_heads, g.num_key_value_heads, g.head_dim, g.intermediate_size
+    lin += g.num_hidden_layers * 2.0 * B * L * (E * (hq + 2 * hkv) * dh + hq * dh * E + 3 * E * I)
+    att += g.num_hidden_layers * 2.0 * B * L * L * hq * dh                          # causal: half of 4 * L^2
+    head = 2.0 * B * L * E * g.vocab_size
+    fwd = pe + lin + att + head
+    step = 2.0 * pe + 3.0 * lin + 3.5 * att + 4.0 * head                            # head: fused fwd + recomputed logits + 2 grads
+    return fwd, step
+
+
+def train_batch(geom, spec, rank, world):
+    """Synthetic training batch of the shapes the reference's collator yields (train_stage1.py:244-250): images
+    [B, 8, 32, 256, 256] with the three raw scales' zero-padded depth, input_ids = <im_patch> x 256 + question + answer,
+    labels = -100 on the visual / question part, question_ids right-padded to Lt."""
+    from u2tokenizer_b200.synthetic import synthetic_inputs
+    B, C, L = spec["batch"], spec["frames"], spec["seq"]
+    images, ids, qids = synthetic_inputs(geom, batch=B, frames=C, n_question=spec["n_question"], lt=spec["lt"], seed=4321 + rank)
+    for b in range(B):   # cfg 4: raw depth 64 / 128 / 256 -> 2 / 4 / 8 real frames, the rest is F.pad zeros
+        depth = (64, 128, 256)[(rank * B + b) % 3]
+        images[b, depth // 32:] = 0
+    gen = torch.Generator().manual_seed(99 + rank)
+    n_prompt = ids.shape[1]
+    if spec["mode"] == "dpo":
+        # one preference pair: chosen and rejected share the study and the prompt (dpo_u2trainer.py:151-183)
+        images = images[:1].expand(2, *images.shape[1:]).contiguous()
+        ids, qids = ids[:1].expand(2, -1).contiguous(), qids[:1].expand(2, -1).contiguous()
+    ans = torch.randint(1, max(16, geom.vocab_size - 16), (ids.shape[0], L - n_prompt), generator=gen)
+    ids = torch.cat([ids, ans], dim=1)
+    labels = ids.clone()
+    labels[:, :n_prompt] = -100
+    mask = torch.zeros_like(ids)
+    mask[:, n_prompt:] = 1
+    return images, ids, qids, labels, mask
+
+
+def run_train_steps(te, spec, geom, batch, steps, warmup, dist=None, ref_model=None):
+    """W warm-up + K timed optimizer steps; per-phase device times (CUDA events on the compute stream):
+    forward | backward (with the overlapped reduce-scatters in flight) | exposed gradient exchange (what is left of the
+    reduce-scatter when the backward's last kernel has finished) | clip + fused AdamW + all-gather."""
+    from u2tokenizer_b200 import _lib, parallel
+    images, ids, qids, labels, mask = [t.cuda() for t in batch]
+    beta = 0.1
+
+    def step(ev=None):
+        te.zero_grad()
+        if ev: ev[0].record()
+        if spec["mode"] == "dpo":
+            with torch.no_grad():
+                ref = ref_model.sequence_logps(images, ids, qids, mask)
+            if ev: ev[1].record()
+            out = te.dpo_forward_backward(images, ids, qids, mask, ref, beta)
+        else:
+            out = te.forward_loss(images, ids, qids, labels)
+            if ev: ev[1].record()
+            te.backward()
+        if ev: ev[2].record()
+        if te.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(te.comm_stream)
+        if ev: ev[3].record()
+        te.optimizer_step()
+        if ev: ev[4].record()
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(max(warmup, 1)):
+        out = step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _lib.launches()
+    e0.record()
+    for i in range(steps):
+        out = step(evs[i])
+    e1.record()
+    barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    ph = [0.0] * 4
+    for ev in evs:
+        for j in range(4):
+            ph[j] += ev[j].elapsed_time(ev[j + 1]) / steps
+    names = ("ref_forward" if spec["mode"] == "dpo" else "forward", "policy_fwd_bwd" if spec["mode"] == "dpo" else "backward",
+             "exposed_reduce_scatter", "clip_adamw_allgather")
+    phases = {n: round(parallel.max_over_ranks(v, device="cuda"), 3) for n, v in zip(names, ph)}
+    return ms, _lib.launches() - n0, phases, out
+
+
+def train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist):
+    """`--workload cfg4|cfg5`: one JSON line for the training step."""
+    from u2tokenizer_b200 import _lib, parallel
+    from u2tokenizer_b200.synthetic import synthetic_state_dict
+    from u2tokenizer_b200.train import TrainEngine
+    log(f"[rank {rank}] building {spec['model']} training state ...")
+    sd = synthetic_state_dict(geom, seed=0, device="cuda", dtype=torch.bfloat16)
+    te = TrainEngine(geom, sd, device="cuda", world_size=world, rank=rank)
+    ref_model = None
+    if spec["mode"] == "dpo":
+        ref_model = TrainEngine(geom, sd, device="cuda", world_size=1, rank=0, trainable={k: False for k in ("vit", "proj", "u2t", "dec", "embed", "head")})
+        ref_model.Gm = ref_model.Gv = None   # frozen reference: no gradient buffers
+    del sd
+    torch.cuda.empty_cache()
+    free, total = torch.cuda.mem_get_info()
+    n_mat = te.lay.mat_total
+    need_f32 = n_mat / world * 12
+    mom = torch.float32 if need_f32 + 40e9 < free else torch.bfloat16
+    te.init_optimizer(lr=4e-6, weight_decay=0.0, max_grad_norm=1.0, moment_dtype=mom)   # script/ct_rate_stage1.sh:36-38
+    batch = train_batch(geom, spec, rank, world)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, phases, out = run_train_steps(te, spec, geom, batch, args.steps, max(args.warmup, 3), dist, ref_model)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    B = spec["batch"] if spec["mode"] != "dpo" else 1   # DPO: one study per pair
+    n_tok = batch[1].shape[0] * batch[1].shape[1]
+    fwd_fl, step_fl = train_flops(geom, batch[1].shape[0], spec["frames"], spec["seq"], spec["lt"])
+    if spec["mode"] == "dpo":
+        step_fl += fwd_fl
+    hbm, tf, src = measured_peaks()
+    per_step = ms / args.steps
+    compute_ms = per_step - phases["exposed_reduce_scatter"] - phases["clip_adamw_allgather"]
+    out_d = dict(base)
+    out_d.update({"value": round(world * B * args.steps / (ms / 1e3), 4), "ms_per_step": round(per_step, 3), "dtype": "bf16",
+                  "tokens_per_sec": round(world * n_tok * args.steps / (ms / 1e3), 1), "gpu_launches": int(launches), "clocks": clocks,
+                  "phases_ms": phases, "loss": [float(x) for x in out.flatten()[:3]] if out.numel() > 1 else float(out),
+                  "optimizer": f"AdamW, ZeRO-1 over {world} rank(s): fp32 master, {str(mom).split('.')[-1]} moments, "
+                               f"{te.lay.n_buckets} gradient buckets of {te.lay.bucket} bf16 elements, max_grad_norm 1.0",
+                  "roofline": {"bound": "tensor", "kernel": "training step (all tcgen05 GEMMs: forward, dgrad, wgrad, attention)",
+                               "achieved": round(step_fl / (compute_ms / 1e3) / 1e12, 1), "peak": tf, "unit": "TFLOP/s",
+                               "frac": round(step_fl / (compute_ms / 1e3) / 1e12 / tf, 4), "traffic": None, "peak_source": src,
+                               "flops_per_step": step_fl, "note": "algorithmic FLOPs of forward + backward per rank / (forward + backward ms)"},
+                  "e2e": {"value": None, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                          "note": "training batches are staged on the device by the loader; see the generate workload for e2e"}})
+    out_d["scaling"] = "weak"
+    out_d["config"]["parallelism"] = f"dp{world}: ZeRO-1 (bucketed NCCL reduce-scatter overlapped with the backward, sharded fused AdamW, all-gather)"
+    print(json.dumps(out_d), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -410,7 +625,7 @@ def main():
         t0 = time.time()
         vals = []
         cb = None
-        for _ in range(max(1, min(args.steps, 2))):
+        for _ in range(1):  # one bounded sample (about 10-30 s of CPU work + the weight generation)
             cb = cpu_baseline(geom, spec)
             vals.append(cb["value"])
         v = statistics.median(vals)
@@ -432,6 +647,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from u2tokenizer_b200 import _lib, parallel
     from u2tokenizer_b200.synthetic import synthetic_inputs
+    if spec["mode"] in ("train", "dpo"):
+        train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     log(f"[rank {rank}] building {spec['model']} ...")
     model = build_model(cfg, geom)
     images, ids, qids = synthetic_inputs(geom, batch=spec["batch"], frames=spec["frames"], n_question=spec["n_question"],
@@ -505,6 +725,13 @@ def main():
         out["roofline_other_kernels"] = extra_rooflines(model, spec, geom)
     except Exception as e:
         out["roofline_other_kernels"] = [{"error": repr(e)}]
+    if world == 1 and os.environ.get("U2_BENCH_GPU_EAGER", "1") != "0":
+        try:
+            out["gpu_eager_baseline"] = gpu_eager_baseline(model, geom, spec, (d_images, d_ids, d_q))
+            out["gpu_eager_baseline"]["speedup_of_value"] = round(out["value"] / out["gpu_eager_baseline"]["value"], 2)
+        except Exception as e:
+            out["gpu_eager_baseline"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         try:
             del model

@@ -30,6 +30,29 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# bench.py's same-box GPU comparator ("stock PyTorch eager": cuBLAS + SDPA / flash attention) flips this; the parity
+# checks always run with the explicit softmax(QK^T)V below
+USE_SDPA = False
+
+
+def _sdpa(q, k, v, scale, bias=None, causal=False):
+    """softmax(q k^T * scale + bias) v for [b, h, s, d] tensors: explicit (the reference's arithmetic) or, for the GPU
+    eager baseline, torch's fused scaled_dot_product_attention."""
+    if USE_SDPA:
+        if k.shape[1] != q.shape[1]:
+            return F.scaled_dot_product_attention(q, k, v, attn_mask=bias, is_causal=causal, scale=scale, enable_gqa=True)
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=bias, is_causal=causal, scale=scale)
+    if k.shape[1] != q.shape[1]:
+        rep = q.shape[1] // k.shape[1]
+        k, v = k.repeat_interleave(rep, dim=1), v.repeat_interleave(rep, dim=1)
+    s = q @ k.transpose(-2, -1) * scale
+    if bias is not None:
+        s = s + bias
+    if causal:
+        sq, sk = q.shape[-2], k.shape[-2]
+        s = s + torch.full((sq, sk), float("-inf"), device=q.device, dtype=s.dtype).triu(diagonal=sk - sq + 1)
+    return torch.softmax(s, dim=-1) @ v
+
 
 def _lin(x: torch.Tensor, sd: SD, name: str, bias: bool = True) -> torch.Tensor:
     b = sd.get(name + ".bias") if bias else None
@@ -62,8 +85,11 @@ def vit_block(sd: SD, pre: str, x: torch.Tensor, num_heads: int) -> torch.Tensor
     # Rearrange("b h (qkv l d) -> qkv b l h d", qkv=3, l=num_heads)
     qkv = qkv.view(b, s, 3, num_heads, dh).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
-    att = torch.softmax(torch.einsum("blxd,blyd->blxy", q, k) * (dh ** -0.5), dim=-1)
-    o = torch.einsum("bhxy,bhyd->bhxd", att, v).permute(0, 2, 1, 3).reshape(b, s, hid)
+    if USE_SDPA:
+        o = _sdpa(q, k, v, dh ** -0.5).permute(0, 2, 1, 3).reshape(b, s, hid)
+    else:
+        att = torch.softmax(torch.einsum("blxd,blyd->blxy", q, k) * (dh ** -0.5), dim=-1)
+        o = torch.einsum("bhxy,bhyd->bhxd", att, v).permute(0, 2, 1, 3).reshape(b, s, hid)
     x = x + _lin(o, sd, pre + "attn.out_proj")
     y = F.layer_norm(x, (hid,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
     y = _lin(F.gelu(_lin(y, sd, pre + "mlp.linear1")), sd, pre + "mlp.linear2")
@@ -127,11 +153,14 @@ def rma(sd: SD, pre: str, x: torch.Tensor, h: int, max_seq_len: int = 512) -> to
     q = _split_heads(_lin(x, sd, pre + "wq"), h)
     k = _split_heads(_lin(x, sd, pre + "wk"), h)
     v = _split_heads(_lin(x, sd, pre + "wv"), h)
-    scores = q @ k.transpose(-2, -1) / math.sqrt(dh)
     pos = torch.arange(s, device=x.device)
     idx = pos[None, :] - pos[:, None] + max_seq_len - 1
-    scores = scores + sd[pre + "relative_bias"][idx].permute(2, 0, 1).unsqueeze(0)
-    ctx = torch.softmax(scores, dim=-1) @ v
+    if USE_SDPA:
+        ctx = _sdpa(q, k, v, 1.0 / math.sqrt(dh), bias=sd[pre + "relative_bias"][idx].permute(2, 0, 1).unsqueeze(0).to(q.dtype))
+    else:
+        scores = q @ k.transpose(-2, -1) / math.sqrt(dh)
+        scores = scores + sd[pre + "relative_bias"][idx].permute(2, 0, 1).unsqueeze(0)
+        ctx = torch.softmax(scores, dim=-1) @ v
     ctx = ctx.permute(0, 2, 1, 3).reshape(b, s, e)
     return _lin(ctx, sd, pre + "dense")
 
@@ -176,7 +205,10 @@ def cross_attn(sd: SD, pre: str, q_in: torch.Tensor, kv_in: torch.Tensor, h: int
     q = _split_heads(_lin(q_in, sd, pre + "wq"), h)
     k = _split_heads(_lin(kv_in, sd, pre + "wk"), h)
     v = _split_heads(kv_in if is_compress else _lin(kv_in, sd, pre + "wv"), h)
-    ctx = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dh), dim=-1) @ v
+    if USE_SDPA:
+        ctx = _sdpa(q, k, v, 1.0 / math.sqrt(dh))
+    else:
+        ctx = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dh), dim=-1) @ v
     ctx = ctx.permute(0, 2, 1, 3).reshape(b, sq, e)
     return ctx if is_compress else _lin(ctx, sd, pre + "dense")
 
@@ -350,10 +382,13 @@ def decoder_forward(sd: SD, inputs_embeds: torch.Tensor, cfg, past=None, return_
             k = torch.cat((past[i][0], k), dim=2)
             v = torch.cat((past[i][1], v), dim=2)
         new_past.append((k, v))
-        kk = k.repeat_interleave(hq // hkv, dim=1)
-        vv = v.repeat_interleave(hq // hkv, dim=1)
-        att = torch.softmax(q @ kk.transpose(-2, -1) / math.sqrt(dh) + mask, dim=-1)
-        o = (att @ vv).transpose(1, 2).reshape(b, s, hq * dh)
+        if USE_SDPA:
+            o = _sdpa(q, k, v, 1.0 / math.sqrt(dh), causal=(s > 1)).transpose(1, 2).reshape(b, s, hq * dh)
+        else:
+            kk = k.repeat_interleave(hq // hkv, dim=1)
+            vv = v.repeat_interleave(hq // hkv, dim=1)
+            att = torch.softmax(q @ kk.transpose(-2, -1) / math.sqrt(dh) + mask, dim=-1)
+            o = (att @ vv).transpose(1, 2).reshape(b, s, hq * dh)
         x = x + _lin(o, sd, lp + "self_attn.o_proj")
         y = _rms(x, sd[lp + "post_attention_layernorm.weight"], eps)
         y = _lin(F.silu(_lin(y, sd, lp + "mlp.gate_proj")) * _lin(y, sd, lp + "mlp.up_proj"), sd, lp + "mlp.down_proj")

@@ -72,6 +72,14 @@ class Layout:
         self.bucket = max(8 * W, (per + 8 * W - 1) // (8 * W) * (8 * W))
         self.mat_total = self.n_buckets * self.bucket
         self.piece = self.bucket // W   # elements of one bucket owned by one rank
+        self.name_buckets = {}          # matrix name -> buckets its slot intersects
+        self.bucket_names = [[] for _ in range(self.n_buckets)]
+        for n in mats:
+            lo, hi = self.mat_off[n], self.mat_off[n] + self._numel(n)
+            bs = list(range(lo // self.bucket, (hi - 1) // self.bucket + 1))
+            self.name_buckets[n] = bs
+            for b in bs:
+                self.bucket_names[b].append(n)
         off = 0
         for n in vecs:
             self.vec_off[n] = off
@@ -137,6 +145,12 @@ class TrainEngine:
         self.opt = None
         self.tape: List = []
         self.stats = {}
+        # gradient exchange overlapped with the backward pass: a bucket's reduce-scatter is issued on the communication
+        # stream as soon as the wgrads of every parameter in it have been issued (reference: DeepSpeed overlap_comm,
+        # config/ds_config.json:35)
+        self.overlap = world_size > 1
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
+        self._pending = None
 
     # =========================================================================================
     # flat-buffer views
@@ -224,6 +238,25 @@ class TrainEngine:
 
     def _tr(self, group: str) -> bool:
         return bool(self.trainable.get(group, True))
+
+    def _mark(self, names: Sequence[str]):
+        """Placed on the tape BEFORE the ops of a segment: in the reversed (backward) order it runs right after the
+        segment's last gradient kernel has been issued, i.e. when the gradients of `names` are final."""
+        names = [n for n in names if n in self.lay.mat_off]
+
+        def done():
+            if self._pending is None:
+                return
+            for n in names:
+                for b in self.lay.name_buckets[n]:
+                    self._pending[b].discard(n)
+                    if not self._pending[b] and not self.opt["reduced"][b]:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        with torch.cuda.stream(self.comm_stream):
+                            self.comm_stream.wait_event(ev)
+                            self.reduce_bucket(b)
+        self.tape.append(done)
 
     # ---- linear ---------------------------------------------------------------------------------
     def linear(self, x: Var, w: torch.Tensor, gw: Optional[torch.Tensor], bias: Optional[torch.Tensor] = None,
@@ -322,7 +355,7 @@ class TrainEngine:
 
     # ---- attention through the GEMM (scores fp32, probabilities bf16 kept for the backward) -----------
     def attention(self, qv: Var, q_view, kv: Var, k_view, vv: Var, v_view, out_shape, scale: float,
-                  rel_name: Optional[str] = None, causal: bool = False, group: str = "u2t") -> Var:
+                  rel_name: Optional[str] = None, causal: bool = False, group: str = "u2t", recompute: bool = False) -> Var:
         """q_view / k_view / v_view map the base tensor of a Var (value or gradient, same shape) to the strided 4-D view
         [b, S, heads, dh]. Returns ctx Var [b, Sq, h*dh] (out_shape may pad the token axis: extra rows stay zero)."""
         q, k, v = q_view(qv.v), k_view(kv.v), v_view(vv.v)
@@ -334,18 +367,34 @@ class TrainEngine:
         rel = self.v32(rel_name).view(-1) if rel_name is not None else None
         ctx_full = torch.zeros(out_shape, device=dev, dtype=BF16) if out_shape[1] != Sq else torch.empty(out_shape, device=dev, dtype=BF16)
         ctx = ctx_full[:, :Sq]
-        sc = torch.empty(b, h, Sq, Skp, device=dev, dtype=F32)
-        pr = torch.empty(b, h, Sq, Skp, device=dev, dtype=BF16)
-        ops.gemm(q, k, sc, M=Sq, N=Sk, K=dh, lda=q.stride(1), ldb=k.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
-                 a_strides=(q.stride(2), q.stride(0)), b_strides=(k.stride(2), k.stride(0)), c_strides=(Sq * Skp, h * Sq * Skp),
-                 alpha=scale)
-        ops.softmax(sc, pr, n0=b, H=h, S=Sq, n=Sk, in_strides=(h * Sq * Skp, Sq * Skp, Skp),
-                    out_strides=(h * Sq * Skp, Sq * Skp, Skp), rel_bias=rel, rel_max=REL_MAX, causal=causal, causal_off=Sk - Sq,
-                    zero_pad_to=Skp)
-        del sc
-        # ctx = P @ V: V [Sk, dh] is consumed as stored (MN-major B operand: no transposed copy)
-        ops.gemm(pr, v, ctx, M=Sq, N=dh, K=Sk, lda=Skp, ldb=v.stride(1), ldc=ctx.stride(1), zi=h, zo=b, b_zi_div=G,
-                 a_strides=(Sq * Skp, h * Sq * Skp), b_strides=(v.stride(2), v.stride(0)), c_strides=(dh, ctx.stride(0)), b_mn=True)
+
+        def probs():
+            sc = torch.empty(b, h, Sq, Skp, device=dev, dtype=F32)
+            p_ = torch.empty(b, h, Sq, Skp, device=dev, dtype=BF16)
+            ops.gemm(q, k, sc, M=Sq, N=Sk, K=dh, lda=q.stride(1), ldb=k.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
+                     a_strides=(q.stride(2), q.stride(0)), b_strides=(k.stride(2), k.stride(0)),
+                     c_strides=(Sq * Skp, h * Sq * Skp), alpha=scale)
+            ops.softmax(sc, p_, n0=b, H=h, S=Sq, n=Sk, in_strides=(h * Sq * Skp, Sq * Skp, Skp),
+                        out_strides=(h * Sq * Skp, Sq * Skp, Skp), rel_bias=rel, rel_max=REL_MAX, causal=causal,
+                        causal_off=Sk - Sq, zero_pad_to=Skp)
+            return p_
+        saved = {}
+        if recompute and dh == 64 and h == hk and rel is None and not causal:
+            # fused tcgen05 attention forward (scores never leave the SM); the probabilities are recomputed in the backward
+            vt = torch.empty(b, hk, dh, Skp, device=dev, dtype=BF16)
+            ops.transpose_heads(v, vt, B=b, S=Sk, H=hk, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
+                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
+            ops.flash_attention_d64(q, k, vt, ctx, scale)
+            del vt
+        else:
+            pr0 = probs()
+            # ctx = P @ V: V [Sk, dh] is consumed as stored (MN-major B operand: no transposed copy)
+            ops.gemm(pr0, v, ctx, M=Sq, N=dh, K=Sk, lda=Skp, ldb=v.stride(1), ldc=ctx.stride(1), zi=h, zo=b, b_zi_div=G,
+                     a_strides=(Sq * Skp, h * Sq * Skp), b_strides=(v.stride(2), v.stride(0)), c_strides=(dh, ctx.stride(0)),
+                     b_mn=True)
+            if not recompute:
+                saved["p"] = pr0
+            del pr0
         out = Var(ctx_full, qv.ng or kv.ng or vv.ng)
         tr_rel = rel_name is not None and self._tr(group)
 
@@ -353,6 +402,9 @@ class TrainEngine:
             if out.g is None:
                 return
             do = out.g[:, :Sq].view(b, Sq, h, dh)
+            pr = saved.pop("p", None)
+            if pr is None:
+                pr = probs()
             # gradient buffers of the operands (first writer allocates; later consumers accumulate)
             fresh = {}
             for var in (qv, kv, vv):
@@ -433,6 +485,7 @@ class TrainEngine:
                  residual=pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
         ops.set_rows(x0, self.w(v + "cls_token").view(Hd), Fr, Sp, 0)
         x_emb = Var(x0.view(Fr * Sp, Hd), trv)   # NOT `x`: that name is rebound by the layer loop below
+        self._mark([v + "patch_embedding.patch_embeddings.1.weight"])
 
         def bwd_embed():
             if x_emb.g is None or not trv:
@@ -454,13 +507,15 @@ class TrainEngine:
             return lambda t: t.view(Fr, Sp, 3, nh, dh)[:, :S, i]
         for li in range(g.vit_layers):
             b = f"{v}blocks.{li}."
+            self._mark([b + "attn.qkv.weight", b + "attn.out_proj.weight", b + "mlp.linear1.weight", b + "mlp.linear2.weight"])
             gw = (lambda n: self.gm(b + n)) if trv else (lambda n: None)
             gb = (lambda n: self.gv(b + n)) if trv else (lambda n: None)
             y = self.layernorm(x, b + "norm1.weight", b + "norm1.bias", "vit")
             has_qb = (b + "attn.qkv.bias") in self.lay.shapes
             qkv = self.linear(y, self.w(b + "attn.qkv.weight"), gw("attn.qkv.weight"),
                               self.v32(b + "attn.qkv.bias") if has_qb else None, gb("attn.qkv.bias") if has_qb else None)
-            ctx = self.attention(qkv, view_q(0), qkv, view_q(1), qkv, view_q(2), (Fr, Sp, Hd), dh ** -0.5, group="vit")
+            ctx = self.attention(qkv, view_q(0), qkv, view_q(1), qkv, view_q(2), (Fr, Sp, Hd), dh ** -0.5, group="vit",
+                                 recompute=True)
             ctx2 = Var(ctx.v.view(Fr * Sp, Hd), ctx.ng)
             self._alias(ctx2, ctx)
             x = self.linear(ctx2, self.w(b + "attn.out_proj.weight"), gw("attn.out_proj.weight"), self.v32(b + "attn.out_proj.bias"),
@@ -495,6 +550,7 @@ class TrainEngine:
         trp = self._tr("proj")
         p = "model.mm_projector.projector."
         n = int(g.proj_layer_num)
+        self._mark([k for k in self.lay.mat_names if k.startswith(p)])
         for i in range(n):
             idx = (2 * i if g.proj_layer_type == "mlp" else i) if i else 0
             z = self.linear(z, self.w(p + f"{idx}.weight"), self.gm(p + f"{idx}.weight") if trp else None,
@@ -701,8 +757,10 @@ class TrainEngine:
         x = v_tokens
         for i in range(g.u2t_num_layers):
             l = f"{u}svt_module.attention_network.layers.{i}."
+            self._mark([k for k in self.lay.mat_names if k.startswith(l)])
             x = self._self_attention(x, B * C, N, l + "spatial_attention.")
             x = self._temporal_attention(x, B, C, N, l + "temporal_attention.")
+        self._mark([u + "svt_module.token_selection.score_net.weight"])
         sel = self._token_selection_diff(x, B, C * N) if g.enable_diffts else self._token_selection_hard(x, B, C * N)
         if sel.v.dim() == 2:
             s3 = Var(sel.v.view(B, -1, E), sel.ng)
@@ -722,8 +780,11 @@ class TrainEngine:
             q_tok.g = None
         self.tape.append(bwd_q)
         q = q_tok
+        lin = u + "tta_module.layer_linagg.linear_aggregator."
+        self._mark([lin + "wq.weight", lin + "wk.weight"])
         for i in range(g.u2t_num_layers):
             l = f"{u}tta_module.layers_vt.{i}."
+            self._mark([k for k in self.lay.mat_names if k.startswith(l)])
             s = self._self_attention(q, B, Q, l + "self_attention.")
             s = self.layernorm(s, l + "norm_self.weight", l + "norm_self.bias", "u2t", residual=q)
             vx = self._cross_attention(s, vis, B, Q, Mv, l + "visual_cross_attention.", residual=None)
@@ -778,6 +839,7 @@ class TrainEngine:
         eps = g.rms_norm_eps
         for li in range(g.num_hidden_layers):
             l = f"model.layers.{li}."
+            self._mark([k for k in self.lay.mat_names if k.startswith(l)])
             y = self.rmsnorm(x, l + "input_layernorm.weight", "dec", eps)
             wn = [l + "self_attn.q_proj.weight", l + "self_attn.k_proj.weight", l + "self_attn.v_proj.weight"]
             qkv_raw = self.linear(y, self.wcat(wn), self.gm(wn) if tr else None)
@@ -832,6 +894,8 @@ class TrainEngine:
         hname, Wh = self._head_w()
         h2 = hidden.v
         lab = labels.to(self.dev, torch.int64).contiguous().view(-1)
+        if not self.tied:
+            self._mark([hname])
         logp, lse, _ = ops.lmhead_logprob(h2, Wh, lab, want_lse=True)
         trh = self._tr("head") if not self.tied else (self._tr("head") or self._tr("embed"))
 
@@ -847,6 +911,11 @@ class TrainEngine:
             if hidden.ng:
                 self._acc(hidden, T.linear_dgrad(dl, Wh), owned=True)
         self.tape.append(bwd)
+        lin = "model.u2tokenizer.tta_module.layer_linagg.linear_aggregator."
+        unused = [lin + "wv.weight", lin + "dense.weight"]   # never run by the reference either (tta.py:47-48,62-65)
+        if not self.g.enable_diffts:
+            unused.append("model.u2tokenizer.svt_module.token_selection.score_net.weight")  # top-k indices carry no gradient
+        self._mark(unused)
         return logp, lse
 
     # =========================================================================================
@@ -858,6 +927,7 @@ class TrainEngine:
         B, Lx = input_ids.shape
         vis = None
         n_vis = 0
+        self._mark(["model.embed_tokens.weight"])   # first on the tape = last in the backward: the embedding's gradient
         if images is not None:
             if g.enable_u2tokenizer:
                 Bi, C = images.shape[0], images.shape[1]
@@ -876,9 +946,14 @@ class TrainEngine:
         return self.decoder(x, B, Lx), B, Lx
 
     def run_backward(self):
+        if self.overlap and self.opt is not None and self.world > 1:
+            self._pending = [set(ns) for ns in self.lay.bucket_names]
+        else:
+            self._pending = None
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        self._pending = None
 
     def forward_loss(self, images, input_ids, question_ids, labels) -> torch.Tensor:
         """Forward half of the training step: HF ForCausalLMLoss of `model(images=, input_ids=, question_ids=, labels=)`
@@ -1007,6 +1082,8 @@ class TrainEngine:
         L = self.lay
         W_, pc, nb = self.world, L.piece, L.n_buckets
         o["step"] += 1
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
         if W_ > 1:
             self.Gv.mul_(1.0 / W_)  # a few MB of fp32: plumbing of the collective (mean), not hot-path arithmetic
             dist.all_reduce(self.Gv, group=self.group)
