@@ -304,9 +304,10 @@ class U2MetaForCausalLM(ABC):
             raise NotImplementedError("HF-driven cached decoding is not supported; call generate() "
                                       "(greedy decode runs inside the engine with its own static KV cache)")
         self._check_right_padded(attention_mask)
-        if (labels is not None and torch.is_grad_enabled() and inputs_embeds is None and input_ids is not None
+        if (labels is not None and self.training and torch.is_grad_enabled() and inputs_embeds is None and input_ids is not None
                 and any(p.requires_grad for p in self.parameters())):
-            # training step (reference train_stage1.py:244-250: batch -> model(**batch) -> loss.backward()): forward with
+            # training step (model.train(), reference train_stage1.py:244-250: batch -> model(**batch) -> loss.backward();
+            # in eval mode the same call returns loss + logits from the inference path): forward with
             # saved activations on the training engine, backward through ONE autograd node that hands every parameter its
             # gradient (computed by the hand-written backward pass, not by torch autograd)
             te = self.train_engine()
