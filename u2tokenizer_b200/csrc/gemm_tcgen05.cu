@@ -40,7 +40,8 @@ struct GemmCfg {
   static constexpr int kBBytes = kBlockN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;  // double-buffered accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 8 * 4096;  // one 32 x 32 fp32 staging tile per epilogue warp (coalesced stores)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
 };
 
 struct GemmDev {
@@ -110,6 +111,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes + 256;  // 8 x 4 KB staging tiles, one per epilogue warp
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -299,10 +301,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
-        if (row_ok) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (row_ok) {
           const bool full = (col0 + 32 <= p.N);
           if (p.bias) {
 #pragma unroll
@@ -332,33 +334,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
             }
           }
+          (void)0;
+        }
+        // ---- store. Fast path: the warp's 32 x 32 block goes through a swizzled shared-memory tile so that every store
+        // instruction writes whole 128-byte (fp32) / 64-byte (bf16) row segments; the thread-per-row pattern it replaces
+        // touched 32 half-used sectors per request, which bounded every short-K GEMM (attention scores, wgrad with few
+        // rows) by its epilogue.
+        const bool fast = (col0 + 32 <= p.N) &&
+                          (p.c_dtype == U2_DT_BF16 ? (((p.ldc | zoff) & 7) == 0) : (((p.ldc | zoff) & 3) == 0));
+        uint8_t* st = smem_epi + (warp_idx - kEpiWarp0) * 4096;
+        const int row0 = m_blk * kBlockM + q * 32;
+        if (fast) {
+          __syncwarp();  // the previous chunk's read-back is complete
           if (p.c_dtype == U2_DT_BF16) {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + col0;
-            if (full && ((p.ldc & 7) == 0) && ((c_off & 7) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(c + j) = o;
+              for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * c + 2 * e], f[8 * c + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+              const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+              const int grow = row0 + rr;
+              if (grow < p.M) {
+                long long orow = grow;
+                if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + zoff + orow * p.ldc + col0 + ch * 8) = o;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) c[j] = __float2bfloat16(f[j]);
             }
           } else {
-            float* c = reinterpret_cast<float*>(p.C) + c_off + col0;
-            if (full && ((p.ldc & 3) == 0) && ((c_off & 3) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(st + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                  make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) c[j] = f[j];
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+              const float4 o = *reinterpret_cast<const float4*>(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              const int grow = row0 + rr;
+              if (grow < p.M) {
+                long long orow = grow;
+                if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + zoff + orow * p.ldc + col0 + ch * 4) = o;
+              }
             }
+          }
+        } else if (row_ok) {
+          if (p.c_dtype == U2_DT_BF16) {
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = __float2bfloat16(f[j]);
+          } else {
+            float* c = reinterpret_cast<float*>(p.C) + c_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) c[j] = f[j];
           }
         }
       }

@@ -233,6 +233,68 @@ softmax_rows_kernel(const SoftmaxArgs a) {
   }
 }
 
+// Long plain rows (the ViT's 2049 keys: no bias, no mask): one WARP per row, 16-byte vector loads, the row held in
+// registers - no block-wide barriers, ~270 bytes in flight per thread (the one-CTA-per-row variant above reached
+// 1.8 TB/s on these rows because every row paid two __syncthreads round trips).
+template <int kMaxV4>
+__global__ void __launch_bounds__(256)
+softmax_warp_vec_kernel(const SoftmaxArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)a.n0 * a.H * a.S;
+  if (row >= total) return;
+  const int i2 = (int)(row % a.S);
+  const int i1 = (int)((row / a.S) % a.H);
+  const long long i0 = row / ((long long)a.S * a.H);
+  const float4* in = reinterpret_cast<const float4*>(a.in + i0 * a.in_s0 + i1 * a.in_s1 + i2 * a.in_s2);
+  __nv_bfloat16* out = a.out + i0 * a.out_s0 + i1 * a.out_s1 + i2 * a.out_s2;
+  const int span = max(a.n, a.zero_pad_to);
+  const int nv = (span + 3) >> 2;  // float4 groups (the padded row is readable: pads are written by the producer GEMM's ld)
+  float4 v[kMaxV4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxV4; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      float4 t = in[c];
+      const int j = c * 4;
+      t.x = j + 0 < a.n ? t.x * a.scale : -INFINITY;
+      t.y = j + 1 < a.n ? t.y * a.scale : -INFINITY;
+      t.z = j + 2 < a.n ? t.z * a.scale : -INFINITY;
+      t.w = j + 3 < a.n ? t.w * a.scale : -INFINITY;
+      v[i] = t;
+      m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV4; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m); v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  s = warp_sum(s);
+  const float inv = s > 0.f ? 1.f / s : 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV4; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv);
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+      if (c * 4 + 3 < span) {
+        reinterpret_cast<uint2*>(out)[c] = o;
+      } else {
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&o);
+        for (int e = 0; e < 4 && c * 4 + e < span; ++e) out[c * 4 + e] = h[e];
+      }
+    }
+  }
+}
+
 // Rows longer than the register-resident variants hold (> 8192 keys, e.g. DiffTS over 64 frames x 256 tokens, the
 // reference's own smoke shape svr.py:190-205): one CTA per row, three passes over the (L2-resident) row.
 __global__ void __launch_bounds__(256)
@@ -344,6 +406,17 @@ extern "C" U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_s
 #define U2_SM_CASE(G, MV)                                                                 \
   softmax_rows_kernel<G, MV><<<(unsigned)((rows + ((G) == 32 ? 4 : 1) - 1) / ((G) == 32 ? 4 : 1)), \
                                (G) == 32 ? 128 : (G), 0, st>>>(a)
+  // long plain rows: warp-per-row vector variant (needs 16-byte aligned fp32 rows, 8-byte aligned bf16 rows, a span that
+  // is a whole number of float4 groups - the callers pad rows to 8 elements)
+  const bool vec_ok = !d->rel_bias && !d->causal && span > 1024 && span <= 2560 && (span & 3) == 0 &&
+                      (d->in_s0 & 3) == 0 && (d->in_s1 & 3) == 0 && (d->in_s2 & 3) == 0 && (d->out_s0 & 3) == 0 &&
+                      (d->out_s1 & 3) == 0 && (d->out_s2 & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 7) == 0 && d->zero_pad_to >= d->n;
+  if (vec_ok) {
+    softmax_warp_vec_kernel<20><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+    U2_CHECK_LAUNCH("softmax");
+    return U2_OK;
+  }
   if (span <= 32) U2_SM_CASE(32, 1);
   else if (span <= 64) U2_SM_CASE(32, 2);
   else if (span <= 128) U2_SM_CASE(32, 4);

@@ -365,6 +365,49 @@ softmax_bwd_kernel(const SmBwdArgs a) {
   }
 }
 
+// long plain rows (ViT, 2049 keys): one warp per row, 16-byte vector loads of P (8 bf16) and dP (2 x float4)
+template <int kMaxV8>
+__global__ void __launch_bounds__(256)
+softmax_bwd_warp_vec_kernel(const SmBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)a.n0 * a.H * a.S;
+  if (row >= total) return;
+  const int i2 = (int)(row % a.S);
+  const int i1 = (int)((row / a.S) % a.H);
+  const long long i0 = row / ((long long)a.S * a.H);
+  const uint4* P = reinterpret_cast<const uint4*>(a.P + i0 * a.p_s0 + i1 * a.p_s1 + i2 * a.p_s2);
+  const float4* dP = reinterpret_cast<const float4*>(a.dP + i0 * a.dp_s0 + i1 * a.dp_s1 + i2 * a.dp_s2);
+  uint4* dS = reinterpret_cast<uint4*>(a.dS + i0 * a.ds_s0 + i1 * a.ds_s1 + i2 * a.ds_s2);
+  const int span = max(a.n, a.zero_pad_to);
+  const int nv = span >> 3;  // groups of 8 (span % 8 == 0 checked by the host)
+  float p[kMaxV8][8], g[kMaxV8][8];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV8; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      t_unpack8(P[c], p[i]);
+      const float4 g0 = dP[2 * c], g1 = dP[2 * c + 1];
+      g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w;
+      g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += (c * 8 + j < a.n) ? p[i][j] * g[i][j] : 0.f;
+    }
+  }
+  dot = t_wsum(dot);
+#pragma unroll
+  for (int i = 0; i < kMaxV8; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (c * 8 + j < a.n) ? p[i][j] * (g[i][j] - dot) : 0.f;
+      dS[c] = t_pack8(o);
+    }
+  }
+}
+
 // rows longer than 8192 (DiffTS over many frames): one CTA per row, two passes
 __global__ void __launch_bounds__(256)
 softmax_bwd_long_kernel(const SmBwdArgs a) {
@@ -1087,6 +1130,15 @@ extern "C" U2_API int u2_softmax_bwd_bf16(const void* P, const float* dP, void* 
   const int span = d->n > d->zero_pad_to ? d->n : d->zero_pad_to;
   const long long rows = (long long)d->n0 * d->H * d->S;
   cudaStream_t st = ST(stream);
+  const bool vec_ok = span > 1024 && span <= 2304 && (span & 7) == 0 && d->zero_pad_to >= d->n &&
+                      ((d->p_s0 | d->p_s1 | d->p_s2 | d->ds_s0 | d->ds_s1 | d->ds_s2) & 7) == 0 &&
+                      ((d->dp_s0 | d->dp_s1 | d->dp_s2) & 3) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dP) & 15) == 0 && (reinterpret_cast<uintptr_t>(dS) & 15) == 0;
+  if (vec_ok) {
+    softmax_bwd_warp_vec_kernel<9><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+    U2_CHECK_LAUNCH("softmax_bwd");
+    return U2_OK;
+  }
 #define U2_SB_CASE(G, MV)                                                                        \
   softmax_bwd_kernel<G, MV><<<(unsigned)((rows + ((G) == 32 ? 4 : 1) - 1) / ((G) == 32 ? 4 : 1)), \
                               (G) == 32 ? 128 : (G), 0, st>>>(a)
