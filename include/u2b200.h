@@ -42,6 +42,10 @@ extern "C" {
 #define U2_ACT_GELU 1 /* exact erf GELU (torch.nn.GELU default) */
 #define U2_ACT_SILU 2
 
+#define U2_EPI_NONE 0
+#define U2_EPI_EXP_ROW 1
+#define U2_EPI_DS_ROW 2
+
 /* Library / device info ----------------------------------------------------------------------- */
 U2_API int u2_version(void);                 /* ABI version, currently 1 */
 U2_API const char* u2_last_error(void);      /* message of the last failing call on this thread */
@@ -81,6 +85,15 @@ typedef struct u2_gemm_desc {
    * [K][M] (element (m, k) at A[k * lda + m]); b_mn != 0 -> B is stored [K][N]. lda / ldb are then the strides
    * between consecutive contraction indices. No transposed copy is made: the tile is loaded MN-major. */
   int32_t a_mn, b_mn;
+  /* fused epilogue of the attention backward (applied after alpha, before bias / act / residual; rowvec is indexed
+   * rowvec[zo * rv_stride_zo + zi * rv_stride_zi + row]):
+   *   U2_EPI_EXP_ROW:  v = exp(v - rowvec[row])             P = exp(scale * q.k - lse) straight out of the score GEMM
+   *   U2_EPI_DS_ROW:   v = mul[row, col] * (v - rowvec[row]) dS = P * (dO.V^T - rowsum(dO * O)); mul (bf16) has C's
+   *                                                          layout (ldc, c_stride_*) and may BE C (in place) */
+  int32_t epi_op;
+  const float* rowvec;
+  int64_t rv_stride_zi, rv_stride_zo;
+  const void* mul;
 } u2_gemm_desc;
 
 U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const u2_gemm_desc* desc, void* stream);
@@ -312,6 +325,8 @@ typedef struct u2_fa_desc {
   int64_t k_sb, k_ss, k_sh;
   int64_t vt_sb, vt_sh, vt_sd;
   int64_t out_sb, out_ss;
+  float* lse; /* optional fp32 [B, H, Sq]: log-sum-exp of the scaled score rows (training: the backward rebuilds the
+                 probabilities as exp(scale * q.k - lse) in the score GEMM's epilogue); NULL at inference */
 } u2_fa_desc;
 U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* vt, void* out, const u2_fa_desc* desc,
                                        void* stream);

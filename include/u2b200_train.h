@@ -66,6 +66,12 @@ U2_API int u2_softmax_bwd_bf16(const void* P, const float* dP, void* dS, const u
 U2_API int u2_relbias_grad_bf16(const void* dS, float* drel, int32_t n0, int32_t H, int32_t S, int32_t n, int64_t s0,
                                 int64_t s1, int64_t s2, int32_t rel_max, void* stream);
 
+/* out[b, h, s] = sum_d a[b, s, h, d] * c[b, s, h, d] (bf16 views with element strides *_sb batch, *_ss token, *_sh head;
+ * out fp32 [B, H, S]): D = rowsum(dO * O), the term that turns dP into dS without the probabilities' row sums. */
+U2_API int u2_rowdot_bf16(const void* a, const void* c, float* out, int32_t B, int32_t S, int32_t H, int32_t dh,
+                          int64_t a_sb, int64_t a_ss, int64_t a_sh, int64_t c_sb, int64_t c_ss, int64_t c_sh,
+                          void* stream);
+
 /* Backward of u2_temporal_attention_bf16 (svr.py:33-36 over rma.py:60-73): recomputes the C x C probabilities of
  * every (batch, token, head) from qkv, then dqkv (same layout as qkv: [q|k|v] columns) from dout; drel (fp32
  * [2*rel_max-1, H], may be NULL) accumulates the relative-bias gradient. C <= 128. */

@@ -80,6 +80,42 @@ def test_gemm_transposed_batched_accumulate():
     close(out, ref, 2e-2, "batched P^T dO accumulate")
 
 
+def test_flash_lse_and_fused_attention_backward_epilogues():
+    """The ViT attention backward without fp32 score / dP round trips: LSE out of the fused forward, P rebuilt in the score
+    GEMM's epilogue, dS formed in the dP GEMM's epilogue (in place) - against explicit fp32 attention."""
+    ops, T = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    b, S, h, dh = 2, 300, 3, 64
+    Skp = (S + 7) // 8 * 8
+    qkv = torch.randn(b, S, 3, h, dh, device="cuda", generator=g).to(BF)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    do = torch.randn(b, S, h, dh, device="cuda", generator=g).to(BF)
+    scale = dh ** -0.5
+    sc = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+    P = torch.softmax(sc, -1)
+    O = torch.einsum("bhqk,bkhd->bqhd", P, v.float())
+    vt = torch.empty(b, h, dh, Skp, device="cuda", dtype=BF)
+    ops.transpose_heads(v, vt, B=b, S=S, H=h, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
+                        out_strides=(h * dh * Skp, dh * Skp), ld_out=Skp)
+    out = torch.empty(b, S, h * dh, device="cuda", dtype=BF)
+    lse = torch.empty(b, h, S, device="cuda")
+    ops.flash_attention_d64(q, k, vt, out, scale, lse=lse)
+    close(out.view(b, S, h, dh), O, 2e-2, "flash out")
+    assert float((lse - torch.logsumexp(sc, -1)).abs().max()) < 2e-2
+    pr = torch.empty(b, h, S, Skp, device="cuda", dtype=BF)
+    ops.gemm(q, k, pr, M=S, N=S, K=dh, lda=q.stride(1), ldb=k.stride(1), ldc=Skp, zi=h, zo=b, a_strides=(q.stride(2), q.stride(0)),
+             b_strides=(k.stride(2), k.stride(0)), c_strides=(S * Skp, h * S * Skp), alpha=scale, epi_op=1, rowvec=lse,
+             rv_strides=(S, h * S))
+    close(pr[..., :S], P, 2e-2, "P from the score GEMM epilogue")
+    D = T.rowdot(do, out.view(b, S, h, dh))
+    close(D, (do.float() * O).sum(-1).permute(0, 2, 1), 2e-2, "rowdot")
+    dP = torch.einsum("bqhd,bkhd->bhqk", do.float(), v.float())
+    dS = P * (dP - (dP * P).sum(-1, keepdim=True))
+    ops.gemm(do, v, pr, M=S, N=S, K=dh, lda=do.stride(1), ldb=v.stride(1), ldc=Skp, zi=h, zo=b, a_strides=(do.stride(2), do.stride(0)),
+             b_strides=(v.stride(2), v.stride(0)), c_strides=(S * Skp, h * S * Skp), epi_op=2, rowvec=D, rv_strides=(S, h * S), mul=pr)
+    close(pr[..., :S], dS, 3e-2, "dS from the dP GEMM epilogue (in place)")
+
+
 def test_linear_dgrad_wgrad():
     ops, T = _ops()
     g = torch.Generator(device="cuda").manual_seed(2)

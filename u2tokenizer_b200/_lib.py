@@ -29,6 +29,10 @@ class GemmDesc(C.Structure):
         ("row_div", C.c_int32), ("row_stride", C.c_int32), ("row_off", C.c_int32),
         ("block_n", C.c_int32),
         ("a_mn", C.c_int32), ("b_mn", C.c_int32),
+        ("epi_op", C.c_int32),
+        ("rowvec", C.c_void_p),
+        ("rv_stride_zi", C.c_int64), ("rv_stride_zo", C.c_int64),
+        ("mul", C.c_void_p),
     ]
 
 
@@ -132,6 +136,7 @@ class FaDesc(C.Structure):
         ("k_sb", C.c_int64), ("k_ss", C.c_int64), ("k_sh", C.c_int64),
         ("vt_sb", C.c_int64), ("vt_sh", C.c_int64), ("vt_sd", C.c_int64),
         ("out_sb", C.c_int64), ("out_ss", C.c_int64),
+        ("lse", C.c_void_p),
     ]
 
 
@@ -228,6 +233,7 @@ SIGNATURES = {
     "u2_rmsnorm_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _L, _L, _L, _L, _F, _P]),
     "u2_softmax_bwd_bf16": (C.c_int, [_P, _P, _P, C.POINTER(SoftmaxBwdDesc), _P]),
     "u2_relbias_grad_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _P]),
+    "u2_rowdot_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
     "u2_temporal_attention_bwd_bf16": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _F, _P, _P, _I, _P]),
     "u2_rope_bwd_bf16": (C.c_int, [_P, _P, C.POINTER(RopeDesc), _P, _P, _P]),
     "u2_spp_pool_bwd_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),

@@ -41,6 +41,8 @@ struct FaArgs {
   float scale_log2e;       // softmax scale * log2(e)
   __nv_bfloat16* out;      // [b][s][h*64 + d]
   long long out_sb, out_ss;  // element strides of batch and token
+  float* lse;              // optional [b][h][Sq]: log-sum-exp of the scaled scores (the attention backward rebuilds P from it)
+  int H;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -251,6 +253,7 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int row = q0 + r;
     if (row < p.Sq) {
       const float inv = 1.f / l;
+      if (p.lse) p.lse[((long long)b * p.H + h) * p.Sq + row] = (m + log2f(l)) * 0.6931471805599453f;
       __nv_bfloat16* dst = p.out + (long long)b * p.out_sb + (long long)row * p.out_ss + h * kFaDh;
 #pragma unroll
       for (int d = 0; d < kFaDh; d += 8) {
@@ -482,6 +485,7 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       const int row = q0 + t * kFaBM + r;
       if (row < p.Sq) {
         const float inv = 1.f / l;
+        if (p.lse) p.lse[((long long)b * p.H + h) * p.Sq + row] = (m + log2f(l)) * 0.6931471805599453f;
         __nv_bfloat16* dst = p.out + (long long)b * p.out_sb + (long long)row * p.out_ss + h * kFaDh;
 #pragma unroll
         for (int d = 0; d < kFaDh; d += 8) {
@@ -534,6 +538,7 @@ extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, 
   a.scale_log2e = d->scale * 1.4426950408889634f;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.out_sb = d->out_sb; a.out_ss = d->out_ss;
+  a.lse = d->lse; a.H = d->H;
   const bool two_tiles = d->Sq > kFaBM && !getenv("U2_FA_V1");
   if (two_tiles) {
     static bool configured2 = false;

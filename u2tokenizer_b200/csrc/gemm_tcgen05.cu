@@ -57,6 +57,10 @@ struct GemmDev {
   int res_row_mod;
   int row_div, row_stride, row_off;
   void* C;
+  int epi_op;                 // U2_EPI_*
+  const float* rowvec;
+  long long rv_zi, rv_zo;
+  const __nv_bfloat16* mul;
   // kMode 1 (fused lm_head + log-softmax statistics): nothing of the N-wide result is stored
   const long long* labels;  // [M], label column per row (< 0: none)
   float4* part;             // [2 * num_n_blocks][part_ld]: (running max, sum exp(x - max), sum x, -) per row and half tile
@@ -304,6 +308,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (row_ok && p.epi_op != U2_EPI_NONE) {
+          // attention backward: probabilities rebuilt from the row log-sum-exp / dS formed against the stored P
+          const float rv = __ldg(p.rowvec + (long long)zo_i * p.rv_zo + (long long)zi_i * p.rv_zi + row);
+          if (p.epi_op == U2_EPI_EXP_ROW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - rv);
+          } else {
+            const __nv_bfloat16* mp = p.mul + c_off + col0;
+            if ((col0 + 32 <= p.N) && (((p.ldc | zoff) & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r = *reinterpret_cast<const uint4*>(mp + j);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rf = __bfloat1622float2(r2[e]);
+                  f[j + 2 * e] = rf.x * (f[j + 2 * e] - rv);
+                  f[j + 2 * e + 1] = rf.y * (f[j + 2 * e + 1] - rv);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                f[j] = (col0 + j < p.N) ? __bfloat162float(mp[j]) * (f[j] - rv) : 0.f;
+            }
+          }
+        }
         if (row_ok) {
           const bool full = (col0 + 32 <= p.N);
           if (p.bias) {
@@ -589,6 +620,14 @@ extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const 
   p.res_row_mod = d->res_row_mod;
   p.row_div = d->row_div; p.row_stride = d->row_stride; p.row_off = d->row_off;
   p.C = C;
+  p.epi_op = d->epi_op;
+  p.rowvec = d->rowvec; p.rv_zi = d->rv_stride_zi; p.rv_zo = d->rv_stride_zo;
+  p.mul = reinterpret_cast<const __nv_bfloat16*>(d->mul);
+  if (p.epi_op != U2_EPI_NONE) {
+    if (!p.rowvec) return set_error(U2_ERR_ARG, "gemm: the fused attention epilogue needs rowvec");
+    if (p.epi_op == U2_EPI_DS_ROW && (!p.mul || d->c_dtype != U2_DT_BF16)) return set_error(U2_ERR_ARG, "gemm: U2_EPI_DS_ROW needs mul and a bf16 C");
+    if (p.row_div > 0) return set_error(U2_ERR_ARG, "gemm: the fused attention epilogue does not combine with row remapping");
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 #define U2_GEMM_BN(MAJ)                                                    \
   switch (block_n) {                                                      \

@@ -451,6 +451,31 @@ relbias_grad_kernel(const __nv_bfloat16* __restrict__ dS, float* __restrict__ dr
 }
 
 // ------------------------------------------------------------------------------------------------
+// D[b, h, s] = sum_d a[b, s, h, d] * c[b, s, h, d]  (rowsum(dO * O) of the attention backward); warp per (b, s, h)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ c, float* __restrict__ out, int B, int S,
+              int H, int dh, long long a_sb, long long a_ss, long long a_sh, long long c_sb, long long c_ss, long long c_sh) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * S * H;
+  for (long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); item < total; item += (long long)gridDim.x * 8) {
+    const int h = (int)(item % H);
+    const int s = (int)((item / H) % S);
+    const long long b = item / ((long long)H * S);
+    const __nv_bfloat16* pa = a + b * a_sb + s * a_ss + h * a_sh;
+    const __nv_bfloat16* pc = c + b * c_sb + s * c_ss + h * c_sh;
+    float d = 0.f;
+    for (int e = lane * 2; e < dh; e += 64) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + e));
+      const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pc + e));
+      d += x.x * y.x + x.y * y.y;
+    }
+    d = t_wsum(d);
+    if (lane == 0) out[(b * H + h) * S + s] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // temporal attention backward: one CTA per (head, token, batch); everything of the C x C problem in smem
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -1167,6 +1192,19 @@ extern "C" U2_API int u2_relbias_grad_bf16(const void* dS, float* drel, int32_t 
   relbias_grad_kernel<<<dim3((unsigned)H, (unsigned)n0), 256, (size_t)(S + n) * sizeof(float), ST(stream)>>>(
       CBF(dS), drel, H, S, n, s0, s1, s2, rel_max);
   U2_CHECK_LAUNCH("relbias_grad");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_rowdot_bf16(const void* a, const void* c, float* out, int32_t B, int32_t S, int32_t H, int32_t dh,
+                                     int64_t a_sb, int64_t a_ss, int64_t a_sh, int64_t c_sb, int64_t c_ss, int64_t c_sh,
+                                     void* stream) {
+  if (!a || !c || !out) return set_error(U2_ERR_ARG, "rowdot: null pointer");
+  if ((dh & 1) || ((a_sb | a_ss | a_sh | c_sb | c_ss | c_sh) & 1)) return set_error(U2_ERR_ARG, "rowdot: dh / strides must be even");
+  if (B <= 0 || S <= 0 || H <= 0) return U2_OK;
+  long long blocks = ((long long)B * S * H + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  rowdot_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(CBF(a), CBF(c), out, B, S, H, dh, a_sb, a_ss, a_sh, c_sb, c_ss, c_sh);
+  U2_CHECK_LAUNCH("rowdot");
   return U2_OK;
 }
 

@@ -40,7 +40,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K
          a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0),
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, ldr: int = 0, res_row_mod: int = 0,
-         row_remap=(0, 0, 0), block_n: int = 0, a_mn: bool = False, b_mn: bool = False) -> torch.Tensor:
+         row_remap=(0, 0, 0), block_n: int = 0, a_mn: bool = False, b_mn: bool = False,
+         epi_op: int = 0, rowvec: Optional[torch.Tensor] = None, rv_strides=(0, 0),
+         mul: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw (batched, strided) GEMM: C[z] = act(alpha * A[z] @ B[z']^T + bias) + residual.
     a_mn / b_mn: the operand is stored transposed ([K][M] / [K][N], lda / ldb = stride between contraction indices)."""
     _need_cuda(a, b, c, bias, residual)
@@ -68,6 +70,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K
     d.row_div, d.row_stride, d.row_off = row_remap
     d.block_n = block_n
     d.a_mn, d.b_mn = int(a_mn), int(b_mn)
+    _need_cuda(rowvec, mul)
+    d.epi_op = int(epi_op)  # 1: exp(v - rowvec[row]); 2: mul * (v - rowvec[row])   (attention backward, see u2b200.h)
+    d.rowvec = _ptr(rowvec)
+    d.rv_stride_zi, d.rv_stride_zo = rv_strides
+    d.mul = _ptr(mul)
     lib = _lib.load()
     _lib.check(lib.u2_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), C.byref(d), _stream()),
                "u2_gemm_bf16")
@@ -443,7 +450,8 @@ def topk_rows(scores: torch.Tensor, k: int, idx_offset_per_row: int = 0) -> torc
     return out
 
 
-def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, scale: float):
+def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, scale: float,
+                        lse: Optional[torch.Tensor] = None):
     """Fused non-causal attention for head_dim 64: q [B,Sq,H,64], k [B,Sk,H,64] (strided views, d contiguous),
     vt [B,H,64,Sk_pad] (token axis contiguous), out [B,Sq,H*64] view."""
     _need_cuda(q, k, vt, out)
@@ -457,6 +465,10 @@ def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out:
     d.k_sb, d.k_ss, d.k_sh = k.stride(0), k.stride(1), k.stride(2)
     d.vt_sb, d.vt_sh, d.vt_sd = vt.stride(0), vt.stride(1), vt.stride(2)
     d.out_sb, d.out_ss = out.stride(0), out.stride(1)
+    _need_cuda(lse)
+    if lse is not None and (lse.dtype != F32 or not lse.is_contiguous() or lse.numel() != B * H * Sq):
+        raise ValueError("flash_attention_d64: lse must be contiguous fp32 [B, H, Sq]")
+    d.lse = _ptr(lse)
     _lib.check(_lib.load().u2_flash_attention_d64_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(),
                                                        C.byref(d), _stream()), "u2_flash_attention_d64_bf16")
     return out

@@ -384,7 +384,9 @@ class TrainEngine:
             vt = torch.empty(b, hk, dh, Skp, device=dev, dtype=BF16)
             ops.transpose_heads(v, vt, B=b, S=Sk, H=hk, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
                                 out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
-            ops.flash_attention_d64(q, k, vt, ctx, scale)
+            lse = torch.empty(b, h, Sq, device=dev, dtype=F32)
+            ops.flash_attention_d64(q, k, vt, ctx, scale, lse=lse)
+            saved["lse"] = lse
             del vt
         else:
             pr0 = probs()
@@ -403,7 +405,14 @@ class TrainEngine:
                 return
             do = out.g[:, :Sq].view(b, Sq, h, dh)
             pr = saved.pop("p", None)
-            if pr is None:
+            lse = saved.pop("lse", None)
+            if pr is None and lse is not None:
+                # P = exp(scale * q.k - lse) straight out of the score GEMM's epilogue (bf16): no fp32 score round trip
+                pr = torch.empty(b, h, Sq, Skp, device=dev, dtype=BF16)
+                ops.gemm(q, k, pr, M=Sq, N=Sk, K=dh, lda=q.stride(1), ldb=k.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
+                         a_strides=(q.stride(2), q.stride(0)), b_strides=(k.stride(2), k.stride(0)),
+                         c_strides=(Sq * Skp, h * Sq * Skp), alpha=scale, epi_op=1, rowvec=lse, rv_strides=(Sq, h * Sq))
+            elif pr is None:
                 pr = probs()
             # gradient buffers of the operands (first writer allocates; later consumers accumulate)
             fresh = {}
@@ -413,19 +422,27 @@ class TrainEngine:
                     if var.g is None:
                         # rows outside the views (ViT padding rows) must read as zero downstream
                         var.g = torch.zeros_like(var.v)
-            dP = torch.empty(b, h, Sq, Skp, device=dev, dtype=F32)
-            # dP = dO @ V^T
-            ops.gemm(do, v, dP, M=Sq, N=Sk, K=dh, lda=do.stride(1), ldb=v.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
-                     a_strides=(do.stride(2), do.stride(0)), b_strides=(v.stride(2), v.stride(0)),
-                     c_strides=(Sq * Skp, h * Sq * Skp))
             # dV = P^T @ dO   (per query head, summed over the group for GQA)
             if vv.ng:
                 dv = v_view(vv.g)
                 self._pt_gemm(pr, do, dv, b, h, hk, Sq, Sk, Skp, dh, 1.0, accumulate=not fresh[id(vv)])
-            # dS = P * (dP - sum(dP * P)) in place of P
-            T.softmax_bwd(pr, dP, pr, n0=b, H=h, S=Sq, n=Sk, p_strides=(h * Sq * Skp, Sq * Skp, Skp),
-                          dp_strides=(h * Sq * Skp, Sq * Skp, Skp), ds_strides=(h * Sq * Skp, Sq * Skp, Skp), zero_pad_to=Skp)
-            del dP
+            if lse is not None:
+                # dS = P * (dO.V^T - D), D = rowsum(dO * O): formed in the dP GEMM's epilogue, in place of P (bf16)
+                D = T.rowdot(do, out.v[:, :Sq].view(b, Sq, h, dh))
+                ops.gemm(do, v, pr, M=Sq, N=Sk, K=dh, lda=do.stride(1), ldb=v.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
+                         a_strides=(do.stride(2), do.stride(0)), b_strides=(v.stride(2), v.stride(0)),
+                         c_strides=(Sq * Skp, h * Sq * Skp), epi_op=2, rowvec=D, rv_strides=(Sq, h * Sq), mul=pr)
+            else:
+                dP = torch.empty(b, h, Sq, Skp, device=dev, dtype=F32)
+                # dP = dO @ V^T
+                ops.gemm(do, v, dP, M=Sq, N=Sk, K=dh, lda=do.stride(1), ldb=v.stride(1), ldc=Skp, zi=h, zo=b, b_zi_div=G,
+                         a_strides=(do.stride(2), do.stride(0)), b_strides=(v.stride(2), v.stride(0)),
+                         c_strides=(Sq * Skp, h * Sq * Skp))
+                # dS = P * (dP - sum(dP * P)) in place of P
+                T.softmax_bwd(pr, dP, pr, n0=b, H=h, S=Sq, n=Sk, p_strides=(h * Sq * Skp, Sq * Skp, Skp),
+                              dp_strides=(h * Sq * Skp, Sq * Skp, Skp), ds_strides=(h * Sq * Skp, Sq * Skp, Skp),
+                              zero_pad_to=Skp)
+                del dP
             if tr_rel:
                 T.relbias_grad(pr, self.gv(rel_name), n0=b, H=h, S=Sq, n=Sk, strides=(h * Sq * Skp, Sq * Skp, Skp), rel_max=REL_MAX)
             # dQ = scale * dS @ K

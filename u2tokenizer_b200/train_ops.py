@@ -132,6 +132,17 @@ def relbias_grad(dS: torch.Tensor, drel: torch.Tensor, *, n0: int, H: int, S: in
     return drel
 
 
+def rowdot(a: torch.Tensor, c: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a, c bf16 views [B, S, H, dh] (dh contiguous) -> fp32 [B, H, S] of sum_d a * c."""
+    _need_cuda(a, c, out)
+    B, S, H, dh = a.shape
+    if out is None:
+        out = torch.empty(B, H, S, device=a.device, dtype=F32)
+    _lib.check(_lib.load().u2_rowdot_bf16(a.data_ptr(), c.data_ptr(), out.data_ptr(), B, S, H, dh, a.stride(0), a.stride(1),
+                                          a.stride(2), c.stride(0), c.stride(1), c.stride(2), _stream()), "u2_rowdot_bf16")
+    return out
+
+
 def temporal_attention_bwd(qkv, dout, dqkv, *, B, C_, N, H, dh, scale, rel_bias=None, drel=None, rel_max=512):
     _need_cuda(qkv, dout, dqkv, rel_bias, drel)
     _lib.check(_lib.load().u2_temporal_attention_bwd_bf16(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, C_, N, H, dh,
