@@ -67,6 +67,12 @@ def make_geometry(workload: str):
                             vit_hidden_size=128, vit_mlp_dim=256, vit_num_layers=2, vit_num_heads=2, u2t_num_layers=2,
                             u2t_top_k=16, num_3d_query_token=16, tie_word_embeddings=False)
         spec = dict(model="tiny", batch=2, frames=2, new_tokens=0, n_question=8, lt=16, seq=48, mode="train")
+    elif workload == "tiny_dpo":
+        cfg = U2Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                            num_key_value_heads=2, head_dim=64, vocab_size=1024, image_size=[16, 64, 64],
+                            vit_hidden_size=128, vit_mlp_dim=256, vit_num_layers=2, vit_num_heads=2, u2t_num_layers=2,
+                            u2t_top_k=16, num_3d_query_token=16, tie_word_embeddings=False)
+        spec = dict(model="tiny", batch=2, frames=2, new_tokens=0, n_question=8, lt=16, seq=48, mode="dpo")
     elif workload == "tiny":  # plumbing check only
         cfg = U2Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
                             num_key_value_heads=2, head_dim=64, vocab_size=1024, image_size=[16, 64, 64],
