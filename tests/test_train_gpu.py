@@ -558,3 +558,51 @@ def test_train_step_zero1_single_gpu_matches_torch_adamw():
         assert float((te.opt["v_master"] - ref_v.data).abs().max()) < 2e-5, it
         close(te.W[:L.mat_total], ref_m.data, 1e-2, "bf16 params after the step")
     assert losses[2] < losses[0], losses
+
+
+def test_dpo_step_matches_oracle_autograd():
+    """Policy side of the stage-2 DPO step (reference dpo_u2trainer.py:185-359 + trl's sigmoid loss, beta 0.1): loss,
+    reward statistics and every parameter gradient against autograd through the oracle's forward, selective log-softmax
+    and -logsigmoid(beta * ((pc - pr) - (rc - rr)))."""
+    from u2tokenizer_b200.train import TrainEngine
+    g = tiny_geometry()
+    sd16 = synthetic_state_dict(g, seed=31, device="cpu", dtype=BF)
+    sd16["model.u2tokenizer.query_tokens"] = (sd16["model.u2tokenizer.query_tokens"].float() * 50).to(BF)
+    images, ids, qids = synthetic_inputs(g, batch=1, frames=2, n_question=6, lt=10)
+    gen = torch.Generator().manual_seed(3)
+    n_prompt = ids.shape[1]
+    ans = torch.randint(1, g.vocab_size - 16, (2, 9), generator=gen)          # chosen / rejected completions
+    ids2 = torch.cat([ids.expand(2, -1), ans], 1)
+    images2, qids2 = images.expand(2, *images.shape[1:]).contiguous(), qids.expand(2, -1).contiguous()
+    mask = torch.zeros_like(ids2)
+    mask[:, n_prompt:] = 1
+    mask[1, -2:] = 0                                                           # a shorter rejected completion
+    ref_logps = torch.tensor([-30.0, -28.5])
+    beta = 0.1
+    sd = {k: v.float().cuda().requires_grad_(True) for k, v in sd16.items()}
+    logits = O.forward_logits(sd, ids2.cuda(), images2.cuda(), qids2.cuda(), g)
+    ptl, allp, _ = O.dpo_per_token_logps(logits, ids2.cuda(), mask.cuda())
+    x = beta * ((allp[0] - allp[1]) - (ref_logps[0] - ref_logps[1]).cuda())
+    loss = -F.logsigmoid(x)
+    loss.backward()
+    te = TrainEngine(g, sd16, device="cuda")
+    te.zero_grad()
+    st = te.dpo_forward_backward(images2.cuda(), ids2.cuda(), qids2.cuda(), mask.cuda(), ref_logps.cuda(), beta)
+    torch.cuda.synchronize()
+    assert abs(float(st[0]) - float(loss)) < 2e-2 * max(1.0, float(loss)), (st, float(loss))
+    seq = te.sequence_logps(images2.cuda(), ids2.cuda(), qids2.cuda(), mask.cuda())
+    close(seq, allp.detach(), 2e-2, "summed sequence log-probabilities")
+    L = te.lay
+    gmax = max(v.grad.abs().max().item() for v in sd.values() if v.grad is not None)
+    bad = []
+    for n in L.mat_names + L.vec_names:
+        want = sd[n].grad
+        if want is None or want.abs().max().item() < 1e-9:
+            continue
+        got = (te.Gm[L.mat_off[n]:L.mat_off[n] + L._numel(n)] if n in L.mat_off else te.Gv[L.vec_off[n]:L.vec_off[n] + L._numel(n)])
+        got = got.view(L.shapes[n]).float().cpu()
+        want = want.cpu()
+        e, c = rel_err(got, want), cosine(got, want)
+        if not (e < 4e-2 and c > 0.995) and (got - want).abs().max().item() >= 2e-3 * gmax:
+            bad.append((n, round(e, 4), round(c, 5)))
+    assert not bad, bad[:6]
