@@ -37,6 +37,7 @@ def main():
         te.zero_grad()
         losses.append(float(te.forward_backward(*batch_for(g, rank)[:3], batch_for(g, rank)[3])))
         te.optimizer_step()
+    te.sync_params()
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
@@ -86,7 +87,7 @@ def main():
                 print(f"   bucket {i}: {int(good.sum())}/{n} agree; rank-0 slice holds {names}; "
                       f"|d_mine| {d_mine.abs().max().item():.3g} |d_ref| {d_ref.abs().max().item():.3g}", flush=True)
         frac = agree / max(tot, 1)
-        ok = frac > 0.995 and tot > 0.5 * used / world
+        ok = frac > 0.995 and tot > 0.25 * used / world
         print(f"ZERO1 world={world} buckets={te.lay.n_buckets} overlap={te.overlap} losses={losses} "
               f"max|dW|={dw:.3g} (max|W| {scale:.3g}) max|dV|={dv:.3g}; rank-0 master displacement agrees on "
               f"{frac:.3%} of the {tot} elements with a significant gradient -> {'OK' if ok else 'MISMATCH'}", flush=True)

@@ -151,6 +151,7 @@ class TrainEngine:
         self.overlap = world_size > 1
         self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         self._pending = None
+        self._ag_ev = [None] * self.lay.n_buckets   # all-gather completion events of the previous optimizer step
 
     # =========================================================================================
     # flat-buffer views
@@ -239,10 +240,29 @@ class TrainEngine:
     def _tr(self, group: str) -> bool:
         return bool(self.trainable.get(group, True))
 
+    def _wait_params(self, names: Sequence[str]):
+        """The previous step's parameter all-gather runs on the communication stream, bucket by bucket in forward order,
+        while this step's forward is already under way: before a segment first reads its weights, make the compute stream
+        wait for the buckets that hold them."""
+        for n in names:
+            for b in self.lay.name_buckets.get(n, ()):
+                ev = self._ag_ev[b]
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                    self._ag_ev[b] = None
+
+    def sync_params(self):
+        """Wait for every outstanding parameter all-gather (before anything outside the training forward reads W)."""
+        for b, ev in enumerate(self._ag_ev):
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+                self._ag_ev[b] = None
+
     def _mark(self, names: Sequence[str]):
         """Placed on the tape BEFORE the ops of a segment: in the reversed (backward) order it runs right after the
         segment's last gradient kernel has been issued, i.e. when the gradients of `names` are final."""
         names = [n for n in names if n in self.lay.mat_off]
+        self._wait_params(names)
 
         def done():
             if self._pending is None:
@@ -495,6 +515,7 @@ class TrainEngine:
         v = "model.vision_tower.vision_tower."
         vol = frames.to(device=self.dev, dtype=F32).contiguous().view(Fr, *g.image_size)
         rows = ops.patchify(vol, g.patch_size)
+        self._wait_params([v + "patch_embedding.patch_embeddings.1.weight"])
         pe_w, pe_b = self.w(v + "patch_embedding.patch_embeddings.1.weight"), self.v32(v + "patch_embedding.patch_embeddings.1.bias")
         pos = self.w(v + "patch_embedding.position_embeddings").view(P, Hd)
         x0 = torch.zeros(Fr, Sp, Hd, device=self.dev, dtype=BF16)
@@ -1101,6 +1122,7 @@ class TrainEngine:
         o["step"] += 1
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.sync_params()
         if W_ > 1:
             self.Gv.mul_(1.0 / W_)  # a few MB of fp32: plumbing of the collective (mean), not hot-path arithmetic
             dist.all_reduce(self.Gv, group=self.group)
@@ -1124,13 +1146,23 @@ class TrainEngine:
             sl = slice(i * pc, (i + 1) * pc)
             T.adamw(o["m_master"][sl], o["m_m"][sl], o["m_v"][sl], self._grad_piece(i), self.W[lo:lo + pc], **kw)
             if W_ > 1:
-                dist.all_gather_into_tensor(self.W[i * L.bucket:(i + 1) * L.bucket], self.W[lo:lo + pc], group=self.group)
+                # all-gather of the updated slice on the communication stream: it overlaps the remaining AdamW launches and
+                # the NEXT step's forward, which waits per bucket (_wait_params) right before a segment reads its weights
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    dist.all_gather_into_tensor(self.W[i * L.bucket:(i + 1) * L.bucket], self.W[lo:lo + pc], group=self.group)
+                    done = torch.cuda.Event()
+                    done.record(self.comm_stream)
+                self._ag_ev[i] = done
         T.adamw(o["v_master"], o["v_m"], o["v_v"], self.Gv, self.W[L.mat_total:], param_out_f32=self.V32, **kw)
         o["reduced"] = [False] * nb
 
     def grads_for_module(self, model) -> None:
         """p.grad views for the HF-style module (matrix grads alias Gm; vector grads are cast to bf16)."""
         L = self.lay
+        self.sync_params()
         gvb = torch.empty(L.vec_total, device=self.dev, dtype=BF16)
         T.cast(self.Gv, gvb)
         for n, p in model.named_parameters():
