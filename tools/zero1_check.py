@@ -61,36 +61,40 @@ def main():
         # per element) must agree - a mis-routed bucket would show up as displacements that differ by O(lr)
         lr = te.opt["lr"]
         L = te.lay
-        agree = tot = 0
-        for i in range(L.n_buckets):
-            lo = i * L.bucket
-            n = min(L.piece, max(0, used - lo))
-            if n <= 0:
-                continue
-            mine = te.opt["m_master"][i * L.piece:i * L.piece + n]
-            theirs = ref.opt["m_master"][lo:lo + n]
-            if i == 0:  # flat start values through the layout (8-aligned slots)
-                start = torch.zeros(L.mat_total, device="cuda")
-                for k in L.mat_names:
-                    start[L.mat_off[k]:L.mat_off[k] + L._numel(k)] = sd[k].float().flatten().cuda()
-            d_mine, d_ref = mine - start[lo:lo + n], theirs - start[lo:lo + n]
-            # elements whose gradient is above the noise floor moved ~lr in the same direction in both steps; the others
-            # (k-projection weights behind a nearly uniform softmax, ...) carry cancellation noise of the order of Adam's
-            # eps, where the update is not a stable function of the gradient in ANY implementation
-            sig = d_ref.abs() >= 1.5 * lr
-            good = ((d_mine - d_ref).abs() < 0.25 * lr) & sig
-            agree += int(good.sum())
-            tot += int(sig.sum())
-            n = int(sig.sum())
-            if int(good.sum()) < 0.99 * n:
-                names = [k for k in L.bucket_names[i] if L.mat_off[k] < lo + n and L.mat_off[k] + L._numel(k) > lo]
-                print(f"   bucket {i}: {int(good.sum())}/{n} agree; rank-0 slice holds {names}; "
-                      f"|d_mine| {d_mine.abs().max().item():.3g} |d_ref| {d_ref.abs().max().item():.3g}", flush=True)
-        frac = agree / max(tot, 1)
-        ok = frac > 0.995 and tot > 0.25 * used / world
-        print(f"ZERO1 world={world} buckets={te.lay.n_buckets} overlap={te.overlap} losses={losses} "
-              f"max|dW|={dw:.3g} (max|W| {scale:.3g}) max|dV|={dv:.3g}; rank-0 master displacement agrees on "
-              f"{frac:.3%} of the {tot} elements with a significant gradient -> {'OK' if ok else 'MISMATCH'}", flush=True)
+        start = torch.zeros(L.mat_total, device="cuda")
+        for k in L.mat_names:
+            start[L.mat_off[k]:L.mat_off[k] + L._numel(k)] = sd[k].float().flatten().cuda()
+        # per parameter, over the part of it that rank 0 owns: elements whose gradient is above the noise floor moved ~lr per
+        # step in a consistent direction; the mu2-tokenizer's attention projections sit behind nearly uniform softmaxes in
+        # this random-init toy model, their gradients are cancellation noise of the order of Adam's eps (the update is then
+        # not a stable function of the gradient in ANY implementation) and are reported separately
+        stats = {"core": [0, 0], "u2tokenizer": [0, 0]}
+        worst = (1.0, "")
+        for k in L.mat_names:
+            p_lo, p_hi = L.mat_off[k], L.mat_off[k] + L._numel(k)
+            agree = tot = 0
+            for i in range(L.n_buckets):
+                lo = max(p_lo, i * L.bucket)
+                hi = min(p_hi, i * L.bucket + L.piece)      # rank 0 owns [i * bucket, i * bucket + piece)
+                if hi <= lo:
+                    continue
+                mine = te.opt["m_master"][i * L.piece + (lo - i * L.bucket):i * L.piece + (hi - i * L.bucket)]
+                d_mine, d_ref = mine - start[lo:hi], ref.opt["m_master"][lo:hi] - start[lo:hi]
+                sig = d_ref.abs() >= 1.5 * lr
+                agree += int((((d_mine - d_ref).abs() < 0.25 * lr) & sig).sum())
+                tot += int(sig.sum())
+            grp = "u2tokenizer" if k.startswith("model.u2tokenizer.") else "core"
+            stats[grp][0] += agree
+            stats[grp][1] += tot
+            if grp == "core" and tot > 100 and agree / tot < worst[0]:
+                worst = (agree / tot, k)
+        fc = stats["core"][0] / max(stats["core"][1], 1)
+        ft = stats["u2tokenizer"][0] / max(stats["u2tokenizer"][1], 1)
+        ok = fc > 0.998 and stats["core"][1] > 0.1 * used / world and ft > 0.9
+        print(f"ZERO1 world={world} buckets={te.lay.n_buckets} overlap={te.overlap} losses={losses} max|dW|={dw:.3g} "
+              f"max|dV|={dv:.3g}; rank-0 fp32 master displacement after 2 steps vs the single-GPU run: ViT / projector / decoder / "
+              f"embeddings {fc:.3%} of {stats['core'][1]} significant elements agree (worst parameter {worst[1]}: {worst[0]:.3%}), "
+              f"mu2-tokenizer (noise-floor gradients) {ft:.3%} of {stats['u2tokenizer'][1]} -> {'OK' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
