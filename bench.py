@@ -261,26 +261,49 @@ def extra_rooflines(model, spec, geom):
     hbm, tf, src = measured_peaks()
     out = []
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    # --- patch-embed gather: fp32 volume -> bf16 patch rows, 32 frames = 268 MB in, 134 MB out per launch
+    # --- the WHOLE 3-D patch-embedding op (97.0 MB of algorithmic traffic per 256^3 volume = fp32 volume in,
+    # bf16 tokens out, weights once; 25.8 GFLOP): brick gather + GEMM (+bias +position table, rows placed behind the cls
+    # row) + cls / padding rows, 32 frames = 4 volumes per pass, two buffer sets alternated (537 MB >> 126 MB L2)
     Fr = 32
     D0, D1, D2 = geom.image_size
+    P, Hd, pd = geom.n_patches, geom.vit_hidden, geom.patch_dim
+    S, Sp = P + 1, (P + 1 + 7) // 8 * 8
     vols = [torch.rand(Fr, D0, D1, D2, device="cuda") for _ in range(2)]
-    rows = [torch.empty(Fr * geom.n_patches, geom.patch_dim, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
-    for i in range(2):
+    rows = [torch.empty(Fr * P, pd, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    xs = [torch.empty(Fr, Sp, Hd, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+
+    def gather(i):
         ops.patchify(vols[i], geom.patch_size, out=rows[i])
-    e0, e1 = ev(), ev()
-    torch.cuda.synchronize()
-    e0.record()
-    for r in range(8):
-        ops.patchify(vols[r % 2], geom.patch_size, out=rows[r % 2])
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3 / 8
-    by = Fr * D0 * D1 * D2 * 6
-    out.append({"kernel": "patchify_tma_kernel (3-D patch-embed brick gather, fp32 volume -> bf16 patch rows)", "bound": "hbm",
-                "achieved": round(by / sec / 1e9, 1), "peak": hbm, "unit": "GB/s", "frac": round(by / sec / 1e9 / hbm, 4),
-                "bytes_per_launch": by, "us_per_launch": round(sec * 1e6, 2), "peak_source": src})
-    del vols, rows
+
+    def embed(i):
+        gather(i)
+        ops.gemm(rows[i], eng.pe_w, xs[i], M=Fr * P, N=Hd, K=pd, lda=pd, ldb=pd, ldc=Hd, bias=eng.pe_b, residual=eng.pos, ldr=Hd,
+                 res_row_mod=P, row_remap=(P, Sp, 1))
+        ops.vit_frame_rows(xs[i], eng.cls, Fr, Sp, S)
+
+    def timed_us(fn, reps=8):
+        for i in range(2):
+            fn(i)
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize()
+        e0.record()
+        for r in range(reps):
+            fn(r % 2)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+    us_op, us_gather = timed_us(embed), timed_us(gather)
+    by_op = Fr * (D0 * D1 * D2 * 4 + P * Hd * 2) + (pd * Hd + P * Hd + Hd) * 2
+    fl_op = 2.0 * Fr * P * pd * Hd
+    out.append({"kernel": "3-D patch embedding, whole op (patchify_tma_kernel + gemm_bf16_tcgen05_kernel<256> + vit_frame_rows_kernel)",
+                "bound": "hbm / tensor (arithmetic intensity 266 FLOP/B vs ridge 218)", "achieved": round(by_op / us_op / 1e3, 1),
+                "peak": hbm, "unit": "GB/s", "frac": round(by_op / us_op / 1e3 / hbm, 4), "bytes_per_launch": by_op,
+                "us_per_launch": round(us_op, 2), "tensor_achieved_tflops": round(fl_op / us_op / 1e6, 1),
+                "tensor_frac": round(fl_op / us_op / 1e6 / tf, 4), "peak_source": src,
+                "note": "algorithmic bytes = 97.0 MB per volume (SURVEY 8d): the bf16 im2col rows the unfused gather writes and the "
+                        "GEMM re-reads are NOT counted; the gather alone moves its own 100.7 MB per volume at "
+                        f"{round(Fr * D0 * D1 * D2 * 6 / us_gather / 1e3 / hbm, 3)} of the HBM peak ({round(us_gather, 1)} us)"})
+    del vols, rows, xs
     # --- decoder prefill GEMM (gate|up): M = batch * prompt rows
     M = max(spec["batch"], 1) * (geom.num_3d_query_token + spec["n_question"])
     E, I = geom.hidden_size, geom.intermediate_size

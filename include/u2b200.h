@@ -147,6 +147,10 @@ U2_API int u2_patchify_f32_bf16(const float* vol, void* rows, int64_t frames, in
 /* dst[(r * row_stride + row_off), :] = vec for r in [0, n_rows)   (cls token rows, vit.py:116-118) */
 U2_API int u2_set_rows_bf16(void* dst, const void* vec, int64_t n_rows, int64_t row_stride, int64_t row_off,
                             int32_t E, void* stream);
+/* ViT sequence buffer dst [frames][Sp][E]: row 0 of every frame = cls, rows [S, Sp) = 0 (the padding that keeps the
+ * frame stride a multiple of 16 bytes); rows 1..S-1 come from the patch-embed GEMM (vit.py:116-118 cls concat). */
+U2_API int u2_vit_frame_rows_bf16(void* dst, const void* cls, int64_t frames, int32_t Sp, int32_t S, int32_t E,
+                                  void* stream);
 /* in[b][s][h][d] (element strides in_sb, in_ss, in_sh; d contiguous) -> out[b][h][d][s] with the s axis
  * padded to ld_out (zeros): the K-major V^T operand of the PV contraction. */
 U2_API int u2_transpose_heads_bf16(const void* in, void* out, int32_t B, int32_t S, int32_t H, int32_t Dh,

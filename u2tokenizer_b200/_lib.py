@@ -202,6 +202,7 @@ SIGNATURES = {
     "u2_silu_mul_bf16": (C.c_int, [_P, _P, _L, _I, _L, _L, _I, _P]),
     "u2_patchify_f32_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "u2_set_rows_bf16": (C.c_int, [_P, _P, _L, _L, _L, _I, _P]),
+    "u2_vit_frame_rows_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _P]),
     "u2_transpose_heads_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
     "u2_spp_pool_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _L, _L, _L, _I, _P]),
     "u2_multiscale_pool_bf16": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _I, _I, _P]),

@@ -123,6 +123,23 @@ __global__ void set_rows_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bflo
   }
 }
 
+// ViT sequence buffer [frames][Sp][E]: row 0 of every frame = cls token, rows [S, Sp) (the 16-byte alignment padding) = 0.
+// One launch replaces zero-filling the whole buffer: rows 1..S-1 are written by the patch-embed GEMM's epilogue.
+__global__ void vit_frame_rows_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ cls, long long frames,
+                                      int Sp, int S, int E) {
+  const int per = 1 + (Sp - S);
+  const long long total = frames * per * E;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % E);
+    const long long t = idx / E;
+    const int k = (int)(t % per);
+    const long long f = t / per;
+    const int row = k == 0 ? 0 : S + k - 1;
+    dst[(f * Sp + row) * E + c] = k == 0 ? cls[c] : __float2bfloat16(0.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // transpose_heads: in[b][s][h][d] (strides given) -> out[b][h][d][s], s padded to ld_out.
 // 32x32 smem tiles, bf16.
@@ -389,6 +406,15 @@ extern "C" U2_API int u2_set_rows_bf16(void* dst, const void* vec, int64_t n_row
   if (n_rows <= 0 || E <= 0) return U2_OK;
   set_rows_kernel<<<grid_for(n_rows * E, 256), 256, 0, ST(stream)>>>(BF(dst), CBF(vec), n_rows, row_stride, row_off, E);
   U2_CHECK_LAUNCH("set_rows");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_vit_frame_rows_bf16(void* dst, const void* cls, int64_t frames, int32_t Sp, int32_t S, int32_t E,
+                                             void* stream) {
+  if (!dst || !cls) return set_error(U2_ERR_ARG, "vit_frame_rows: null pointer");
+  if (frames <= 0 || E <= 0 || S <= 0 || Sp < S) return set_error(U2_ERR_ARG, "vit_frame_rows: bad extents");
+  vit_frame_rows_kernel<<<grid_for(frames * (1 + Sp - S) * E, 256), 256, 0, ST(stream)>>>(BF(dst), CBF(cls), frames, Sp, S, E);
+  U2_CHECK_LAUNCH("vit_frame_rows");
   return U2_OK;
 }
 

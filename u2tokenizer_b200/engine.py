@@ -292,10 +292,10 @@ class U2Engine:
         vol = frames.to(device=self.dev, dtype=F32).contiguous().view(Fr, *g.image_size)
         # --- patch embedding: brick gather -> GEMM (+bias +position table, rows scattered behind the cls row)
         rows = ops.patchify(vol, g.patch_size)
-        x = torch.zeros(Fr, Sp, Hd, device=self.dev, dtype=BF16)
+        x = torch.empty(Fr, Sp, Hd, device=self.dev, dtype=BF16)
         ops.gemm(rows, self.pe_w, x, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd,
                  bias=self.pe_b, residual=self.pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
-        ops.set_rows(x, self.cls, Fr, Sp, 0)
+        ops.vit_frame_rows(x, self.cls, Fr, Sp, S)  # cls row + the 7 zero padding rows per frame (no full-buffer memset)
         del rows
         # --- transformer blocks
         nh = g.vit_heads

@@ -211,6 +211,14 @@ def set_rows(dst: torch.Tensor, vec: torch.Tensor, n_rows: int, row_stride: int,
     return dst
 
 
+def vit_frame_rows(dst: torch.Tensor, cls: torch.Tensor, frames: int, Sp: int, S: int):
+    """dst [frames, Sp, E]: cls row + zeroed padding rows (everything the patch-embed GEMM does not write)."""
+    _need_cuda(dst, cls)
+    _lib.check(_lib.load().u2_vit_frame_rows_bf16(dst.data_ptr(), cls.data_ptr(), frames, Sp, S, cls.numel(), _stream()),
+               "u2_vit_frame_rows_bf16")
+    return dst
+
+
 def transpose_heads(x: torch.Tensor, out: torch.Tensor, *, B: int, S: int, H: int, Dh: int,
                     in_strides, out_strides, ld_out: int):
     """in[b][s][h][d] -> out[b][h][d][s(pad ld_out)]; strides in elements: in (sb, ss, sh), out (sb, sh)."""

@@ -518,10 +518,10 @@ class TrainEngine:
         self._wait_params([v + "patch_embedding.patch_embeddings.1.weight"])
         pe_w, pe_b = self.w(v + "patch_embedding.patch_embeddings.1.weight"), self.v32(v + "patch_embedding.patch_embeddings.1.bias")
         pos = self.w(v + "patch_embedding.position_embeddings").view(P, Hd)
-        x0 = torch.zeros(Fr, Sp, Hd, device=self.dev, dtype=BF16)
+        x0 = torch.empty(Fr, Sp, Hd, device=self.dev, dtype=BF16)
         ops.gemm(rows, pe_w, x0, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd, bias=pe_b,
                  residual=pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
-        ops.set_rows(x0, self.w(v + "cls_token").view(Hd), Fr, Sp, 0)
+        ops.vit_frame_rows(x0, self.w(v + "cls_token").view(Hd), Fr, Sp, S)
         x_emb = Var(x0.view(Fr * Sp, Hd), trv)   # NOT `x`: that name is rebound by the layer loop below
         self._mark([v + "patch_embedding.patch_embeddings.1.weight"])
 
