@@ -625,6 +625,51 @@ def train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist):
     print(json.dumps(out_d), flush=True)
 
 
+def train_substep(model, rank, local_rank, world, dist, steps=3, warmup=3):
+    """cfg 4 training step (2 volumes / GPU, 512-token sequences) on the model the generate benchmark just used: its
+    parameters move into the training engine's flat buffer (no second copy), every rank joins the ZeRO-1 exchange."""
+    import gc
+    from u2tokenizer_b200 import parallel
+    cfg4, geom4, spec4 = make_geometry("cfg4")
+    model.invalidate_engine()
+    gc.collect()
+    torch.cuda.empty_cache()
+    model.train()
+    te = model.train_engine(world_size=world, rank=rank)
+    try:
+        gc.collect()
+        torch.cuda.empty_cache()
+        free, total = torch.cuda.mem_get_info()
+        mom = torch.float32 if te.lay.mat_total / world * 12 + 40e9 < free else torch.bfloat16
+        te.init_optimizer(lr=4e-6, weight_decay=0.0, max_grad_norm=1.0, moment_dtype=mom)
+        batch = train_batch(geom4, spec4, rank, world)
+        ms, launches, phases, out = run_train_steps(te, spec4, geom4, batch, steps, warmup, dist)
+        n_tok = batch[1].shape[0] * batch[1].shape[1]
+        fwd_fl, step_fl = train_flops(geom4, batch[1].shape[0], spec4["frames"], spec4["seq"], spec4["lt"])
+        hbm, tf, src = measured_peaks()
+        per = ms / steps
+        comp = per - phases["exposed_reduce_scatter"] - phases["clip_adamw"]
+        return {"workload": "cfg4: mu2-Qwen3-8B training step, 2 volumes / GPU (raw depth 64 / 128 / 256 zero-padded to 8 frames), "
+                            "512-token sequences, forward + backward + ZeRO-1 (bucketed NCCL reduce-scatter overlapped with the "
+                            "backward, sharded fused AdamW, all-gather overlapped with the next forward)",
+                "value": round(world * spec4["batch"] * steps / (ms / 1e3), 4), "unit": "volumes/s", "ms_per_step": round(per, 3),
+                "tokens_per_sec": round(world * n_tok * steps / (ms / 1e3), 1), "phases_ms": phases, "steps": steps, "warmup": warmup,
+                "gpu_launches": int(launches), "loss": float(out),
+                "optimizer": f"AdamW, ZeRO-1 over {world} rank(s), fp32 master, {str(mom).split('.')[-1]} moments, "
+                             f"{te.lay.n_buckets} buckets of {te.lay.bucket} bf16 gradients",
+                "tensor_frac_fwd_bwd": round(step_fl / (comp / 1e3) / 1e12 / tf, 4), "flops_per_step": step_fl}
+    finally:
+        te.sync_params()
+        torch.cuda.synchronize()
+        model.__dict__.pop("_u2_train_engine", None)
+        te.Gm = te.Gv = te.opt = None
+        te.tape = []
+        del te
+        model.eval()
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -733,36 +778,57 @@ def main():
     ms_e2e, _, res_h = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     n_new = int(res.shape[1]) if spec["mode"] == "generate" else 0
+    out = None
+    if rank == 0:
+        vols = world * B * args.steps
+        value = vols / (ms_dev / 1e3)
+        e2e_v = vols / (ms_e2e / 1e3)
+        out = dict(base)
+        out.update({"value": round(value, 4), "ms_per_step": round(ms_dev / args.steps, 3), "dtype": "bf16",
+                    "tokens_per_sec": round(world * B * n_new * args.steps / (ms_dev / 1e3), 2) if n_new else None,
+                    "e2e": {"value": round(e2e_v, 4), "unit": "volumes/s",
+                            "h2d_bytes_per_step": int(h_images.numel() * 4 + h_ids.numel() * 8 + h_q.numel() * 8),
+                            "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size()),
+                            "tokens_per_sec": round(world * B * n_new * args.steps / (ms_e2e / 1e3), 2) if n_new else None},
+                    "gpu_launches": int(launches), "clocks": clocks})
+        try:
+            out["roofline"] = roofline_probe(model, spec, geom)
+        except Exception as e:  # the probe must never cost the bench line
+            out["roofline"] = {"error": repr(e)}
+        try:
+            out["roofline_other_kernels"] = extra_rooflines(model, spec, geom)
+        except Exception as e:
+            out["roofline_other_kernels"] = [{"error": repr(e)}]
+        if world == 1 and os.environ.get("U2_BENCH_GPU_EAGER", "1") != "0":
+            try:
+                out["gpu_eager_baseline"] = gpu_eager_baseline(model, geom, spec, (d_images, d_ids, d_q))
+                out["gpu_eager_baseline"]["speedup_of_value"] = round(out["value"] / out["gpu_eager_baseline"]["value"], 2)
+            except Exception as e:
+                out["gpu_eager_baseline"] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    # ---- the training step of the same model on the same ranks (cfg 4: forward + backward + ZeRO-1 gradient exchange + fused
+    # AdamW) - the one place where the data-parallel job has a real collective. Every rank takes part; a watchdog makes sure
+    # that a failure in here can never cost the generate line above.
+    if args.workload == "cfg3" and os.environ.get("U2_BENCH_TRAIN", "1") != "0":
+        def bail():
+            if rank == 0 and out is not None:
+                out["train_step"] = {"error": "training sub-measurement exceeded its time limit"}
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+        wd = threading.Timer(float(os.environ.get("U2_BENCH_TRAIN_TIMEOUT", "420")), bail)
+        wd.daemon = True
+        wd.start()
+        try:
+            ts = train_substep(model, rank, local_rank, world, dist)
+        except Exception as e:
+            ts = {"error": repr(e)}
+        wd.cancel()
+        if out is not None:
+            out["train_step"] = ts
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    vols = world * B * args.steps
-    value = vols / (ms_dev / 1e3)
-    e2e_v = vols / (ms_e2e / 1e3)
-    out = dict(base)
-    out.update({"value": round(value, 4), "ms_per_step": round(ms_dev / args.steps, 3), "dtype": "bf16",
-                "tokens_per_sec": round(world * B * n_new * args.steps / (ms_dev / 1e3), 2) if n_new else None,
-                "e2e": {"value": round(e2e_v, 4), "unit": "volumes/s",
-                        "h2d_bytes_per_step": int(h_images.numel() * 4 + h_ids.numel() * 8 + h_q.numel() * 8),
-                        "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size()),
-                        "tokens_per_sec": round(world * B * n_new * args.steps / (ms_e2e / 1e3), 2) if n_new else None},
-                "gpu_launches": int(launches), "clocks": clocks})
-    try:
-        out["roofline"] = roofline_probe(model, spec, geom)
-    except Exception as e:  # the probe must never cost the bench line
-        out["roofline"] = {"error": repr(e)}
-    try:
-        out["roofline_other_kernels"] = extra_rooflines(model, spec, geom)
-    except Exception as e:
-        out["roofline_other_kernels"] = [{"error": repr(e)}]
-    if world == 1 and os.environ.get("U2_BENCH_GPU_EAGER", "1") != "0":
-        try:
-            out["gpu_eager_baseline"] = gpu_eager_baseline(model, geom, spec, (d_images, d_ids, d_q))
-            out["gpu_eager_baseline"]["speedup_of_value"] = round(out["value"] / out["gpu_eager_baseline"]["value"], 2)
-        except Exception as e:
-            out["gpu_eager_baseline"] = {"error": repr(e)}
-        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         try:
             del model
