@@ -275,10 +275,18 @@ def extra_rooflines(model, spec, geom):
     def gather(i):
         ops.patchify(vols[i], geom.patch_size, out=rows[i])
 
-    def embed(i):
+    def embed_unfused(i):
         gather(i)
         ops.gemm(rows[i], eng.pe_w, xs[i], M=Fr * P, N=Hd, K=pd, lda=pd, ldb=pd, ldc=Hd, bias=eng.pe_b, residual=eng.pos, ldr=Hd,
                  res_row_mod=P, row_remap=(P, Sp, 1))
+        ops.vit_frame_rows(xs[i], eng.cls, Fr, Sp, S)
+
+    fused = eng.fused_patch_embed and ops.patch_embed_supported(geom.image_size, geom.patch_size, Hd)
+
+    def embed(i):
+        if not fused:
+            return embed_unfused(i)
+        ops.patch_embed(vols[i], geom.patch_size, eng.pe_w, eng.pe_b, eng.pos, xs[i])
         ops.vit_frame_rows(xs[i], eng.cls, Fr, Sp, S)
 
     def timed_us(fn, reps=8):
@@ -293,16 +301,21 @@ def extra_rooflines(model, spec, geom):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / reps
     us_op, us_gather = timed_us(embed), timed_us(gather)
+    us_unfused = timed_us(embed_unfused) if fused else us_op
     by_op = Fr * (D0 * D1 * D2 * 4 + P * Hd * 2) + (pd * Hd + P * Hd + Hd) * 2
     fl_op = 2.0 * Fr * P * pd * Hd
-    out.append({"kernel": "3-D patch embedding, whole op (patchify_tma_kernel + gemm_bf16_tcgen05_kernel<256> + vit_frame_rows_kernel)",
+    out.append({"kernel": ("3-D patch embedding, whole op (patch_embed_tcgen05_kernel: 5-D TMA slabs -> in-smem fp32->bf16 A operand -> "
+                           "tcgen05, bias + position epilogue; + vit_frame_rows_kernel)") if fused else
+                          "3-D patch embedding, whole op (patchify_tma_kernel + gemm_bf16_tcgen05_kernel<256> + vit_frame_rows_kernel)",
                 "bound": "hbm / tensor (arithmetic intensity 266 FLOP/B vs ridge 218)", "achieved": round(by_op / us_op / 1e3, 1),
                 "peak": hbm, "unit": "GB/s", "frac": round(by_op / us_op / 1e3 / hbm, 4), "bytes_per_launch": by_op,
                 "us_per_launch": round(us_op, 2), "tensor_achieved_tflops": round(fl_op / us_op / 1e6, 1),
                 "tensor_frac": round(fl_op / us_op / 1e6 / tf, 4), "peak_source": src,
-                "note": "algorithmic bytes = 97.0 MB per volume (SURVEY 8d): the bf16 im2col rows the unfused gather writes and the "
-                        "GEMM re-reads are NOT counted; the gather alone moves its own 100.7 MB per volume at "
-                        f"{round(Fr * D0 * D1 * D2 * 6 / us_gather / 1e3 / hbm, 3)} of the HBM peak ({round(us_gather, 1)} us)"})
+                "unfused_us_per_launch": round(us_unfused, 2),
+                "note": "algorithmic bytes = 97.0 MB per volume (SURVEY 8d); the unfused variant (gather + GEMM, "
+                        f"{round(us_unfused, 1)} us) writes and re-reads bf16 im2col rows that are NOT counted; its gather alone moves "
+                        f"its own 100.7 MB per volume at {round(Fr * D0 * D1 * D2 * 6 / us_gather / 1e3 / hbm, 3)} of the HBM peak "
+                        f"({round(us_gather, 1)} us)"})
     del vols, rows, xs
     # --- decoder prefill GEMM (gate|up): M = batch * prompt rows
     M = max(spec["batch"], 1) * (geom.num_3d_query_token + spec["n_question"])

@@ -144,6 +144,16 @@ U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t rows, int32_
  */
 U2_API int u2_patchify_f32_bf16(const float* vol, void* rows, int64_t frames, int32_t d0, int32_t d1,
                                 int32_t d2, int32_t p0, int32_t p1, int32_t p2, void* stream);
+/* Fused 3-D patch embedding: out[f, 1 + t, :] = bf16(patch(f, t) . W^T + bias + pos[t]) for the fp32 volume
+ * vol [frames, d0, d1, d2] (single channel), W [N, p0*p1*p2] bf16 in MONAI's (p1 p2 p3 c) feature order, bias fp32 [N],
+ * pos bf16 [tokens, N], out bf16 [frames, out_frame_rows, N] (row 0 = cls and the rows behind the tokens are left to
+ * u2_vit_frame_rows_bf16). 5-D TMA slabs of the volume are converted to the swizzled bf16 A operand in shared memory: the
+ * einops gather of MONAI PatchEmbeddingBlock + Linear + position add (reference vit.py:90-99,115) in one kernel, the volume
+ * is read once. Covers patch (p0, 4k, 16) on a (g0, 8m, 16) token grid (the canonical 4 x 16 x 16 patches of
+ * 32 x 256 x 256 frames); other geometries return U2_ERR_UNSUPPORTED (use u2_patchify_f32_bf16 + u2_gemm_bf16). */
+U2_API int u2_patch_embed_f32_bf16(const float* vol, const void* W, const float* bias, const void* pos, void* out,
+                                   int64_t frames, int32_t d0, int32_t d1, int32_t d2, int32_t p0, int32_t p1, int32_t p2,
+                                   int32_t N, int64_t out_frame_rows, void* stream);
 /* dst[(r * row_stride + row_off), :] = vec for r in [0, n_rows)   (cls token rows, vit.py:116-118) */
 U2_API int u2_set_rows_bf16(void* dst, const void* vec, int64_t n_rows, int64_t row_stride, int64_t row_off,
                             int32_t E, void* stream);

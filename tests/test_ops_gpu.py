@@ -531,3 +531,35 @@ def test_sampling_distribution(temperature, top_k, top_p):
     a = ops.sample(logits, temperature=temperature, top_k=top_k, top_p=top_p, seed=7, step=3)
     b2 = ops.sample(logits, temperature=temperature, top_k=top_k, top_p=top_p, seed=7, step=3)
     assert torch.equal(a, b2) and a.unique().numel() > 1
+
+
+@pytest.mark.parametrize("image,hidden,frames", [([8, 128, 256], 96, 3), ([32, 256, 256], 768, 5)])
+def test_patch_embed_fused(image, hidden, frames):
+    """One-kernel patch embedding (5-D TMA slabs -> converted A operand -> tcgen05, + bias + position table) against the
+    MONAI restatement in the oracle and against the unfused gather + GEMM path, canonical 4 x 16 x 16 patches."""
+    from oracle import u2_oracle as O
+    from u2tokenizer_b200 import ops
+    patch = [4, 16, 16]
+    assert ops.patch_embed_supported(image, patch, hidden)
+    gen = torch.Generator(device="cuda").manual_seed(hidden)
+    vol = torch.rand(frames, *image, device="cuda", generator=gen)
+    K = 4 * 16 * 16
+    P = (image[0] // 4) * (image[1] // 16) * (image[2] // 16)
+    w = (torch.randn(hidden, K, device="cuda", generator=gen) * K ** -0.5).bfloat16()
+    b = 0.1 * torch.randn(hidden, device="cuda", generator=gen)
+    pos = (0.1 * torch.randn(P, hidden, device="cuda", generator=gen)).bfloat16()
+    Sp = (P + 1 + 7) // 8 * 8
+    out = torch.full((frames, Sp, hidden), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.patch_embed(vol, patch, w, b, pos, out)
+    sd = {"v.patch_embedding.patch_embeddings.1.weight": w.float(), "v.patch_embedding.patch_embeddings.1.bias": b,
+          "v.patch_embedding.position_embeddings": pos.float()[None]}
+    ref = O.patch_embed(sd, "v.", vol[:, None], patch)
+    got = out[:, 1:1 + P].float()
+    e = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert e < 1e-2, e
+    assert float(out[:, 0].float().min()) == 7.0 and float(out[:, P + 1:].float().min()) == 7.0   # cls / padding rows untouched
+    rows = ops.patchify(vol, patch)
+    x2 = torch.empty_like(out)
+    ops.gemm(rows, w, x2, M=frames * P, N=hidden, K=K, lda=K, ldb=K, ldc=hidden, bias=b, residual=pos, ldr=hidden, res_row_mod=P,
+             row_remap=(P, Sp, 1))
+    assert float((x2[:, 1:1 + P].float() - got).abs().max()) <= 2 ** -6 * float(ref.abs().max())

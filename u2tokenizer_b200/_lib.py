@@ -201,6 +201,7 @@ SIGNATURES = {
     "u2_softmax_f32_bf16": (C.c_int, [_P, _P, C.POINTER(SoftmaxDesc), _P]),
     "u2_silu_mul_bf16": (C.c_int, [_P, _P, _L, _I, _L, _L, _I, _P]),
     "u2_patchify_f32_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "u2_patch_embed_f32_bf16": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _L, _P]),
     "u2_set_rows_bf16": (C.c_int, [_P, _P, _L, _L, _L, _I, _P]),
     "u2_vit_frame_rows_bf16": (C.c_int, [_P, _P, _L, _I, _I, _I, _P]),
     "u2_transpose_heads_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),

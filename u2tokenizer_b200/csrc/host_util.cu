@@ -95,6 +95,22 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1,
   return U2_OK;
 }
 
+int make_tmap_f32_nd(CUtensorMap* out, const void* base, int n, const int64_t* dims, const int64_t* strides_bytes,
+                     const int* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(U2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (n < 1 || n > 5) return set_error(U2_ERR_ARG, "tensor map rank %d", n);
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < n; ++i) { d[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < n; ++i) st[i] = (cuuint64_t)strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)n, const_cast<void*>(base), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(U2_ERR_CUDA, "cuTensorMapEncodeTiled(f32 %d-d) failed: %d", n, (int)r);
+  return U2_OK;
+}
+
 }  // namespace u2
 
 namespace u2 { const char* last_error(); }

@@ -22,6 +22,10 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, int64_t k, int64_t row
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2,
                      int64_t stride1_elems, int64_t stride2_elems, int box0, int box1, int box2);
 
+// n-D fp32 tensor map (no swizzle): dims / box inner -> outer, strides in BYTES for dims 1..n-1.
+int make_tmap_f32_nd(CUtensorMap* out, const void* base, int n, const int64_t* dims, const int64_t* strides_bytes,
+                     const int* box);
+
 }  // namespace u2
 
 #define U2_CHECK_LAUNCH(what)                                                          \

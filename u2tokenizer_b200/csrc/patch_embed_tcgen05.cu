@@ -1,0 +1,311 @@
+// Fused 3-D patch embedding (K1 / K2 of SURVEY.md section 2d): fp32 CT volume -> bf16 ViT tokens in ONE kernel.
+//
+//   x[f, 1 + t, :] = bf16( patch(f, t) [1024 fp32 voxels] . W^T + bias + pos[t] )      t = (h, w, d) over the 8 x 16 x 16 grid
+//
+// The einops gather "b c (h p1) (w p2) (d p3) -> b (h w d) (p1 p2 p3 c)" of MONAI's PatchEmbeddingBlock (reference
+// src/model/multimodal_encoder/vit.py:90-99,115) never materialises: a 128-token M tile is the 8 (w) x 16 (d) tokens of one
+// (frame, h) slab, and k-block kb = (p1, 4 consecutive p2, 16 p3) of those tokens is ONE 5-D TMA box
+// {256 (D2), 4 (p2), 8 (w), 1 (D0 = 4 h + p1), 1 (frame)} = 32 KB of fp32 that lands in shared memory as
+// [w][p2][256]. A converter warp-group (thread = token) rewrites it as the 128 x 64 bf16 K-major SWIZZLE_128B A tile the
+// tensor core wants (bank-conflict-free: the four 16-byte pieces of a thread's 64-byte segment are read in an order
+// rotated by the token index), tcgen05.mma accumulates in TMEM, the epilogue adds bias + position embedding and stores the
+// rows behind the cls row through a swizzled staging tile (whole 64-byte segments per store). The unfused path wrote and
+// re-read 134 MB of bf16 im2col rows per 4 volumes; here the volume is read once (the three N tiles of an M tile run on
+// neighbouring CTAs in the same time window, so the second and third read of a slab hit L2).
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over (m tile, n tile)):
+//   warp 0      TMA producer: fp32 slabs -> 2-stage staging ring, W tiles (256 x 64 bf16) -> 3-stage ring
+//   warp 1      MMA issuer (one thread), 128 x 256 x 16 UMMAs, fp32 accumulators double-buffered in TMEM
+//   warp 2      TMEM allocator
+//   warps 4-7   converter warp-group (fp32 staging -> swizzled bf16 A ring, 3 stages)
+//   warps 8-11  epilogue (TMEM lane quarter = warp % 4, all 256 columns)
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+#include "u2b200.h"
+
+namespace u2 {
+
+constexpr int kPeM = 128, kPeN = 256, kPeK = 64;
+constexpr int kPeStg = 2, kPeA = 3, kPeB = 3;
+constexpr int kPeStgBytes = 128 * 64 * 4;   // 32 KB fp32 slab
+constexpr int kPeABytes = kPeM * kPeK * 2;  // 16 KB
+constexpr int kPeBBytes = kPeN * kPeK * 2;  // 32 KB
+constexpr int kPeEpiBytes = 4 * 4096;
+constexpr int kPeSmem = kPeA * kPeABytes + kPeB * kPeBBytes + kPeStg * kPeStgBytes + kPeEpiBytes + 1024 + 256;
+constexpr int kPeThreads = 384;
+
+struct PeArgs {
+  int frames, g0, g1, g2;   // token grid per frame (8, 16, 16)
+  int p0, p1;               // patch extents along D0, D1 (4, 16); the extent along D2 is 16
+  int N;                    // hidden size (768)
+  int P, Sp;                // tokens per frame, padded rows per frame of the output buffer
+  const float* bias;        // [N]
+  const __nv_bfloat16* pos; // [P, N]
+  __nv_bfloat16* out;       // [frames, Sp, N]; token t goes to row 1 + t
+};
+
+// 5-D tiled load (fp32 slab of the volume)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kPeThreads, 1)
+patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const __grid_constant__ CUtensorMap tmap_w,
+                           const PeArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kPeA * kPeABytes;
+  uint8_t* sStg = sB + kPeB * kPeBBytes;
+  uint8_t* sEpi = sStg + kPeStg * kPeStgBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kPeEpiBytes);
+  uint64_t* stg_full = bars;                 // [2]
+  uint64_t* stg_empty = stg_full + kPeStg;   // [2]
+  uint64_t* a_full = stg_empty + kPeStg;     // [3]
+  uint64_t* a_empty = a_full + kPeA;         // [3]
+  uint64_t* b_full = a_empty + kPeA;         // [3]
+  uint64_t* b_empty = b_full + kPeB;         // [3]
+  uint64_t* t_full = b_empty + kPeB;         // [2]
+  uint64_t* t_empty = t_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w_tiles = p.g1 / 8;                                // M tiles per (frame, h)
+  const int num_m = p.frames * p.g0 * w_tiles;
+  const int num_n = (p.N + kPeN - 1) / kPeN;
+  const int num_tiles = num_m * num_n;
+  const int kb_per_p0 = p.p1 / 4;
+  const int num_kb = p.p0 * kb_per_p0;                          // 16
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_vol);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kPeStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 128); }
+    for (int s = 0; s < kPeA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kPeB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ss = 0, bs = 0;
+      uint32_t sph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int wt = m_blk % w_tiles;
+        const int fh = m_blk / w_tiles;
+        const int h = fh % p.g0, f = fh / p.g0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int q0 = kb / kb_per_p0, q1 = (kb - q0 * kb_per_p0) * 4;
+          mbar_wait(&stg_empty[ss], sph ^ 1);
+          mbar_arrive_expect_tx(&stg_full[ss], kPeStgBytes);
+          tma_load_5d(sStg + ss * kPeStgBytes, &tmap_vol, &stg_full[ss], 0, q1, wt * 8, h * p.p0 + q0, f);
+          if (++ss == kPeStg) { ss = 0; sph ^= 1; }
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          mbar_arrive_expect_tx(&b_full[bs], kPeBBytes);
+          tma_load_4d(sB + bs * kPeBBytes, &tmap_w, &b_full[bs], kb * kPeK, n_blk * kPeN, 0, 0);
+          if (++bs == kPeB) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kPeM, kPeN);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&t_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPeN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&a_full[as], aph);
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + as * kPeABytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + bs * kPeBBytes));
+#pragma unroll
+          for (int k = 0; k < kPeK / 16; ++k) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&a_empty[as]);
+          umma_commit(&b_empty[bs]);
+          if (++as == kPeA) { as = 0; aph ^= 1; }
+          if (++bs == kPeB) { bs = 0; bph ^= 1; }
+        }
+        umma_commit(&t_full[acc]);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4 && warp_idx < 8) {
+    // ===================== converter: fp32 [w][p2][256] slab -> bf16 K-major SW128 A tile =====================
+    const int r = threadIdx.x - 128;     // token row of the tile: w = r / 16, d = r % 16
+    const int w = r >> 4, d = r & 15;
+    const int rot = (d >> 1) & 3;        // piece order rotation: 8 consecutive threads hit 8 distinct 16-byte bank groups
+    int ss = 0, as = 0;
+    uint32_t sph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&stg_full[ss], sph);
+        mbar_wait(&a_empty[as], aph ^ 1);
+        const uint8_t* src = sStg + ss * kPeStgBytes + (w * 4) * 1024 + d * 64;
+        uint8_t* dst = sA + as * kPeABytes + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {    // q = p2 offset inside the k-block: 16 consecutive fp32 = 2 bf16 chunks
+          float4 pc[4];
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const int piece = (s + rot) & 3;
+            const float4 v = *reinterpret_cast<const float4*>(src + q * 1024 + piece * 16);
+            // static register indexing: route the piece to its slot with predicated moves
+            if (piece == 0) pc[0] = v; else if (piece == 1) pc[1] = v; else if (piece == 2) pc[2] = v; else pc[3] = v;
+          }
+          uint4 c0, c1;
+          *reinterpret_cast<__nv_bfloat162*>(&c0.x) = __floats2bfloat162_rn(pc[0].x, pc[0].y);
+          *reinterpret_cast<__nv_bfloat162*>(&c0.y) = __floats2bfloat162_rn(pc[0].z, pc[0].w);
+          *reinterpret_cast<__nv_bfloat162*>(&c0.z) = __floats2bfloat162_rn(pc[1].x, pc[1].y);
+          *reinterpret_cast<__nv_bfloat162*>(&c0.w) = __floats2bfloat162_rn(pc[1].z, pc[1].w);
+          *reinterpret_cast<__nv_bfloat162*>(&c1.x) = __floats2bfloat162_rn(pc[2].x, pc[2].y);
+          *reinterpret_cast<__nv_bfloat162*>(&c1.y) = __floats2bfloat162_rn(pc[2].z, pc[2].w);
+          *reinterpret_cast<__nv_bfloat162*>(&c1.z) = __floats2bfloat162_rn(pc[3].x, pc[3].y);
+          *reinterpret_cast<__nv_bfloat162*>(&c1.w) = __floats2bfloat162_rn(pc[3].z, pc[3].w);
+          *reinterpret_cast<uint4*>(dst + (((2 * q) ^ (r & 7)) << 4)) = c0;
+          *reinterpret_cast<uint4*>(dst + (((2 * q + 1) ^ (r & 7)) << 4)) = c1;
+        }
+        fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&a_full[as]);
+        mbar_arrive(&stg_empty[ss]);
+        if (++ss == kPeStg) { ss = 0; sph ^= 1; }
+        if (++as == kPeA) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 8) {
+    // ===================== epilogue =====================
+    const int q = warp_idx & 3;
+    uint8_t* st = sEpi + q * 4096;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      mbar_wait(&t_full[acc], acc_ph);
+      tc_fence_after();
+      const long long row = (long long)m_blk * kPeM + q * 32 + lane;   // global token index (frame * P + t)
+      const int t = (int)(row % p.P);
+      const uint32_t taddr = tmem_base + acc * kPeN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kPeN; c0 += 32) {
+        const int col0 = n_blk * kPeN + c0;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        float f[32];
+        const __nv_bfloat16* pr = p.pos + (long long)t * p.N + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 rr = *reinterpret_cast<const uint4*>(pr + j);
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 rf = __bfloat1622float2(r2[e]);
+            f[j + 2 * e] = __uint_as_float(v[j + 2 * e]) + __ldg(p.bias + col0 + j + 2 * e) + rf.x;
+            f[j + 2 * e + 1] = __uint_as_float(v[j + 2 * e + 1]) + __ldg(p.bias + col0 + j + 2 * e + 1) + rf.y;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * c + 2 * e], f[8 * c + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+          const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+          const long long grow = (long long)m_blk * kPeM + q * 32 + rr;
+          const long long orow = (grow / p.P) * p.Sp + 1 + grow % p.P;
+          *reinterpret_cast<uint4*>(p.out + orow * p.N + col0 + ch * 8) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&t_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace u2
+
+extern "C" U2_API int u2_patch_embed_f32_bf16(const float* vol, const void* W, const float* bias, const void* pos, void* out,
+                                              int64_t frames, int32_t d0, int32_t d1, int32_t d2, int32_t p0, int32_t p1,
+                                              int32_t p2, int32_t N, int64_t out_frame_rows, void* stream) {
+  using namespace u2;
+  if (!vol || !W || !bias || !pos || !out) return set_error(U2_ERR_ARG, "patch_embed: null pointer");
+  if (p0 <= 0 || p1 <= 0 || p2 <= 0 || d0 % p0 || d1 % p1 || d2 % p2) return set_error(U2_ERR_ARG, "patch_embed: image not divisible by the patch");
+  const int g0 = d0 / p0, g1 = d1 / p1, g2 = d2 / p2;
+  // the fused tiling: 16-voxel patch rows along D2, 16 tokens along D2 per (h, w) and groups of 8 w per M tile
+  if (p2 != 16 || g2 != 16 || (p1 & 3) || (g1 & 7) || d2 > 256 || (N & 31))
+    return set_error(U2_ERR_UNSUPPORTED, "patch_embed: fused kernel covers patch (*, 4k, 16) on a (*, 8m, 16) token grid with D2 <= 256 "
+                                         "(got patch %d x %d x %d, grid %d x %d x %d); use u2_patchify_f32_bf16 + u2_gemm_bf16", p0, p1, p2, g0, g1, g2);
+  const long long P = (long long)g0 * g1 * g2;
+  if (out_frame_rows < P + 1) return set_error(U2_ERR_ARG, "patch_embed: out_frame_rows must be >= tokens + 1 (cls row)");
+  if ((reinterpret_cast<uintptr_t>(vol) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(pos) & 15))
+    return set_error(U2_ERR_ARG, "patch_embed: pointers must be 16-byte aligned");
+  if (frames <= 0) return U2_OK;
+  const int K = p0 * p1 * p2;
+  CUtensorMap tv, tw;
+  {
+    // volume [frames][D0][D1 = (w, p2)][D2] fp32 as a 5-D map {D2, p2, w, D0, frame}; box {D2, 4, 8, 1, 1}
+    const int64_t dims[5] = {d2, p1, g1, d0, frames};
+    const int64_t strides[4] = {(int64_t)d2 * 4, (int64_t)p1 * d2 * 4, (int64_t)d1 * d2 * 4, (int64_t)d0 * d1 * d2 * 4};
+    const int box[5] = {d2, 4, 8, 1, 1};
+    int rc = make_tmap_f32_nd(&tv, vol, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  int rc = make_tmap_bf16_4d(&tw, W, K, N, 1, 1, K, 0, 0, kPeK, kPeN);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeSmem);
+    if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "patch_embed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  PeArgs a;
+  a.frames = (int)frames; a.g0 = g0; a.g1 = g1; a.g2 = g2; a.p0 = p0; a.p1 = p1; a.N = N;
+  a.P = (int)P; a.Sp = (int)out_frame_rows;
+  a.bias = bias; a.pos = reinterpret_cast<const __nv_bfloat16*>(pos); a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const long long tiles = (long long)frames * g0 * (g1 / 8) * ((N + kPeN - 1) / kPeN);
+  const int sms = num_sms();
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  patch_embed_tcgen05_kernel<<<grid, kPeThreads, kPeSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tv, tw, a);
+  U2_CHECK_LAUNCH("patch_embed");
+  return U2_OK;
+}

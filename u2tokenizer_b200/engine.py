@@ -94,6 +94,7 @@ class U2Engine:
         self.attn_pdl = os.environ.get("U2_ATTN_PDL", "0") != "0"  # PDL launch of the split-KV decode attention
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
+        self.fused_patch_embed = os.environ.get("U2_FUSED_PATCH_EMBED", "1") != "0"  # one-kernel gather + Linear (canonical patches)
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
         self.fine_deps = os.environ.get("U2_FINE_DEPS", "0") != "0"  # per-tile flags instead of grid-wide waits
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
@@ -290,13 +291,17 @@ class U2Engine:
         S = P + 1
         Sp = _pad8(S)
         vol = frames.to(device=self.dev, dtype=F32).contiguous().view(Fr, *g.image_size)
-        # --- patch embedding: brick gather -> GEMM (+bias +position table, rows scattered behind the cls row)
-        rows = ops.patchify(vol, g.patch_size)
         x = torch.empty(Fr, Sp, Hd, device=self.dev, dtype=BF16)
-        ops.gemm(rows, self.pe_w, x, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd,
-                 bias=self.pe_b, residual=self.pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
+        if self.fused_patch_embed and ops.patch_embed_supported(g.image_size, g.patch_size, Hd):
+            # --- fused patch embedding: 5-D TMA slabs of the fp32 volume -> bf16 A operand in smem -> tcgen05 (+bias +pos)
+            ops.patch_embed(vol, g.patch_size, self.pe_w, self.pe_b, self.pos, x)
+        else:
+            # --- brick gather -> GEMM (+bias +position table, rows scattered behind the cls row)
+            rows = ops.patchify(vol, g.patch_size)
+            ops.gemm(rows, self.pe_w, x, M=Fr * P, N=Hd, K=g.patch_dim, lda=g.patch_dim, ldb=g.patch_dim, ldc=Hd,
+                     bias=self.pe_b, residual=self.pos, ldr=Hd, res_row_mod=P, row_remap=(P, Sp, 1))
+            del rows
         ops.vit_frame_rows(x, self.cls, Fr, Sp, S)  # cls row + the 7 zero padding rows per frame (no full-buffer memset)
-        del rows
         # --- transformer blocks
         nh = g.vit_heads
         dh = Hd // nh

@@ -203,6 +203,32 @@ def patchify(vol: torch.Tensor, patch_size, out: Optional[torch.Tensor] = None) 
     return out
 
 
+def patch_embed_supported(image_size, patch_size, hidden: int) -> bool:
+    """Geometries the fused patch-embedding kernel covers (see u2_patch_embed_f32_bf16)."""
+    d0, d1, d2 = image_size
+    p0, p1, p2 = patch_size
+    if d0 % p0 or d1 % p1 or d2 % p2:
+        return False
+    return p2 == 16 and d2 // p2 == 16 and p1 % 4 == 0 and (d1 // p1) % 8 == 0 and d2 <= 256 and hidden % 32 == 0
+
+
+def patch_embed(vol: torch.Tensor, patch_size, w: torch.Tensor, bias: torch.Tensor, pos: torch.Tensor,
+                out: torch.Tensor) -> torch.Tensor:
+    """Fused gather + Linear + bias + position embedding: vol fp32 [F, D0, D1, D2] -> out bf16 [F, Sp, N] rows 1..P."""
+    _need_cuda(vol, w, bias, pos, out)
+    if vol.dtype != F32 or not vol.is_contiguous() or w.dtype != BF16 or bias.dtype != F32 or pos.dtype != BF16:
+        raise TypeError("patch_embed: fp32 contiguous volume, bf16 weight / position table, fp32 bias")
+    F_, d0, d1, d2 = vol.shape
+    p0, p1, p2 = patch_size
+    N = w.shape[0]
+    if out.shape[0] != F_ or out.shape[2] != N or not out.is_contiguous() or not w.is_contiguous() or not pos.is_contiguous():
+        raise ValueError("patch_embed: out must be contiguous [frames, rows, N]")
+    _lib.check(_lib.load().u2_patch_embed_f32_bf16(vol.data_ptr(), w.data_ptr(), bias.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                                                   F_, d0, d1, d2, p0, p1, p2, N, out.shape[1], _stream()),
+               "u2_patch_embed_f32_bf16")
+    return out
+
+
 def set_rows(dst: torch.Tensor, vec: torch.Tensor, n_rows: int, row_stride: int, row_off: int):
     _need_cuda(dst, vec)
     E = vec.numel()
