@@ -14,10 +14,10 @@
 // neighbouring CTAs in the same time window, so the second and third read of a slab hit L2).
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over (m tile, n tile)):
-//   warp 0      TMA producer: fp32 slabs -> 2-stage staging ring, W tiles (256 x 64 bf16) -> 3-stage ring
+//   warp 0      TMA producer: fp32 slabs -> 3-stage staging ring (96 KB in flight), W tiles (256 x 64 bf16) -> 2-stage ring
 //   warp 1      MMA issuer (one thread), 128 x 256 x 16 UMMAs, fp32 accumulators double-buffered in TMEM
 //   warp 2      TMEM allocator
-//   warps 4-7   converter warp-group (fp32 staging -> swizzled bf16 A ring, 3 stages)
+//   warps 4-7   converter warp-group (fp32 staging -> swizzled bf16 A ring, 2 stages)
 //   warps 8-11  epilogue (TMEM lane quarter = warp % 4, all 256 columns)
 #include <cuda_bf16.h>
 
@@ -28,7 +28,7 @@
 namespace u2 {
 
 constexpr int kPeM = 128, kPeN = 256, kPeK = 64;
-constexpr int kPeStg = 2, kPeA = 3, kPeB = 3;
+constexpr int kPeStg = 3, kPeA = 2, kPeB = 2;
 constexpr int kPeStgBytes = 128 * 64 * 4;   // 32 KB fp32 slab
 constexpr int kPeABytes = kPeM * kPeK * 2;  // 16 KB
 constexpr int kPeBBytes = kPeN * kPeK * 2;  // 32 KB
@@ -68,12 +68,12 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
   uint8_t* sStg = sB + kPeB * kPeBBytes;
   uint8_t* sEpi = sStg + kPeStg * kPeStgBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kPeEpiBytes);
-  uint64_t* stg_full = bars;                 // [2]
-  uint64_t* stg_empty = stg_full + kPeStg;   // [2]
-  uint64_t* a_full = stg_empty + kPeStg;     // [3]
-  uint64_t* a_empty = a_full + kPeA;         // [3]
-  uint64_t* b_full = a_empty + kPeA;         // [3]
-  uint64_t* b_empty = b_full + kPeB;         // [3]
+  uint64_t* stg_full = bars;                 // [kPeStg]
+  uint64_t* stg_empty = stg_full + kPeStg;   // [kPeStg]
+  uint64_t* a_full = stg_empty + kPeStg;     // [kPeA]
+  uint64_t* a_empty = a_full + kPeA;         // [kPeA]
+  uint64_t* b_full = a_empty + kPeA;         // [kPeB]
+  uint64_t* b_empty = b_full + kPeB;         // [kPeB]
   uint64_t* t_full = b_empty + kPeB;         // [2]
   uint64_t* t_empty = t_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);

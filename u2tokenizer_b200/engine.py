@@ -94,7 +94,7 @@ class U2Engine:
         self.attn_pdl = os.environ.get("U2_ATTN_PDL", "0") != "0"  # PDL launch of the split-KV decode attention
         self.pdl = os.environ.get("U2_PDL", "1") != "0"  # programmatic dependent launch between decode linears
         self.multi_op = os.environ.get("U2_MULTI_OP", "1") != "0"  # o_proj/gate-up/down/qkv chained in one launch
-        self.fused_patch_embed = os.environ.get("U2_FUSED_PATCH_EMBED", "1") != "0"  # one-kernel gather + Linear (canonical patches)
+        self.fused_patch_embed = os.environ.get("U2_FUSED_PATCH_EMBED", "0") != "0"  # one-kernel gather + Linear (canonical patches); see DESIGN.md
         self.use_flash = os.environ.get("U2_FLASH", "1") != "0"  # fused tcgen05 attention where it applies (dh 64)
         self.fine_deps = os.environ.get("U2_FINE_DEPS", "0") != "0"  # per-tile flags instead of grid-wide waits
         self.dl_sched = int(os.environ.get("U2_DL_SCHED", "0"))  # 1: whole 64-row tiles per CTA; 0: stream-K / 128
