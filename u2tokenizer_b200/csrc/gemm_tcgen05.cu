@@ -30,8 +30,8 @@ namespace u2 {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 384;   // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarp0 = 4;
+constexpr int kNumThreads = 352;   // 3 control warps + 8 epilogue warps (352 threads -> 186 registers per thread)
+constexpr int kEpiWarp0 = 3;
 constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter, each takes half of the tile's columns
 
 template <int kBlockN>
@@ -247,8 +247,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= kEpiWarp0) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = (warp_idx - kEpiWarp0) & 3;    // == warp_idx % 4: the TMEM lane quarter this warp may read
-    const int half = (warp_idx - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
+    const int q = warp_idx & 3;                    // the TMEM lane quarter this warp may read is warp_idx % 4
+    const int half = (warp_idx - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains (warps 3-6 / 7-10)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -320,6 +320,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
+        // operands that do not depend on the accumulator are requested BEFORE the TMEM load is waited for: the residual /
+        // position-table row segment (4 x 16 B per thread) is in flight while tcgen05.ld completes (the serial
+        // wait -> load -> wait chain per 32-column chunk made every short-K GEMM with a residual epilogue-bound)
+        const bool full = (col0 + 32 <= p.N);
+        const bool res_vec = row_ok && res_ptr && full && ((p.ldr & 7) == 0);
+        uint4 rres[4];
+        if (res_vec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = *reinterpret_cast<const uint4*>(res_ptr + col0 + 8 * j);
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -332,7 +342,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - rv);
           } else {
             const __nv_bfloat16* mp = p.mul + c_off + col0;
-            if ((col0 + 32 <= p.N) && (((p.ldc | zoff) & 7) == 0)) {
+            if (full && (((p.ldc | zoff) & 7) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 const uint4 r = *reinterpret_cast<const uint4*>(mp + j);
@@ -352,34 +362,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         if (row_ok) {
-          const bool full = (col0 + 32 <= p.N);
           if (p.bias) {
+            if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+            }
           }
           if (p.act != U2_ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
           }
-          if (res_ptr) {
-            if (full && ((p.ldr & 7) == 0)) {
+          if (res_vec) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + col0 + j);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 rf = __bfloat1622float2(r2[e]);
-                  f[j + 2 * e] += rf.x;
-                  f[j + 2 * e + 1] += rf.y;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float2 rf = __bfloat1622float2(r2[e]);
+                f[8 * j + 2 * e] += rf.x;
+                f[8 * j + 2 * e + 1] += rf.y;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
             }
+          } else if (res_ptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
           }
           (void)0;
         }
