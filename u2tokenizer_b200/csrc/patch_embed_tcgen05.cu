@@ -13,12 +13,15 @@
 // re-read 134 MB of bf16 im2col rows per 4 volumes; here the volume is read once (the three N tiles of an M tile run on
 // neighbouring CTAs in the same time window, so the second and third read of a slab hit L2).
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over (m tile, n tile)):
+// Warp roles (480 threads, 1 CTA / SM, persistent over (m tile, n tile)):
 //   warp 0      TMA producer: fp32 slabs -> 3-stage staging ring (96 KB in flight), W tiles (256 x 64 bf16) -> 2-stage ring
 //   warp 1      MMA issuer (one thread), 128 x 256 x 16 UMMAs, fp32 accumulators double-buffered in TMEM
 //   warp 2      TMEM allocator
-//   warps 4-7   converter warp-group (fp32 staging -> swizzled bf16 A ring, 2 stages)
-//   warps 8-11  epilogue (TMEM lane quarter = warp % 4, all 256 columns)
+//   warps 3-6   converter warp-group (fp32 staging -> swizzled bf16 A ring, 2 stages)
+//   warps 7-14  epilogue: two warps per TMEM lane quarter (quarter = warp % 4), each drains half of the 256 columns; the
+//               position-table segment of a chunk is requested before the TMEM load is waited for (with K = 1024 a tile's
+//               mainloop is only ~7 us: the first version, 4 epilogue warps with serial wait -> load -> wait chunks, was
+//               epilogue-bound at 419 us per 4 volumes)
 #include <cuda_bf16.h>
 
 #include "host_util.h"
@@ -32,9 +35,10 @@ constexpr int kPeStg = 3, kPeA = 2, kPeB = 2;
 constexpr int kPeStgBytes = 128 * 64 * 4;   // 32 KB fp32 slab
 constexpr int kPeABytes = kPeM * kPeK * 2;  // 16 KB
 constexpr int kPeBBytes = kPeN * kPeK * 2;  // 32 KB
-constexpr int kPeEpiBytes = 4 * 4096;
+constexpr int kPeEpiBytes = 8 * 2048;   // one 32 x 32 bf16 staging tile per epilogue warp
 constexpr int kPeSmem = kPeA * kPeABytes + kPeB * kPeBBytes + kPeStg * kPeStgBytes + kPeEpiBytes + 1024 + 256;
-constexpr int kPeThreads = 384;
+constexpr int kPeThreads = 480;
+constexpr int kPeConvWarp0 = 3, kPeEpiWarp0 = 7;
 
 struct PeArgs {
   int frames, g0, g1, g2;   // token grid per frame (8, 16, 16)
@@ -94,7 +98,7 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
     for (int s = 0; s < kPeStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 128); }
     for (int s = 0; s < kPeA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kPeB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 256); }
     fence_barrier_init();
   }
   if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
@@ -153,9 +157,9 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp_idx >= 4 && warp_idx < 8) {
+  } else if (warp_idx >= kPeConvWarp0 && warp_idx < kPeEpiWarp0) {
     // ===================== converter: fp32 [w][p2][256] slab -> bf16 K-major SW128 A tile =====================
-    const int r = threadIdx.x - 128;     // token row of the tile: w = r / 16, d = r % 16
+    const int r = threadIdx.x - kPeConvWarp0 * 32;   // token row of the tile: w = r / 16, d = r % 16
     const int w = r >> 4, d = r & 15;
     const int rot = (d >> 1) & 3;        // piece order rotation: 8 consecutive threads hit 8 distinct 16-byte bank groups
     int ss = 0, as = 0;
@@ -195,37 +199,48 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
         if (++as == kPeA) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp_idx >= 8) {
+  } else if (warp_idx >= kPeEpiWarp0) {
     // ===================== epilogue =====================
-    const int q = warp_idx & 3;
-    uint8_t* st = sEpi + q * 4096;
+    const int q = warp_idx & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp_idx - kPeEpiWarp0) >> 2;   // which 128 of the tile's 256 columns
+    uint8_t* st = sEpi + (warp_idx - kPeEpiWarp0) * 2048;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-      mbar_wait(&t_full[acc], acc_ph);
-      tc_fence_after();
       const long long row = (long long)m_blk * kPeM + q * 32 + lane;   // global token index (frame * P + t)
       const int t = (int)(row % p.P);
       const uint32_t taddr = tmem_base + acc * kPeN + (static_cast<uint32_t>(q * 32) << 16);
+      const __nv_bfloat16* prow = p.pos + (long long)t * p.N;
+      mbar_wait(&t_full[acc], acc_ph);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kPeN; c0 += 32) {
+      for (int c0 = half * (kPeN / 2); c0 < (half + 1) * (kPeN / 2); c0 += 32) {
         const int col0 = n_blk * kPeN + c0;
         if (col0 >= p.N) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
+        uint4 rr[4];                                   // position-table segment: in flight while tcgen05.ld completes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(prow + col0 + 8 * j);
         tmem_ld_wait();
         float f[32];
-        const __nv_bfloat16* pr = p.pos + (long long)t * p.N + col0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 rr = *reinterpret_cast<const uint4*>(pr + j);
-          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          f[j] = __uint_as_float(v[j]) + b4.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 rf = __bfloat1622float2(r2[e]);
-            f[j + 2 * e] = __uint_as_float(v[j + 2 * e]) + __ldg(p.bias + col0 + j + 2 * e) + rf.x;
-            f[j + 2 * e + 1] = __uint_as_float(v[j + 2 * e + 1]) + __ldg(p.bias + col0 + j + 2 * e + 1) + rf.y;
+            f[8 * j + 2 * e] += rf.x;
+            f[8 * j + 2 * e + 1] += rf.y;
           }
         }
         __syncwarp();
@@ -240,9 +255,9 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + (lane >> 2), ch = lane & 3;
-          const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-          const long long grow = (long long)m_blk * kPeM + q * 32 + rr;
+          const int rw = it * 8 + (lane >> 2), ch = lane & 3;
+          const uint4 o = *reinterpret_cast<const uint4*>(st + rw * 64 + ((ch ^ ((rw >> 1) & 3)) << 4));
+          const long long grow = (long long)m_blk * kPeM + q * 32 + rw;
           const long long orow = (grow / p.P) * p.Sp + 1 + grow % p.P;
           *reinterpret_cast<uint4*>(p.out + orow * p.N + col0 + ch * 8) = o;
         }
@@ -277,7 +292,7 @@ extern "C" U2_API int u2_patch_embed_f32_bf16(const float* vol, const void* W, c
   const long long P = (long long)g0 * g1 * g2;
   if (out_frame_rows < P + 1) return set_error(U2_ERR_ARG, "patch_embed: out_frame_rows must be >= tokens + 1 (cls row)");
   if ((reinterpret_cast<uintptr_t>(vol) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
-      (reinterpret_cast<uintptr_t>(pos) & 15))
+      (reinterpret_cast<uintptr_t>(pos) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15))
     return set_error(U2_ERR_ARG, "patch_embed: pointers must be 16-byte aligned");
   if (frames <= 0) return U2_OK;
   const int K = p0 * p1 * p2;
