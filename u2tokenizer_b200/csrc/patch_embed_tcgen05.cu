@@ -108,12 +108,14 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer 1: fp32 volume slabs =====================
+    // (separate from the weight-tile producer: with one thread feeding both rings the slab prefetch depth was tied to the
+    //  2-stage weight ring and every other k-block paid a full HBM latency)
     if (lane == 0) {
-      int ss = 0, bs = 0;
-      uint32_t sph = 0, bph = 0;
+      int ss = 0;
+      uint32_t sph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int m_blk = tile / num_n;
         const int wt = m_blk % w_tiles;
         const int fh = m_blk / w_tiles;
         const int h = fh % p.g0, f = fh / p.g0;
@@ -123,6 +125,17 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
           mbar_arrive_expect_tx(&stg_full[ss], kPeStgBytes);
           tma_load_5d(sStg + ss * kPeStgBytes, &tmap_vol, &stg_full[ss], 0, q1, wt * 8, h * p.p0 + q0, f);
           if (++ss == kPeStg) { ss = 0; sph ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 2) {
+    // ===================== TMA producer 2: weight tiles (this warp allocated TMEM above) =====================
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&b_empty[bs], bph ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], kPeBBytes);
           tma_load_4d(sB + bs * kPeBBytes, &tmap_w, &b_full[bs], kb * kPeK, n_blk * kPeN, 0, 0);
