@@ -403,7 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // rows) by its epilogue.
         const bool fast = (col0 + 32 <= p.N) &&
                           (p.c_dtype == U2_DT_BF16 ? (((p.ldc | zoff) & 7) == 0) : (((p.ldc | zoff) & 3) == 0));
-        uint8_t* st = smem_epi + (warp_idx - kEpiWarp0) * 4096;
+        const uint32_t st = smem_u32(smem_epi) + (warp_idx - kEpiWarp0) * 4096;
         const int row0 = m_blk * kBlockM + q * 32;
         if (fast) {
           __syncwarp();  // the previous chunk's read-back is complete
@@ -414,13 +414,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
               for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * c + 2 * e], f[8 * c + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+              sts128(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), o);
             }
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int rr = it * 8 + (lane >> 2), ch = lane & 3;
-              const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+              const uint4 o = lds128(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
               const int grow = row0 + rr;
               if (grow < p.M) {
                 long long orow = grow;
@@ -431,13 +431,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           } else {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(st + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                  make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+              sts128(st + lane * 128 + ((c ^ (lane & 7)) << 4),
+                     make_uint4(__float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]), __float_as_uint(f[4 * c + 2]),
+                                __float_as_uint(f[4 * c + 3])));
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + (lane >> 3), ch = lane & 7;
-              const float4 o = *reinterpret_cast<const float4*>(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              const float4 o = lds128_f32(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
               const int grow = row0 + rr;
               if (grow < p.M) {
                 long long orow = grow;

@@ -181,15 +181,15 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&stg_full[ss], sph);
         mbar_wait(&a_empty[as], aph ^ 1);
-        const uint8_t* src = sStg + ss * kPeStgBytes + (w * 4) * 1024 + d * 64;
-        uint8_t* dst = sA + as * kPeABytes + r * 128;
+        const uint32_t src = smem_u32(sStg) + ss * kPeStgBytes + (w * 4) * 1024 + d * 64;
+        const uint32_t dst = smem_u32(sA) + as * kPeABytes + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {    // q = p2 offset inside the k-block: 16 consecutive fp32 = 2 bf16 chunks
           float4 pc[4];
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             const int piece = (s + rot) & 3;
-            const float4 v = *reinterpret_cast<const float4*>(src + q * 1024 + piece * 16);
+            const float4 v = lds128_f32(src + q * 1024 + piece * 16);
             // static register indexing: route the piece to its slot with predicated moves
             if (piece == 0) pc[0] = v; else if (piece == 1) pc[1] = v; else if (piece == 2) pc[2] = v; else pc[3] = v;
           }
@@ -202,8 +202,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
           *reinterpret_cast<__nv_bfloat162*>(&c1.y) = __floats2bfloat162_rn(pc[2].z, pc[2].w);
           *reinterpret_cast<__nv_bfloat162*>(&c1.z) = __floats2bfloat162_rn(pc[3].x, pc[3].y);
           *reinterpret_cast<__nv_bfloat162*>(&c1.w) = __floats2bfloat162_rn(pc[3].z, pc[3].w);
-          *reinterpret_cast<uint4*>(dst + (((2 * q) ^ (r & 7)) << 4)) = c0;
-          *reinterpret_cast<uint4*>(dst + (((2 * q + 1) ^ (r & 7)) << 4)) = c1;
+          sts128(dst + (((2 * q) ^ (r & 7)) << 4), c0);
+          sts128(dst + (((2 * q + 1) ^ (r & 7)) << 4), c1);
         }
         fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(&a_full[as]);
@@ -216,7 +216,7 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
     // ===================== epilogue =====================
     const int q = warp_idx & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp_idx - kPeEpiWarp0) >> 2;   // which 128 of the tile's 256 columns
-    uint8_t* st = sEpi + (warp_idx - kPeEpiWarp0) * 2048;
+    const uint32_t st = smem_u32(sEpi) + (warp_idx - kPeEpiWarp0) * 2048;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -263,13 +263,13 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
           __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * c + 2 * e], f[8 * c + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+          sts128(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), o);
         }
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rw = it * 8 + (lane >> 2), ch = lane & 3;
-          const uint4 o = *reinterpret_cast<const uint4*>(st + rw * 64 + ((ch ^ ((rw >> 1) & 3)) << 4));
+          const uint4 o = lds128(st + rw * 64 + ((ch ^ ((rw >> 1) & 3)) << 4));
           const long long grow = (long long)m_blk * kPeM + q * 32 + rw;
           const long long orow = (grow / p.P) * p.Sp + 1 + grow % p.P;
           *reinterpret_cast<uint4*>(p.out + orow * p.N + col0 + ch * 8) = o;
