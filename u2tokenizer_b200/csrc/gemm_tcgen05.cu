@@ -153,7 +153,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kEpiThreads);
+      mbar_init(&tmem_empty_bar[s], kEpiThreads / 32);  // one arrival per epilogue warp (256 per-thread arrivals serialise)
     }
     fence_barrier_init();
   }
@@ -464,7 +464,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }  // kMode
       // hand the accumulator buffer back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

@@ -23,6 +23,7 @@
 //               mainloop is only ~7 us: the first version, 4 epilogue warps with serial wait -> load -> wait chunks, was
 //               epilogue-bound at 419 us per 4 volumes)
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -48,6 +49,7 @@ struct PeArgs {
   const float* bias;        // [N]
   const __nv_bfloat16* pos; // [P, N]
   __nv_bfloat16* out;       // [frames, Sp, N]; token t goes to row 1 + t
+  int dbg;                  // timing experiments only (U2_PE_DBG): 1 no proxy fence, 2 no staging reads, 4 no A-tile stores
 };
 
 // 5-D tiled load (fp32 slab of the volume)
@@ -95,10 +97,12 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
     tma_prefetch_desc(&tmap_w);
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < kPeStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 128); }
-    for (int s = 0; s < kPeA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    // consumer barriers count WARPS, not threads: 128 mbarrier.arrive on one barrier serialise (~10 ns each) - with per-thread
+    // arrivals on a_full and stg_empty every k-block cost 2.5 us whatever the converter did (first version: 419 us per pass)
+    for (int s = 0; s < kPeStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 4); }
+    for (int s = 0; s < kPeA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kPeB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp_idx == 2) tmem_alloc<512>(tmem_slot);
@@ -189,7 +193,7 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             const int piece = (s + rot) & 3;
-            const float4 v = lds128_f32(src + q * 1024 + piece * 16);
+            const float4 v = (p.dbg & 2) ? make_float4(1.f, 2.f, 3.f, 4.f) : lds128_f32(src + q * 1024 + piece * 16);
             // static register indexing: route the piece to its slot with predicated moves
             if (piece == 0) pc[0] = v; else if (piece == 1) pc[1] = v; else if (piece == 2) pc[2] = v; else pc[3] = v;
           }
@@ -202,12 +206,17 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
           *reinterpret_cast<__nv_bfloat162*>(&c1.y) = __floats2bfloat162_rn(pc[2].z, pc[2].w);
           *reinterpret_cast<__nv_bfloat162*>(&c1.z) = __floats2bfloat162_rn(pc[3].x, pc[3].y);
           *reinterpret_cast<__nv_bfloat162*>(&c1.w) = __floats2bfloat162_rn(pc[3].z, pc[3].w);
-          sts128(dst + (((2 * q) ^ (r & 7)) << 4), c0);
-          sts128(dst + (((2 * q + 1) ^ (r & 7)) << 4), c1);
+          if (!(p.dbg & 4)) {
+            sts128(dst + (((2 * q) ^ (r & 7)) << 4), c0);
+            sts128(dst + (((2 * q + 1) ^ (r & 7)) << 4), c1);
+          }
         }
-        fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&a_full[as]);
-        mbar_arrive(&stg_empty[ss]);
+        if (!(p.dbg & 1)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[as]);
+          mbar_arrive(&stg_empty[ss]);
+        }
         if (++ss == kPeStg) { ss = 0; sph ^= 1; }
         if (++as == kPeA) { as = 0; aph ^= 1; }
       }
@@ -276,7 +285,8 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
         }
       }
       tc_fence_before();
-      mbar_arrive(&t_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
@@ -329,6 +339,7 @@ extern "C" U2_API int u2_patch_embed_f32_bf16(const float* vol, const void* W, c
   PeArgs a;
   a.frames = (int)frames; a.g0 = g0; a.g1 = g1; a.g2 = g2; a.p0 = p0; a.p1 = p1; a.N = N;
   a.P = (int)P; a.Sp = (int)out_frame_rows;
+  a.dbg = getenv("U2_PE_DBG") ? atoi(getenv("U2_PE_DBG")) : 0;
   a.bias = bias; a.pos = reinterpret_cast<const __nv_bfloat16*>(pos); a.out = reinterpret_cast<__nv_bfloat16*>(out);
   const long long tiles = (long long)frames * g0 * (g1 / 8) * ((N + kPeN - 1) / kPeN);
   const int sms = num_sms();
