@@ -89,11 +89,11 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 4);   // one arrival per softmax WARP: 128 per-thread arrivals on one mbarrier serialise (~10 ns each)
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
+      mbar_init(&o_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -198,7 +198,8 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
         }
         tc_fence_before();
-        mbar_arrive(&o_empty[pb]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&o_empty[pb]);
       }
       // ---- pass 2: probabilities -> shared memory (bf16, 128-byte swizzled K-major rows)
       mbar_wait(&p_empty[buf], (n & 1) ^ 1);
@@ -228,13 +229,15 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[buf]);  // S[buf] may be overwritten by the scores of tile j + 2
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&s_empty[buf]);  // S[buf] may be overwritten by the scores of tile j + 2
       l = l * alpha + rowsum;
 #pragma unroll
       for (int d = 0; d < kFaDh; ++d) o[d] *= alpha;
       m = m_new;
       fence_proxy_async_smem();    // generic-proxy P stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&p_full[buf]);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&p_full[buf]);
     }
     // ---- last PV partial, normalise, store
     {
@@ -322,11 +325,11 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 4);   // one arrival per softmax WARP: 128 per-thread arrivals on one mbarrier serialise (~10 ns each)
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
+      mbar_init(&o_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -436,7 +439,8 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
           }
           tc_fence_before();
-          mbar_arrive(&o_empty[t]);
+          __syncwarp();
+          if ((threadIdx.x & 31) == 0) mbar_arrive(&o_empty[t]);
         }
         mbar_wait(&p_empty[t], (j & 1) ^ 1);
         float rowsum = 0.f;
@@ -464,13 +468,15 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           }
         }
         tc_fence_before();
-        mbar_arrive(&s_empty[t]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&s_empty[t]);
         l = l * alpha + rowsum;
 #pragma unroll
         for (int d = 0; d < kFaDh; ++d) o[d] *= alpha;
         m = m_new;
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[t]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&p_full[t]);
       }
       mbar_wait(&o_full[t], (J - 1) & 1);
       tc_fence_after();
