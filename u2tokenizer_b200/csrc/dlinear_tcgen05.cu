@@ -248,7 +248,7 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], 4);  // one arrival per epilogue warp (128 per-thread arrivals on one mbarrier serialise)
     }
     fence_barrier_init();
   }
@@ -480,7 +480,8 @@ dlinear_tcgen05_kernel(const __grid_constant__ DlinMulti mp) {
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);  // accumulator buffer is free again
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&tmem_empty_bar[acc]);  // accumulator buffer is free again
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
