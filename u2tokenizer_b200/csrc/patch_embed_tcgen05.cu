@@ -176,39 +176,36 @@ patch_embed_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_vol, const _
     }
   } else if (warp_idx >= kPeConvWarp0 && warp_idx < kPeEpiWarp0) {
     // ===================== converter: fp32 [w][p2][256] slab -> bf16 K-major SW128 A tile =====================
-    const int r = threadIdx.x - kPeConvWarp0 * 32;   // token row of the tile: w = r / 16, d = r % 16
-    const int w = r >> 4, d = r & 15;
-    const int rot = (d >> 1) & 3;        // piece order rotation: 8 consecutive threads hit 8 distinct 16-byte bank groups
+    // A staging row (w, p2) holds 16 tokens (d) x 16 fp32 (p3) = 1 KB: a warp reads it with two fully coalesced 16-byte
+    // loads per lane (lane l -> token d = l / 4 (+ 8), p3 quarter l % 4), converts and writes 8 bytes into row
+    // r = 16 w + d of the A tile at chunk (2 p2 + quarter / 2) ^ (r & 7): 32 lanes x 8 B cover every bank exactly twice.
+    // All register indices are static (the first version routed pieces with data-dependent selects, which the compiler
+    // turned into divergent branch trees: 819 instructions per warp and k-block, 2.5 us per k-block).
+    const int cw = warp_idx - kPeConvWarp0;   // this warp converts w = 2 cw, 2 cw + 1
+    const int dq = lane >> 2, quarter = lane & 3;
     int ss = 0, as = 0;
     uint32_t sph = 0, aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&stg_full[ss], sph);
         mbar_wait(&a_empty[as], aph ^ 1);
-        const uint32_t src = smem_u32(sStg) + ss * kPeStgBytes + (w * 4) * 1024 + d * 64;
-        const uint32_t dst = smem_u32(sA) + as * kPeABytes + r * 128;
+        const uint32_t src0 = smem_u32(sStg) + ss * kPeStgBytes + lane * 16;
+        const uint32_t dst0 = smem_u32(sA) + as * kPeABytes + (quarter & 1) * 8;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {    // q = p2 offset inside the k-block: 16 consecutive fp32 = 2 bf16 chunks
-          float4 pc[4];
+        for (int wi = 0; wi < 2; ++wi) {
+          const int w = 2 * cw + wi;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const int piece = (s + rot) & 3;
-            const float4 v = (p.dbg & 2) ? make_float4(1.f, 2.f, 3.f, 4.f) : lds128_f32(src + q * 1024 + piece * 16);
-            // static register indexing: route the piece to its slot with predicated moves
-            if (piece == 0) pc[0] = v; else if (piece == 1) pc[1] = v; else if (piece == 2) pc[2] = v; else pc[3] = v;
-          }
-          uint4 c0, c1;
-          *reinterpret_cast<__nv_bfloat162*>(&c0.x) = __floats2bfloat162_rn(pc[0].x, pc[0].y);
-          *reinterpret_cast<__nv_bfloat162*>(&c0.y) = __floats2bfloat162_rn(pc[0].z, pc[0].w);
-          *reinterpret_cast<__nv_bfloat162*>(&c0.z) = __floats2bfloat162_rn(pc[1].x, pc[1].y);
-          *reinterpret_cast<__nv_bfloat162*>(&c0.w) = __floats2bfloat162_rn(pc[1].z, pc[1].w);
-          *reinterpret_cast<__nv_bfloat162*>(&c1.x) = __floats2bfloat162_rn(pc[2].x, pc[2].y);
-          *reinterpret_cast<__nv_bfloat162*>(&c1.y) = __floats2bfloat162_rn(pc[2].z, pc[2].w);
-          *reinterpret_cast<__nv_bfloat162*>(&c1.z) = __floats2bfloat162_rn(pc[3].x, pc[3].y);
-          *reinterpret_cast<__nv_bfloat162*>(&c1.w) = __floats2bfloat162_rn(pc[3].z, pc[3].w);
-          if (!(p.dbg & 4)) {
-            sts128(dst + (((2 * q) ^ (r & 7)) << 4), c0);
-            sts128(dst + (((2 * q + 1) ^ (r & 7)) << 4), c1);
+          for (int q = 0; q < 4; ++q) {      // p2 offset inside the k-block
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const float4 v = (p.dbg & 2) ? make_float4(1.f, 2.f, 3.f, 4.f)
+                                           : lds128_f32(src0 + (w * 4 + q) * 1024 + half * 512);
+              const int r = w * 16 + half * 8 + dq;
+              const int chunk = 2 * q + (quarter >> 1);
+              __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+              if (!(p.dbg & 4))
+                sts64(dst0 + r * 128 + ((chunk ^ (r & 7)) << 4), *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
           }
         }
         if (!(p.dbg & 1)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
