@@ -128,13 +128,20 @@ def plan_buckets(numels: Sequence[int], bucket_elems: int) -> List[List[int]]:
     return buckets
 
 
+def _group_world(group=None) -> Tuple[int, int]:
+    """(rank, world size) INSIDE `group` (the default group when None)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
 def reduce_scatter_mean(flat: torch.Tensor, layout: FlatLayout, group=None) -> torch.Tensor:
     """Mean over ranks of `flat` [total], returning this rank's shard [total / W] (a new tensor)."""
-    rank, ws = world()
+    rank, ws = _group_world(group)
     lo, hi = layout.shard_bounds(rank)
     if ws == 1:
         return flat[lo:hi].clone()
-    if dist.get_backend(group) == "nccl":
+    if flat.is_cuda:  # NCCL path chosen from where the data lives, not from the backend's name
         out = torch.empty(layout.shard, dtype=flat.dtype, device=flat.device)
         dist.reduce_scatter_tensor(out, flat, op=dist.ReduceOp.SUM, group=group)
         return out.div_(ws)
@@ -145,11 +152,11 @@ def reduce_scatter_mean(flat: torch.Tensor, layout: FlatLayout, group=None) -> t
 
 def all_gather_flat(shard: torch.Tensor, layout: FlatLayout, out: torch.Tensor, group=None) -> torch.Tensor:
     """Concatenate every rank's shard into `out` [total]."""
-    rank, ws = world()
+    rank, ws = _group_world(group)
     if ws == 1:
         out.copy_(shard)
         return out
-    if dist.get_backend(group) == "nccl":
+    if shard.is_cuda:
         dist.all_gather_into_tensor(out, shard.contiguous(), group=group)
         return out
     parts = [torch.empty_like(shard) for _ in range(ws)]
@@ -167,13 +174,16 @@ class Zero1Step:
         -> all-gather of the updated shards -> parameters.
     `update_fn` owns the optimiser arithmetic and its state (`state` is a dict this object keeps per rank; on the GPU it is
     the fused AdamW kernel with fp32 moments - optimiser state per rank drops to 1/W, which is what lets cfg 5 fit:
-    SURVEY.md section 8e). The master copy of the shard is kept in `master_dtype` (fp32 by default)."""
+    SURVEY.md section 8e). The master copy of the shard is kept in `master_dtype` (fp32 by default).
+    This class is the backend-agnostic reference of the exchange (gloo tests on CPU); the product's step -
+    bucket-interleaved ownership, reduce-scatter overlapped with the backward, all-gather overlapped with the next
+    forward - is `train.TrainEngine.optimizer_step`."""
 
     def __init__(self, params: Sequence[torch.Tensor], update_fn, master_dtype=torch.float32, align: int = 8, group=None):
         self.params = list(params)
         self.update_fn = update_fn
         self.group = group
-        self.rank, ws = world()
+        self.rank, ws = _group_world(group)
         self.layout = FlatLayout([p.numel() for p in self.params], ws, align)
         dev = self.params[0].device
         self.flat_grad = torch.zeros(self.layout.total, dtype=self.params[0].dtype, device=dev)
