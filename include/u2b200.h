@@ -353,6 +353,19 @@ U2_API int u2_sample_f32(const float* logits, int64_t* out, int32_t B, int32_t V
                          int32_t top_k, float top_p, uint64_t seed, const int32_t* step_dev, int32_t step,
                          void* stream);
 
+/* Same head with its parameters in DEVICE memory (24 bytes): a decode step captured in a CUDA graph reads them at
+ * replay time, so a new seed / temperature / top-k / top-p per request (HF generate kwargs) needs one small
+ * host-to-device copy, not a new capture. The caller validates temperature > 0 and 0 < top_p <= 1. */
+typedef struct u2_sample_params {
+  float temperature;
+  int32_t top_k;
+  float top_p;
+  int32_t reserved;
+  uint64_t seed;
+} u2_sample_params;
+U2_API int u2_sample_dev_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld,
+                             const u2_sample_params* params_dev, const int32_t* step_dev, int32_t step, void* stream);
+
 /* Fused lm_head + selective log-softmax (the DPO / SFT log-probability head) -----------------------------------
  * logp[r] = log_softmax(hidden[r] . W^T)[labels[r]]  (0 where labels[r] < 0) without materialising the [R, V] logits:
  * the GEMM's epilogue reduces every 128-column half tile to (max, sum exp, sum) per row, a second small kernel merges

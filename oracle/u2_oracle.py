@@ -188,12 +188,31 @@ def rope_mha(sd: SD, pre: str, x: torch.Tensor, h: int) -> torch.Tensor:
     return _lin(ctx.permute(0, 2, 1, 3).reshape(b, s, e), sd, pre + "dense")
 
 
+def mha_seq_first(sd: SD, pre: str, x: torch.Tensor, h: int) -> torch.Tensor:
+    """The fallback of src/model/u2tokenizer/svr.py:17-18 and tta.py:83-84: any attn_type other than "rma" /
+    "rope" builds torch.nn.MultiheadAttention(E, heads) with its default batch_first=False and calls it as
+    attn(x, x, x), so dim 0 of x is the SEQUENCE and dim 1 the batch: spatial attention mixes the (batch, frame)
+    axis per token, temporal attention mixes (batch, token) per frame, the TTA self-attention mixes the batch
+    samples per query. Restated from the published module (packed in_proj_weight [3E, E] = q | k | v, in_proj_bias,
+    out_proj, scale 1/sqrt(dh), no mask, dropout 0)."""
+    a, bt, e = x.shape
+    dh = e // h
+    qkv = x @ sd[pre + "in_proj_weight"].to(x.dtype).T + sd[pre + "in_proj_bias"].to(x.dtype)
+    q, k, v = (t.reshape(a, bt, h, dh).permute(1, 2, 0, 3) for t in qkv.split(e, dim=-1))  # [bt, h, a, dh]
+    if USE_SDPA:
+        ctx = _sdpa(q, k, v, 1.0 / math.sqrt(dh))
+    else:
+        ctx = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dh), dim=-1) @ v
+    ctx = ctx.permute(2, 0, 1, 3).reshape(a, bt, e)
+    return ctx @ sd[pre + "out_proj.weight"].to(x.dtype).T + sd[pre + "out_proj.bias"].to(x.dtype)
+
+
 def self_attn(sd: SD, pre: str, x: torch.Tensor, h: int, attn_type: str) -> torch.Tensor:
     if attn_type == "rma":
         return rma(sd, pre, x, h)
     if attn_type == "rope":
         return rope_mha(sd, pre, x, h)
-    raise NotImplementedError(f"attn_type={attn_type!r}: only 'rma' and 'rope' are restated")
+    return mha_seq_first(sd, pre, x, h)
 
 
 def cross_attn(sd: SD, pre: str, q_in: torch.Tensor, kv_in: torch.Tensor, h: int,

@@ -45,7 +45,7 @@ def test_encode_images(ptype):
 
 
 @pytest.mark.parametrize("attn_type,dmtp,multi", [("rma", True, True), ("rope", True, True), ("rma", False, True),
-                                                   ("rma", False, False)])
+                                                   ("rma", False, False), ("mha", True, True)])
 def test_u2tokenizer(attn_type, dmtp, multi):
     g = tiny_geometry(attn_type=attn_type, enable_dmtp=dmtp, use_multi_scale=multi)
     eng, sd = build(g, 2)
@@ -57,7 +57,7 @@ def test_u2tokenizer(attn_type, dmtp, multi):
     check(eng.u2tokenizer(v.cuda(), t.cuda()), ref, what="u2tokenizer")
 
 
-@pytest.mark.parametrize("attn_type", ["rma", "rope"])
+@pytest.mark.parametrize("attn_type", ["rma", "rope", "mha"])  # "mha" = the nn.MultiheadAttention fallback
 def test_u2tokenizer_vs_reference_golden(attn_type):
     """CUDA path against the committed outputs of the REFERENCE u2Tokenizer (tests/golden)."""
     from make_golden import golden_geometry
@@ -69,6 +69,21 @@ def test_u2tokenizer_vs_reference_golden(attn_type):
     v = torch.randn(2, 3, g.tokens_per_frame, g.hidden_size, generator=gen).bfloat16()
     t = torch.randn(2, 24, g.hidden_size, generator=gen).bfloat16()
     check(eng.u2tokenizer(v.cuda(), t.cuda()), gold[f"u2tok_{attn_type}_11"], what="golden u2tokenizer")
+
+
+@pytest.mark.parametrize("B,C,E", [(1, 4, 128), (3, 2, 512), (1, 1, 128)])
+def test_u2tokenizer_mha_fallback_shapes(B, C, E):
+    """attn_type outside {"rma", "rope"} -> torch.nn.MultiheadAttention called sequence-first (reference svr.py:17-18,
+    tta.py:83-84): one study (no regrouping copy), three studies (frame-major regrouping), head_dim 64 (the fused
+    attention kernel on transposed views) and the degenerate single-frame / single-sample sequences of length 1."""
+    g = tiny_geometry(attn_type="mha", hidden_size=E, intermediate_size=2 * E, head_dim=E // 4)
+    eng, sd = build(g, 5)
+    gen = torch.Generator().manual_seed(2)
+    v = torch.randn(B, C, g.tokens_per_frame, E, generator=gen).bfloat16()
+    t = torch.randn(B, 7, E, generator=gen).bfloat16()
+    with torch.no_grad():
+        ref = O.u2tokenizer(sd, "model.u2tokenizer.", v.float(), t.float(), g)
+    check(eng.u2tokenizer(v.cuda(), t.cuda()), ref, what=f"mha fallback B={B} C={C} E={E}")
 
 
 @pytest.mark.parametrize("family", ["qwen3", "llama"])

@@ -23,7 +23,8 @@ def golden_u2tok_inputs(g):
     return v, t
 
 
-@pytest.mark.parametrize("attn_type,diffts,dmtp", [("rma", True, True), ("rope", True, True), ("rma", False, False)])
+@pytest.mark.parametrize("attn_type,diffts,dmtp", [("rma", True, True), ("rope", True, True), ("rma", False, False),
+                                                     ("mha", True, True)])
 def test_oracle_u2tokenizer_vs_golden(attn_type, diffts, dmtp):
     g = golden_geometry()
     g.attn_type, g.enable_diffts, g.enable_dmtp = attn_type, diffts, dmtp

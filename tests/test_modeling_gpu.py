@@ -95,8 +95,14 @@ def test_sampled_generate_surface():
     kw = dict(question_ids=qids.cuda(), max_new_tokens=8, do_sample=True, top_p=0.9, temperature=1.0)
     a = model.generate(images.cuda(), ids.cuda(), seed=11, **kw).cpu()
     b = model.generate(images.cuda(), ids.cuda(), seed=11, **kw).cpu()
+    st = model.engine()._gen_state
+    graph = st["graph"]
     c = model.generate(images.cuda(), ids.cuda(), seed=12, **kw).cpu()
     assert a.shape == (2, 8) and torch.equal(a, b) and not torch.equal(a, c)
+    # seed / temperature / top-p live in a device block: a new request replays the SAME captured decode graph
+    d = model.generate(images.cuda(), ids.cuda(), seed=12, **dict(kw, temperature=0.5, top_p=0.5)).cpu()
+    assert graph is not None and model.engine()._gen_state is st and st["graph"] is graph
+    assert d.shape == (2, 8)
     greedy = model.generate(images.cuda(), ids.cuda(), question_ids=qids.cuda(), max_new_tokens=8, do_sample=False).cpu()
     tiny_nucleus = model.generate(images.cuda(), ids.cuda(), question_ids=qids.cuda(), max_new_tokens=8, do_sample=True,
                                   top_p=1e-6, temperature=1.0, seed=5).cpu()

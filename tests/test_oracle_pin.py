@@ -21,7 +21,7 @@ def _sub(sd, prefix):
 
 
 @needs_ref
-@pytest.mark.parametrize("attn_type", ["rma", "rope"])
+@pytest.mark.parametrize("attn_type", ["rma", "rope", "mha"])  # "mha": any other string -> nn.MultiheadAttention
 @pytest.mark.parametrize("diffts,dmtp,multi", [(True, True, True), (False, False, True), (True, False, False)])
 def test_u2tokenizer_matches_reference(attn_type, diffts, dmtp, multi):
     refshim.install()

@@ -42,7 +42,7 @@ def main():
     from src.model.multimodal_projector.spatial_pooling_projector import SpatialPoolingProjector
     os.makedirs(OUT, exist_ok=True)
     gold = {}
-    for attn_type, diffts, dmtp in (("rma", True, True), ("rope", True, True), ("rma", False, False)):
+    for attn_type, diffts, dmtp in (("rma", True, True), ("rope", True, True), ("rma", False, False), ("mha", True, True)):
         g = golden_geometry()
         g.attn_type, g.enable_diffts, g.enable_dmtp = attn_type, diffts, dmtp
         sd = fp32_sd(g, seed=11)

@@ -218,6 +218,7 @@ SIGNATURES = {
     "u2_decode_embed_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
     "u2_flash_attention_d64_bf16": (C.c_int, [_P, _P, _P, _P, C.POINTER(FaDesc), _P]),
     "u2_sample_f32": (C.c_int, [_P, _P, _I, _I, _L, _F, _I, _F, C.c_uint64, _P, _I, _P]),
+    "u2_sample_dev_f32": (C.c_int, [_P, _P, _I, _I, _L, _P, _P, _I, _P]),
     "u2_topk_rows_f32": (C.c_int, [_P, _P, _I, _I, _I, _L, _L, _P]),
     "u2_dlinear_ws_elems": (C.c_int64, [_I, _I]),
     "u2_dlinear_multi_bf16": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _P]),

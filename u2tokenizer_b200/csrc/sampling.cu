@@ -47,9 +47,17 @@ __device__ __forceinline__ unsigned int mix32(unsigned int x) {
 
 __global__ void __launch_bounds__(kSampThreads)
 sample_kernel(const float* __restrict__ logits, long long ld, int V, float inv_temp, int top_k, float top_p,
-              unsigned long long seed, const int* __restrict__ step_dev, int step_host, long long* __restrict__ out) {
+              unsigned long long seed, const u2_sample_params* __restrict__ pdev, const int* __restrict__ step_dev,
+              int step_host, long long* __restrict__ out) {
   __shared__ float red[kSampThreads / 32];
   __shared__ float s_scan[kSampThreads];
+  if (pdev) {
+    // parameters live in device memory: a captured CUDA graph keeps replaying while the host changes them
+    inv_temp = 1.0f / pdev->temperature;
+    top_k = pdev->top_k;
+    top_p = pdev->top_p;
+    seed = pdev->seed;
+  }
   const int b = blockIdx.x;
   const float* l = logits + (long long)b * ld;
   const int tid = threadIdx.x;
@@ -147,7 +155,19 @@ extern "C" U2_API int u2_sample_f32(const float* logits, int64_t* out, int32_t B
   if (!(temperature > 0.f)) return set_error(U2_ERR_ARG, "sample: temperature must be > 0");
   if (!(top_p > 0.f) || top_p > 1.f) return set_error(U2_ERR_ARG, "sample: top_p must be in (0, 1]");
   sample_kernel<<<B, kSampThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, ld, V, 1.0f / temperature, top_k, top_p, seed, step_dev, step, reinterpret_cast<long long*>(out));
+      logits, ld, V, 1.0f / temperature, top_k, top_p, seed, nullptr, step_dev, step, reinterpret_cast<long long*>(out));
   U2_CHECK_LAUNCH("sample");
+  return U2_OK;
+}
+
+extern "C" U2_API int u2_sample_dev_f32(const float* logits, int64_t* out, int32_t B, int32_t V, int64_t ld,
+                                        const u2_sample_params* params_dev, const int32_t* step_dev, int32_t step,
+                                        void* stream) {
+  using namespace u2;
+  if (!logits || !out || !params_dev) return set_error(U2_ERR_ARG, "sample_dev: null pointer");
+  if (B <= 0 || V <= 0) return U2_OK;
+  sample_kernel<<<B, kSampThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, ld, V, 1.0f, 0, 1.0f, 0ull, params_dev, step_dev, step, reinterpret_cast<long long*>(out));
+  U2_CHECK_LAUNCH("sample_dev");
   return U2_OK;
 }

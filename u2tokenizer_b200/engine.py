@@ -58,12 +58,13 @@ class _Take:
 
 
 @dataclass
-class _SelfAttnW:  # RelativeMultiheadAttention / RotaryMultiheadAttention
+class _SelfAttnW:  # RelativeMultiheadAttention / RotaryMultiheadAttention / the nn.MultiheadAttention fallback
     wqkv: torch.Tensor
     bqkv: torch.Tensor
     wd: torch.Tensor
     bd: torch.Tensor
     rel: Optional[torch.Tensor]
+    seq_first: bool = False  # nn.MultiheadAttention with batch_first=False: dim 0 of the input is the sequence
 
 
 @dataclass
@@ -103,8 +104,6 @@ class U2Engine:
         self.l2_next_units = int(os.environ.get("U2_L2_NEXT", "-1"))            # x16 KB per CTA of the next gate|up
         if geom.vision_select_feature != "patch":
             raise NotImplementedError("only vision_select_feature='patch' is supported (the spp projector needs it)")
-        if geom.attn_type not in ("rma", "rope"):
-            raise NotImplementedError(f"attn_type={geom.attn_type!r}: 'rma' and 'rope' are implemented")
         t = _Take(dict(state_dict), self.dev)
         self._prep_vit(t)
         self._prep_projector(t)
@@ -114,6 +113,8 @@ class U2Engine:
         self._gen_state = None
         self._fwd_state = None
         self._sampling = None
+        self._samp_dev = None   # 24-byte u2_sample_params block in device memory (read by the captured decode graph)
+        self._samp_host = None
 
     # =========================================================================================
     # weight preparation
@@ -148,6 +149,12 @@ class U2Engine:
             self.proj.append((t.bf(p + f"{idx}.weight"), t.f32(p + f"{idx}.bias")))
 
     def _self_attn_w(self, t: _Take, pre: str) -> _SelfAttnW:
+        if self.g.attn_type not in ("rma", "rope"):
+            # any other attn_type is torch.nn.MultiheadAttention in the reference (svr.py:17-18, tta.py:83-84):
+            # packed q | k | v projection, called sequence-first
+            return _SelfAttnW(wqkv=t.bf(pre + "in_proj_weight"), bqkv=t.f32(pre + "in_proj_bias"),
+                              wd=t.bf(pre + "out_proj.weight"), bd=t.f32(pre + "out_proj.bias"), rel=None,
+                              seq_first=True)
         rel = t.f32(pre + "relative_bias") if self.g.attn_type == "rma" else None
         return _SelfAttnW(
             wqkv=t.cat_bf([pre + "wq.weight", pre + "wk.weight", pre + "wv.weight"]),
@@ -346,7 +353,13 @@ class U2Engine:
             ops.rope(qkv, rows=nb * S, ld=3 * E, dh=dh, n_q=H, n_k=H, inv_freq=self.u2t_inv_freq, pos_div=1, pos_mod=S)
         q5 = qkv.view(nb, S, 3, H, dh)
         ctx = torch.empty(nb, S, E, device=self.dev, dtype=BF16)
-        self._attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], ctx, 1.0 / math.sqrt(dh), rel_bias=w.rel)
+        if w.seq_first:
+            # nn.MultiheadAttention fallback: the reference hands it [nb, S, E] with batch_first=False, so the attention
+            # runs ALONG dim 0 (length nb) for each of the S positions: the same kernels on transposed views, no copies
+            q5, ctx_v = q5.transpose(0, 1), ctx.transpose(0, 1)
+            self._attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], ctx_v, 1.0 / math.sqrt(dh))
+        else:
+            self._attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], ctx, 1.0 / math.sqrt(dh), rel_bias=w.rel)
         return ops.linear(ctx.view(nb * S, E), w.wd, w.bd, residual=residual)
 
     def _u2t_temporal_attention(self, x2: torch.Tensor, B: int, C: int, N: int, w: _SelfAttnW) -> torch.Tensor:
@@ -356,6 +369,18 @@ class U2Engine:
         E, H = g.hidden_size, g.u2t_num_heads
         dh = E // H
         qkv = ops.linear(x2, w.wqkv, w.bqkv)
+        if w.seq_first:
+            # nn.MultiheadAttention fallback: the reference's [B*N, C, E] input is read sequence-first, i.e. attention
+            # over the B*N (batch, token) pairs of every frame c. Rows are (b, c, n): for B = 1 that is plain attention
+            # with the frames as the batch; B > 1 regroups the rows frame-major (the one copy this rare path pays).
+            if B > 1:
+                qkv = qkv.view(B, C, N, 3 * E).transpose(0, 1).contiguous()
+            q5 = qkv.view(C, B * N, 3, H, dh)
+            ctx = torch.empty(C, B * N, E, device=self.dev, dtype=BF16)
+            self._attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], ctx, 1.0 / math.sqrt(dh))
+            if B > 1:
+                ctx = ctx.view(C, B, N, E).transpose(0, 1).contiguous()
+            return ops.linear(ctx.view(B * C * N, E), w.wd, w.bd)
         if g.attn_type == "rope":
             ops.rope(qkv, rows=B * C * N, ld=3 * E, dh=dh, n_q=H, n_k=H, inv_freq=self.u2t_inv_freq, pos_div=N, pos_mod=C)
         ctx = torch.empty(B * C * N, E, device=self.dev, dtype=BF16)
@@ -679,8 +704,20 @@ class U2Engine:
         if sp is None:
             ops.argmax(logits, ids_out)
         else:
-            ops.sample(logits, ids_out, temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"],
-                       seed=sp["seed"], step=step, step_dev=step_dev)
+            # parameters (seed included) are read from a device block: the captured decode graph survives a new
+            # request's seed / temperature / top-k / top-p
+            ops.sample_dev(logits, self._sampling_block(sp), ids_out, step=step, step_dev=step_dev)
+
+    def _sampling_block(self, sp: dict) -> torch.Tensor:
+        cur = tuple(sorted(sp.items()))
+        if self._samp_dev is None:
+            self._samp_dev = ops.sample_params(self.dev, sp["temperature"], sp["top_k"], sp["top_p"], sp["seed"])
+        elif self._samp_host != cur:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("sampling parameters changed inside a CUDA-graph capture")
+            ops.sample_params(self.dev, sp["temperature"], sp["top_k"], sp["top_p"], sp["seed"], out=self._samp_dev)
+        self._samp_host = cur
+        return self._samp_dev
 
     def decode_step(self, cache: "KVCache") -> torch.Tensor:
         """Consumes buffers['ids'] [B,1] (the last token of every sequence), appends to the cache at
@@ -743,8 +780,7 @@ class U2Engine:
     def _gen_state_for(self, B: int, cap: int):
         """The static KV cache and the captured decode-step graph are kept across calls with the same (batch, capacity,
         head configuration): capture + instantiation cost ~0.1 s, which would otherwise be paid per request."""
-        key = (B, cap, self.decode_impl, self.multi_op, self.fine_deps,
-               tuple(sorted(self._sampling.items())) if self._sampling else None)
+        key = (B, cap, self.decode_impl, self.multi_op, self.fine_deps, self._sampling is not None)
         st = self._gen_state if (self._gen_state is not None and self._gen_state["key"] == key) else None
         if st is None:
             self._gen_state = None  # drop the old cache before allocating the new one

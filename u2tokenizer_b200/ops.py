@@ -521,6 +521,38 @@ def sample(logits: torch.Tensor, out: Optional[torch.Tensor] = None, *, temperat
     return out
 
 
+def sample_params(device, temperature: float, top_k: int, top_p: float, seed: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The 24-byte u2_sample_params block (include/u2b200.h) in device memory: temperature f32, top_k i32, top_p f32,
+    pad, seed u64. `out` (a block made earlier) is overwritten in place, which is how a captured decode graph gets new
+    sampling parameters without a new capture."""
+    import struct
+    if not temperature > 0:
+        raise ValueError("sample: temperature must be > 0")
+    if not 0 < top_p <= 1:
+        raise ValueError("sample: top_p must be in (0, 1]")
+    raw = struct.pack("<fifiQ", float(temperature), int(top_k), float(top_p), 0, int(seed) & ((1 << 64) - 1))
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    if out is None:
+        return host.to(device)
+    out.copy_(host)
+    return out
+
+
+def sample_dev(logits: torch.Tensor, params: torch.Tensor, out: Optional[torch.Tensor] = None, *, step: int = 0,
+               step_dev=None) -> torch.Tensor:
+    """ops.sample with the parameters read from a device block made by sample_params()."""
+    _need_cuda(logits, params, step_dev)
+    B, V = logits.shape
+    if params.dtype != torch.uint8 or params.numel() != 24:
+        raise ValueError("sample_dev: params must be the 24-byte block of sample_params()")
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    _lib.check(_lib.load().u2_sample_dev_f32(logits.data_ptr(), out.data_ptr(), B, V, logits.stride(0), params.data_ptr(),
+                                             _ptr(step_dev), int(step), _stream()), "u2_sample_dev_f32")
+    return out
+
+
 def lmhead_logprob(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, *, want_lse: bool = False,
                    want_logit_sum: bool = False, nll_acc: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None):
     """logp[r] = log_softmax(hidden[r] @ weight.T)[labels[r]] (0 where labels[r] < 0) without materialising the logits.

@@ -45,6 +45,11 @@ def param_shapes(g: Geometry) -> Dict[str, Tuple[int, ...]]:
         s[u + "query_tokens"] = (1, g.num_3d_query_token, E)
 
         def mha(pre, rel):
+            if rel and g.attn_type not in ("rma", "rope"):
+                # torch.nn.MultiheadAttention fallback (reference svr.py:17-18, tta.py:83-84)
+                s[pre + "in_proj_weight"] = (3 * E, E); s[pre + "in_proj_bias"] = (3 * E,)
+                s[pre + "out_proj.weight"] = (E, E); s[pre + "out_proj.bias"] = (E,)
+                return
             for n in ("wq", "wk", "wv", "dense"):
                 s[f"{pre}{n}.weight"] = (E, E); s[f"{pre}{n}.bias"] = (E,)
             if rel and g.attn_type == "rma":
