@@ -529,15 +529,21 @@ def train_batch(geom, spec, rank, world):
     return images, ids, qids, labels, mask
 
 
-def run_train_steps(te, spec, geom, batch, steps, warmup, dist=None, ref_model=None):
+def run_train_steps(te, spec, geom, batch, steps, warmup, dist=None, ref_model=None, e2e=False):
     """W warm-up + K timed optimizer steps; per-phase device times (CUDA events on the compute stream):
     forward | backward (with the overlapped reduce-scatters in flight) | exposed gradient exchange (what is left of the
-    reduce-scatter when the backward's last kernel has finished) | clip + fused AdamW + all-gather."""
+    reduce-scatter when the backward's last kernel has finished) | clip + fused AdamW + all-gather.
+    e2e: a second timed loop of K steps in which every step copies its batch from PINNED HOST memory (what a DataLoader
+    with pin_memory hands over) and reads the loss back to the host; returned as the 5th element (ms, bytes in, bytes out)."""
     from u2tokenizer_b200 import _lib, parallel
     images, ids, qids, labels, mask = [t.cuda() for t in batch]
     beta = 0.1
+    host = [t.contiguous().pin_memory() for t in batch] if e2e else None
 
-    def step(ev=None):
+    def step(ev=None, from_host=False):
+        nonlocal images, ids, qids, labels, mask
+        if from_host:
+            images, ids, qids, labels, mask = [t.cuda(non_blocking=True) for t in host]
         te.zero_grad()
         if ev: ev[0].record()
         if spec["mode"] == "dpo":
@@ -583,7 +589,22 @@ def run_train_steps(te, spec, geom, batch, steps, warmup, dist=None, ref_model=N
     names = ("ref_forward" if spec["mode"] == "dpo" else "forward", "policy_fwd_bwd" if spec["mode"] == "dpo" else "backward",
              "exposed_reduce_scatter", "clip_adamw")   # the parameter all-gather overlaps the next step's forward
     phases = {n: round(parallel.max_over_ranks(v, device="cuda"), 3) for n, v in zip(names, ph)}
-    return ms, _lib.launches() - n0, phases, out
+    n_launch = _lib.launches() - n0
+    if not e2e:
+        return ms, n_launch, phases, out
+    barrier()
+    e0.record()
+    d2h = 0
+    for i in range(steps):
+        o = step(from_host=True)
+        o = o.float().cpu()             # the loss (DPO: loss / reward accuracy / margin) back on the host, every step
+        d2h = o.numel() * 4
+    te.sync_params()
+    e1.record()
+    barrier()
+    ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    return ms, n_launch, phases, out, (ms_e2e, h2d, d2h)
 
 
 def train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist):
@@ -609,7 +630,8 @@ def train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, launches, phases, out = run_train_steps(te, spec, geom, batch, args.steps, max(args.warmup, 3), dist, ref_model)
+    ms, launches, phases, out, (ms_e2e, h2d, d2h) = run_train_steps(te, spec, geom, batch, args.steps, max(args.warmup, 3), dist,
+                                                                    ref_model, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -631,8 +653,10 @@ def train_main(args, cfg, geom, spec, base, rank, local_rank, world, dist):
                                "achieved": round(step_fl / (compute_ms / 1e3) / 1e12, 1), "peak": tf, "unit": "TFLOP/s",
                                "frac": round(step_fl / (compute_ms / 1e3) / 1e12 / tf, 4), "traffic": None, "peak_source": src,
                                "flops_per_step": step_fl, "note": "algorithmic FLOPs of forward + backward per rank / (forward + backward ms)"},
-                  "e2e": {"value": None, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                          "note": "training batches are staged on the device by the loader; see the generate workload for e2e"}})
+                  "e2e": {"value": round(world * B * args.steps / (ms_e2e / 1e3), 4), "unit": "volumes/s",
+                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3),
+                          "note": "every step copies its batch (fp32 volumes, ids, labels / masks) from pinned host memory and "
+                                  "reads the loss back; h2d / d2h bytes are per rank"}})
     out_d["scaling"] = "weak"
     out_d["config"]["parallelism"] = f"dp{world}: ZeRO-1 (bucketed NCCL reduce-scatter overlapped with the backward, sharded fused AdamW, all-gather)"
     print(json.dumps(out_d), flush=True)
@@ -656,7 +680,7 @@ def train_substep(model, rank, local_rank, world, dist, steps=3, warmup=3):
         mom = torch.float32 if te.lay.mat_total / world * 12 + 40e9 < free else torch.bfloat16
         te.init_optimizer(lr=4e-6, weight_decay=0.0, max_grad_norm=1.0, moment_dtype=mom)
         batch = train_batch(geom4, spec4, rank, world)
-        ms, launches, phases, out = run_train_steps(te, spec4, geom4, batch, steps, warmup, dist)
+        ms, launches, phases, out, (ms_e2e, h2d, d2h) = run_train_steps(te, spec4, geom4, batch, steps, warmup, dist, e2e=True)
         n_tok = batch[1].shape[0] * batch[1].shape[1]
         fwd_fl, step_fl = train_flops(geom4, batch[1].shape[0], spec4["frames"], spec4["seq"], spec4["lt"])
         hbm, tf, src = measured_peaks()
@@ -668,6 +692,8 @@ def train_substep(model, rank, local_rank, world, dist, steps=3, warmup=3):
                 "value": round(world * spec4["batch"] * steps / (ms / 1e3), 4), "unit": "volumes/s", "ms_per_step": round(per, 3),
                 "tokens_per_sec": round(world * n_tok * steps / (ms / 1e3), 1), "phases_ms": phases, "steps": steps, "warmup": warmup,
                 "gpu_launches": int(launches), "loss": float(out),
+                "e2e": {"value": round(world * spec4["batch"] * steps / (ms_e2e / 1e3), 4), "unit": "volumes/s",
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "optimizer": f"AdamW, ZeRO-1 over {world} rank(s), fp32 master, {str(mom).split('.')[-1]} moments, "
                              f"{te.lay.n_buckets} buckets of {te.lay.bucket} bf16 gradients",
                 "tensor_frac_fwd_bwd": round(step_fl / (comp / 1e3) / 1e12 / tf, 4), "flops_per_step": step_fl}

@@ -128,10 +128,19 @@ __device__ __forceinline__ float4 ld_relaxed_f4(const float4* p) {
 }
 
 // single-thread poll (relaxed loads: one L2 round trip each), acquire fence once the target is reached
+// The barrier needs every CTA of the grid to be resident (grid = #SMs, one CTA per SM: checked on the host against
+// the occupancy calculator). If something outside this library takes SMs away for good (an MPS active-thread limit,
+// a kernel of another context that never ends), the missing CTAs never arrive: after ~2^24 L2 round trips (seconds;
+// a healthy wait is tens of microseconds) the poller traps, so the step fails loudly instead of hanging the GPU.
 __device__ __forceinline__ void grid_barrier_wait(const unsigned int* bar, unsigned int target) {
-  unsigned int v;
+  unsigned int v, spins = 0;
   do {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    if (++spins == (1u << 24)) {
+      printf("u2 dlinear: grid barrier timed out (CTA %d sees %u of %u arrivals): CTAs of the launch are not co-resident\n",
+             (int)blockIdx.x, v, target);
+      __trap();
+    }
   } while (v < target);
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -702,6 +711,12 @@ static int launch_multi_t(DlinMulti& mp, int pdl, cudaStream_t stream) {
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dlinear_tcgen05_kernel<kM>, cudaFuncAttributeMaxDynamicSharedMemorySize, DlCfg<kM>::kSmem);
     if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "dlinear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    // the software grid barrier between the chained linears needs grid <= resident CTA capacity
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dlinear_tcgen05_kernel<kM>, kDlThreads, DlCfg<kM>::kSmem);
+    if (e != cudaSuccess || per_sm < 1)
+      return set_error(U2_ERR_CUDA, "dlinear: kernel cannot be resident on an SM (%s, %d CTA/SM): set U2_MULTI_OP=0",
+                       cudaGetErrorString(e), per_sm);
     configured = true;
   }
   int grid = num_sms();

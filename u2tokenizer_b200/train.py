@@ -152,6 +152,14 @@ class TrainEngine:
         self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         self._pending = None
         self._ag_ev = [None] * self.lay.n_buckets   # all-gather completion events of the previous optimizer step
+        # Matrix gradients are not zero-filled per step: the first wgrad of a step OVERWRITES its slot (no memset of
+        # the 2 bytes / parameter buffer, no accumulating read in the GEMM epilogue), later writers accumulate.
+        # _gm_written: names written since zero_grad(); _gm_dirty: names whose slot holds a gradient of any step (a
+        # dirty slot that a step does not write is zeroed when its segment's marker fires, see _mark / run_backward).
+        self._gm_written = set()
+        self._gm_dirty = set()
+        self._gm_offs = sorted((L.mat_off[n], n) for n in L.mat_names)
+        self._gm_names_cache = {}
 
     # =========================================================================================
     # flat-buffer views
@@ -221,9 +229,67 @@ class TrainEngine:
         if self.tied and "lm_head.weight" in sd_names:
             sd_names["lm_head.weight"].data = self.w("model.embed_tokens.weight")
 
-    def zero_grad(self):
-        self.Gm.zero_()
+    def zero_grad(self, set_to_zero: bool = False, keep=()):
+        """Start a new gradient: the fp32 vector gradients are cleared; the matrix slots are overwritten by their first
+        writer of the step (set_to_zero=True also clears them now, e.g. before reading gradients of a partial pass).
+        keep: matrix names whose slots already hold a gradient that this pass must ADD to (micro-batch accumulation
+        when the module's p.grad aliases the slot)."""
         self.Gv.zero_()
+        self._gm_written = set(keep)
+        self._gm_dirty.update(keep)
+        if set_to_zero:
+            assert not keep
+            self.Gm.zero_()
+            self._gm_dirty = set()
+
+    def _gm_names(self, gw: torch.Tensor):
+        """Parameter names covered by a matrix-gradient view (a single matrix or a fused group of adjacent ones)."""
+        off = (gw.data_ptr() - self.Gm.data_ptr()) // 2
+        key = (off, gw.numel())
+        names = self._gm_names_cache.get(key)
+        if names is None:
+            import bisect
+            i = bisect.bisect_left(self._gm_offs, (off, ""))
+            names = []
+            while i < len(self._gm_offs) and self._gm_offs[i][0] < off + gw.numel():
+                names.append(self._gm_offs[i][1])
+                i += 1
+            assert names and self.lay.mat_off[names[0]] == off, "gradient view does not start at a parameter"
+            self._gm_names_cache[key] = names = tuple(names)
+        return names
+
+    def _gm_begin_write(self, gw: torch.Tensor) -> bool:
+        """Called right before a kernel writes the matrix-gradient view `gw`. Returns True when the kernel has to
+        ACCUMULATE (the slot already holds a contribution of this step), False when it may overwrite."""
+        names = self._gm_names(gw)
+        fresh = [n for n in names if n not in self._gm_written]
+        self._gm_written.update(names)
+        self._gm_dirty.update(names)
+        if len(fresh) == len(names):
+            return False
+        for n in fresh:   # a fused view after one of its members was written on its own: clear the others, then add
+            self.gm(n).zero_()
+        return True
+
+    def _gm_clear_stale(self, names):
+        """Slots that hold an earlier step's gradient but were not written in this one (a parameter that dropped out of
+        the graph) must read as zero before they are reduced / consumed."""
+        for n in names:
+            if n in self._gm_dirty and n not in self._gm_written:
+                self.gm(n).zero_()
+                self._gm_dirty.discard(n)
+
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor):
+        """gw (+)= dy^T x on the tensor cores; the first write of a step overwrites."""
+        T.linear_wgrad(dy, x, gw, accumulate=self._gm_begin_write(gw))
+
+    def _gm_scatter_target(self, name: str) -> torch.Tensor:
+        """Gradient slot for a kernel that ADDS into it (embedding scatter): cleared first when this is the step's first
+        writer."""
+        gw = self.gm(name)
+        if not self._gm_begin_write(gw):
+            gw.zero_()
+        return gw
 
     # =========================================================================================
     # tape helpers
@@ -265,6 +331,7 @@ class TrainEngine:
         self._wait_params(names)
 
         def done():
+            self._gm_clear_stale(names)
             if self._pending is None:
                 return
             for n in names:
@@ -290,7 +357,7 @@ class TrainEngine:
             if dy is None:
                 return
             if gw is not None:
-                T.linear_wgrad(dy, x.v, gw, accumulate=True)
+                self.wgrad(dy, x.v, gw)
             if gbias is not None:
                 T.colsum(dy, gbias)
             if x.ng:
@@ -530,7 +597,7 @@ class TrainEngine:
                 return
             dx = x_emb.g.view(Fr, Sp, Hd)
             dy = dx[:, 1:1 + P].contiguous().view(Fr * P, Hd)
-            T.linear_wgrad(dy, rows, self.gm(v + "patch_embedding.patch_embeddings.1.weight"), accumulate=True)
+            self.wgrad(dy, rows, self.gm(v + "patch_embedding.patch_embeddings.1.weight"))
             T.colsum(dy, self.gv(v + "patch_embedding.patch_embeddings.1.bias"))
             T.colsum(dy, self.gv(v + "patch_embedding.position_embeddings"), rows=Fr, cols=P * Hd, ld=P * Hd)
             T.colsum(dx, self.gv(v + "cls_token"), rows=Fr, cols=Hd, ld=Sp * Hd)
@@ -842,7 +909,7 @@ class TrainEngine:
 
         def bwd():
             if out.g is not None and self._tr("embed"):
-                T.embed_scatter_add(ids, out.g.contiguous(), self.gm("model.embed_tokens.weight"), None)
+                T.embed_scatter_add(ids, out.g.contiguous(), self._gm_scatter_target("model.embed_tokens.weight"), None)
             out.g = None
         self.tape.append(bwd)
         return out
@@ -860,8 +927,8 @@ class TrainEngine:
             if out.g is None:
                 return
             dvis = torch.empty(B * n_vis, E, device=self.dev, dtype=BF16) if (vis is not None and vis.ng) else None
-            T.embed_scatter_add(ids, out.g.contiguous(), self.gm("model.embed_tokens.weight") if self._tr("embed") else None,
-                                dvis, n_vis)
+            T.embed_scatter_add(ids, out.g.contiguous(),
+                                self._gm_scatter_target("model.embed_tokens.weight") if self._tr("embed") else None, dvis, n_vis)
             if dvis is not None:
                 self._acc(vis, dvis, owned=True)
             out.g = None
@@ -945,7 +1012,7 @@ class TrainEngine:
             dl = T.ce_bwd(logits, lse, lab.clamp_min(0), coef)
             del logits
             if trh:
-                T.linear_wgrad(dl, h2, self.gm(hname), accumulate=True)
+                self.wgrad(dl, h2, self.gm(hname))
             if hidden.ng:
                 self._acc(hidden, T.linear_dgrad(dl, Wh), owned=True)
         self.tape.append(bwd)
@@ -992,6 +1059,7 @@ class TrainEngine:
             fn()
         self.tape = []
         self._pending = None
+        self._gm_clear_stale(tuple(self._gm_dirty))   # whatever no marker covered
 
     def forward_loss(self, images, input_ids, question_ids, labels) -> torch.Tensor:
         """Forward half of the training step: HF ForCausalLMLoss of `model(images=, input_ids=, question_ids=, labels=)`
@@ -1012,8 +1080,9 @@ class TrainEngine:
         return -(logp.sum() / n_valid)
 
     def backward(self, grad_scale=1.0):
-        """Backward half: gradients are ACCUMULATED into Gm / Gv (zero_grad() per optimizer step). grad_scale: float or a
-        device scalar (the upstream gradient of the loss)."""
+        """Backward half: gradients go to Gm / Gv - the first matrix write after zero_grad() overwrites its slot, every
+        later one (a second backward() before the next zero_grad(): micro-batch accumulation) adds. grad_scale: float or
+        a device scalar (the upstream gradient of the loss)."""
         self._grad_scale = grad_scale
         self.run_backward()
 
