@@ -709,6 +709,51 @@ def train_substep(model, rank, local_rank, world, dist, steps=3, warmup=3):
         torch.cuda.empty_cache()
 
 
+def cfg2_forward_substep(steps=10, warmup=3):
+    """BASELINE configs[1] (cfg 2) next to the headline: mu2-Qwen3-1.7B, ONE 256 x 256 x 128 study (4 frames), 288-token
+    teacher-forced forward through model(images=, input_ids=, question_ids=) on one GPU. Device-resident and end-to-end
+    (pinned host inputs copied every step, the last position's argmax read back) timings, CUDA events."""
+    from u2tokenizer_b200 import _lib
+    from u2tokenizer_b200.synthetic import synthetic_inputs
+    cfg2, geom2, spec2 = make_geometry("cfg2")
+    m = build_model(cfg2, geom2)
+    try:
+        images, ids, qids = synthetic_inputs(geom2, batch=spec2["batch"], frames=spec2["frames"], n_question=spec2["n_question"],
+                                             lt=spec2["lt"], seed=1234)
+        h = [t.pin_memory() for t in (images, ids, qids)]
+        d = [t.cuda() for t in h]
+
+        def run(im, i, q):
+            return m(images=im, input_ids=i, question_ids=q).logits[:, -1].float().argmax(-1)
+
+        def timed(fn):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = _lib.launches()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, (_lib.launches() - n0) // steps
+        for _ in range(warmup):
+            run(*d)
+        ms, launches = timed(lambda: run(*d))
+        ms_e2e, _ = timed(lambda: run(*[t.cuda(non_blocking=True) for t in h]).cpu())
+        fwd_fl, _ = train_flops(geom2, spec2["batch"], spec2["frames"], ids.shape[1], spec2["lt"])
+        hbm, tf, src = measured_peaks()
+        return {"workload": "cfg2: mu2-Qwen3-1.7B forward, one 256x256x128 study (4 frames), 288-token sequence, 1 GPU",
+                "value": round(spec2["batch"] / (ms / 1e3), 3), "unit": "volumes/s", "ms_per_step": round(ms, 3), "steps": steps,
+                "warmup": warmup, "gpu_launches_per_step": int(launches),
+                "e2e": {"value": round(spec2["batch"] / (ms_e2e / 1e3), 3), "unit": "volumes/s",
+                        "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h)), "d2h_bytes_per_step": 8},
+                "tensor_frac": round(fwd_fl / (ms / 1e3) / 1e12 / tf, 4), "flops_per_step": fwd_fl,
+                "note": "repeated same-shape forwards replay one CUDA graph over static buffers (engine.forward_logits)"}
+    finally:
+        del m
+        torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -868,6 +913,11 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
+    if world == 1 and args.workload == "cfg3" and os.environ.get("U2_BENCH_CFG2", "1") != "0":
+        try:
+            out["cfg2_forward"] = cfg2_forward_substep()
+        except Exception as e:
+            out["cfg2_forward"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             del model

@@ -259,9 +259,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int zo_i = z / p.zi;
       const int zi_i = z - zo_i * p.zi;
 
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-
       const int row = m_blk * kBlockM + q * 32 + lane;  // row of the logical (M x N) output
       const bool row_ok = row < p.M;
       long long out_row = row;
@@ -274,6 +271,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
       const uint32_t taddr = tmem_base + acc * kBlockN + (static_cast<uint32_t>(q * 32) << 16);
       if constexpr (kMode == 1) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
         // log-softmax statistics of this thread's row over its half of the tile's columns; the logits never leave
         // the SM (reference dpo_u2trainer.py:289-300 materialises [rows, vocab] logits and log-softmaxes them)
         const long long lab = row_ok ? p.labels[row] : -1;
@@ -313,159 +312,206 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         // always written, also for a half tile that lies entirely past N: (-inf, 0, 0) is the merge's neutral element
         if (row_ok) p.part[(long long)(n_blk * 2 + half) * p.part_ld + row] = make_float4(mx, se, sx, 0.f);
+        // hand the accumulator buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       } else {
-#pragma unroll 1
-      for (int c0 = half * (kBlockN / 2); c0 < (half + 1) * (kBlockN / 2); c0 += 32) {
-        const int col0 = n_blk * kBlockN + c0;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        // operands that do not depend on the accumulator are requested BEFORE the TMEM load is waited for: the residual /
-        // position-table row segment (4 x 16 B per thread) is in flight while tcgen05.ld completes (the serial
-        // wait -> load -> wait chain per 32-column chunk made every short-K GEMM with a residual epilogue-bound)
-        const bool full = (col0 + 32 <= p.N);
-        const bool res_vec = row_ok && res_ptr && full && ((p.ldr & 7) == 0);
-        uint4 rres[4];
-        if (res_vec) {
+        // ---- software-pipelined drain of this warp's 32 rows x (kBlockN / 2) columns in 32-column chunks. A short-K GEMM
+        // (attention scores / dP with K = 64: ONE k-block per tile) is nothing but this loop, and with 8 warps per SM
+        // a serial  tcgen05.ld -> wait -> global loads -> math -> store  chain per chunk left the SM idle for most of
+        // the ~2000 cycles each chunk took (4.8 us per 128 x 256 tile, 76 - 108 TFLOP/s on those GEMMs). Now
+        //   * everything that does not depend on the accumulator (row vector, the first chunk's residual / P segment)
+        //     is requested BEFORE the wait for the MMA,
+        //   * chunk c + 1's TMEM load and its residual / P loads are issued right after chunk c's TMEM data arrived,
+        //     so they fly while chunk c is computed and stored,
+        //   * the accumulator buffer goes back to the MMA warp as soon as the last TMEM load has landed.
+        constexpr int kChunks = kBlockN / 64;  // 32-column chunks per half tile
+        const int colb = n_blk * kBlockN + half * (kBlockN / 2);
+        const bool ds_vec_ok = p.epi_op == U2_EPI_DS_ROW && (((p.ldc | zoff) & 7) == 0);
+        const bool res_vec_ok = res_ptr && p.epi_op != U2_EPI_DS_ROW && ((p.ldr & 7) == 0);
+        // 2: the P ("mul") segment is prefetched, 1: the residual segment is prefetched, 0: nothing / element-wise tail path
+        auto side_kind = [&](int col0) -> int {
+          if (!row_ok || col0 + 32 > p.N) return 0;
+          return ds_vec_ok ? 2 : (res_vec_ok ? 1 : 0);
+        };
+        auto side_load = [&](int col0, int kind, uint4 (&sd)[4]) {
+          if (kind == 0) return;
+          const __nv_bfloat16* src = (kind == 2) ? (p.mul + c_off + col0) : (res_ptr + col0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = *reinterpret_cast<const uint4*>(res_ptr + col0 + 8 * j);
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        if (row_ok && p.epi_op != U2_EPI_NONE) {
-          // attention backward: probabilities rebuilt from the row log-sum-exp / dS formed against the stored P
-          const float rv = __ldg(p.rowvec + (long long)zo_i * p.rv_zo + (long long)zi_i * p.rv_zi + row);
-          if (p.epi_op == U2_EPI_EXP_ROW) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - rv);
-          } else {
-            const __nv_bfloat16* mp = p.mul + c_off + col0;
-            if (full && (((p.ldc | zoff) & 7) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 r = *reinterpret_cast<const uint4*>(mp + j);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 rf = __bfloat1622float2(r2[e]);
-                  f[j + 2 * e] = rf.x * (f[j + 2 * e] - rv);
-                  f[j + 2 * e + 1] = rf.y * (f[j + 2 * e + 1] - rv);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                f[j] = (col0 + j < p.N) ? __bfloat162float(mp[j]) * (f[j] - rv) : 0.f;
-            }
-          }
-        }
-        if (row_ok) {
-          if (p.bias) {
-            if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (p.act != U2_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-          }
-          if (res_vec) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 rf = __bfloat1622float2(r2[e]);
-                f[8 * j + 2 * e] += rf.x;
-                f[8 * j + 2 * e + 1] += rf.y;
-              }
-            }
-          } else if (res_ptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
-          }
-          (void)0;
-        }
-        // ---- store. Fast path: the warp's 32 x 32 block goes through a swizzled shared-memory tile so that every store
-        // instruction writes whole 128-byte (fp32) / 64-byte (bf16) row segments; the thread-per-row pattern it replaces
-        // touched 32 half-used sectors per request, which bounded every short-K GEMM (attention scores, wgrad with few
-        // rows) by its epilogue.
-        const bool fast = (col0 + 32 <= p.N) &&
-                          (p.c_dtype == U2_DT_BF16 ? (((p.ldc | zoff) & 7) == 0) : (((p.ldc | zoff) & 3) == 0));
+          for (int j = 0; j < 4; ++j) sd[j] = *reinterpret_cast<const uint4*>(src + 8 * j);
+        };
         const uint32_t st = smem_u32(smem_epi) + (warp_idx - kEpiWarp0) * 4096;
         const int row0 = m_blk * kBlockM + q * 32;
-        if (fast) {
-          __syncwarp();  // the previous chunk's read-back is complete
-          if (p.c_dtype == U2_DT_BF16) {
+
+        uint32_t v[32];
+        uint4 sd[4];   // residual / P segment of the chunk in flight (requested as soon as the previous one is consumed)
+        int kind = 0;
+        const bool any = colb < p.N;  // warp-uniform
+        float rv = 0.f;
+        if (row_ok && p.epi_op != U2_EPI_NONE)
+          rv = __ldg(p.rowvec + (long long)zo_i * p.rv_zo + (long long)zi_i * p.rv_zi + row);
+        if (any) {
+          kind = side_kind(colb);
+          side_load(colb, kind, sd);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        bool released = false;
+        if (any) tmem_ld_32x32b_x32(taddr + half * (kBlockN / 2), v);
+        // the loop stays ROLLED (one copy of the body in the instruction cache: the 4x unrolled variant ran 1.7x slower);
+        // the pipelining needs no second register set - the accumulator values are consumed into f[] right after the wait,
+        // which frees v[] for the next chunk's TMEM load
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = colb + 32 * c;
+          if (col0 < p.N) {  // warp-uniform
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 o;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * c + 2 * e], f[8 * c + 2 * e + 1]);
-              sts128(st + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), o);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            const bool more = (c + 1 < kChunks) && (col0 + 32 < p.N);
+            if (more) {
+              tmem_ld_32x32b_x32(taddr + half * (kBlockN / 2) + 32 * (c + 1), v);
+            } else {
+              // every TMEM load of this warp has landed: hand the accumulator buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+              released = true;
             }
-            __syncwarp();
+            const int kd = kind;
+            const bool full = (col0 + 32 <= p.N);
+            if (row_ok && p.epi_op != U2_EPI_NONE) {
+              // attention backward: probabilities rebuilt from the row log-sum-exp / dS formed against the stored P
+              if (p.epi_op == U2_EPI_EXP_ROW) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + (lane >> 2), ch = lane & 3;
-              const uint4 o = lds128(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-              const int grow = row0 + rr;
-              if (grow < p.M) {
-                long long orow = grow;
-                if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + zoff + orow * p.ldc + col0 + ch * 8) = o;
+                for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - rv);
+              } else if (kd == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&sd[j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 rf = __bfloat1622float2(r2[e]);
+                    f[8 * j + 2 * e] = rf.x * (f[8 * j + 2 * e] - rv);
+                    f[8 * j + 2 * e + 1] = rf.y * (f[8 * j + 2 * e + 1] - rv);
+                  }
+                }
+              } else {
+                const __nv_bfloat16* mp = p.mul + c_off + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  f[j] = (col0 + j < p.N) ? __bfloat162float(mp[j]) * (f[j] - rv) : 0.f;
               }
             }
-          } else {
+            if (row_ok) {
+              if (p.bias) {
+                if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              sts128(st + lane * 128 + ((c ^ (lane & 7)) << 4),
-                     make_uint4(__float_as_uint(f[4 * c]), __float_as_uint(f[4 * c + 1]), __float_as_uint(f[4 * c + 2]),
-                                __float_as_uint(f[4 * c + 3])));
-            __syncwarp();
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                  }
+                } else {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3), ch = lane & 7;
-              const float4 o = lds128_f32(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
-              const int grow = row0 + rr;
-              if (grow < p.M) {
-                long long orow = grow;
-                if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + zoff + orow * p.ldc + col0 + ch * 4) = o;
+                  for (int j = 0; j < 32; ++j)
+                    if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+                }
+              }
+              if (p.act != U2_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+              }
+              if (kd == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&sd[j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 rf = __bfloat1622float2(r2[e]);
+                    f[8 * j + 2 * e] += rf.x;
+                    f[8 * j + 2 * e + 1] += rf.y;
+                  }
+                }
+              } else if (res_ptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) f[j] += __bfloat162float(res_ptr[col0 + j]);
               }
             }
-          }
-        } else if (row_ok) {
-          if (p.c_dtype == U2_DT_BF16) {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + col0;
+            if (more) {  // the side operands of chunk c are consumed: request chunk c + 1's (in flight during the store below)
+              kind = side_kind(col0 + 32);
+              side_load(col0 + 32, kind, sd);
+            }
+            // ---- store. Fast path: the warp's 32 x 32 block goes through a swizzled shared-memory tile so that every
+            // store instruction writes whole 128-byte (fp32) / 64-byte (bf16) row segments; the thread-per-row pattern it
+            // replaces touched 32 half-used sectors per request, which bounded every short-K GEMM by its epilogue.
+            const bool fast = full &&
+                              (p.c_dtype == U2_DT_BF16 ? (((p.ldc | zoff) & 7) == 0) : (((p.ldc | zoff) & 3) == 0));
+            if (fast) {
+              __syncwarp();  // the previous chunk's read-back is complete
+              if (p.c_dtype == U2_DT_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) c[j] = __float2bfloat16(f[j]);
-          } else {
-            float* c = reinterpret_cast<float*>(p.C) + c_off + col0;
+                for (int cc = 0; cc < 4; ++cc) {
+                  uint4 o;
+                  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) c[j] = f[j];
+                  for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * cc + 2 * e], f[8 * cc + 2 * e + 1]);
+                  sts128(st + lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4), o);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  const int rr = it * 8 + (lane >> 2), ch = lane & 3;
+                  const uint4 o = lds128(st + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                  const int grow = row0 + rr;
+                  if (grow < p.M) {
+                    long long orow = grow;
+                    if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + zoff + orow * p.ldc + col0 + ch * 8) = o;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                  sts128(st + lane * 128 + ((cc ^ (lane & 7)) << 4),
+                         make_uint4(__float_as_uint(f[4 * cc]), __float_as_uint(f[4 * cc + 1]), __float_as_uint(f[4 * cc + 2]),
+                                    __float_as_uint(f[4 * cc + 3])));
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+                  const float4 o = lds128_f32(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                  const int grow = row0 + rr;
+                  if (grow < p.M) {
+                    long long orow = grow;
+                    if (p.row_div > 0) orow = (long long)(grow / p.row_div) * p.row_stride + p.row_off + grow % p.row_div;
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + zoff + orow * p.ldc + col0 + ch * 4) = o;
+                  }
+                }
+              }
+            } else if (row_ok) {
+              if (p.c_dtype == U2_DT_BF16) {
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = __float2bfloat16(f[j]);
+              } else {
+                float* cp = reinterpret_cast<float*>(p.C) + c_off + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = f[j];
+              }
+            }
           }
         }
-      }
+        if (!released) {  // this half tile lies entirely past N
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
       }  // kMode
-      // hand the accumulator buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

@@ -76,9 +76,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K
     d.rv_stride_zi, d.rv_stride_zo = rv_strides
     d.mul = _ptr(mul)
     lib = _lib.load()
+    if GEMM_TRACE is not None:   # tuning aid (tools/gemm_trace.py): per-call CUDA events keyed by shape / operand layout
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.u2_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), C.byref(d), _stream()),
                "u2_gemm_bf16")
+    if GEMM_TRACE is not None:
+        e1.record()
+        GEMM_TRACE.append(((M, N, K, zi * zo, int(a_mn), int(b_mn), "f32" if c.dtype == F32 else "bf16", int(bias is not None),
+                            int(act), int(residual is not None), int(epi_op)), e0, e1))
     return c
+
+
+GEMM_TRACE = None   # set to a list to record (key, start event, end event) per gemm() call
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
