@@ -328,21 +328,22 @@ U2_API int u2_topk_rows_f32(const float* scores, int64_t* out_idx, int32_t rows,
 
 /* Fused attention forward, head_dim 64, non-causal (ViT3D): out = softmax(q k^T * scale) v, scores never leave
  * the SM (tcgen05: S and PV partials in TMEM, P through swizzled shared memory).
- * q [B, Sq, H, 64], k [B, Sk, H, 64] as strided views (element strides *_sb batch, *_ss token, *_sh head; d contiguous),
- * vt = v transposed [B, H, 64, Sk_pad] (strides vt_sb, vt_sh, vt_sd; token axis contiguous, see
- * u2_transpose_heads_bf16), out [B, Sq, H*64] (strides out_sb, out_ss). All strides multiples of 8 elements.
+ * q [B, Sq, H, 64], k [B, Sk, H, 64], v [B, Sk, H, 64] as strided views (element strides *_sb batch, *_ss token,
+ * *_sh head; d contiguous) - typically the three slices of one fused QKV activation; v is consumed as stored (MN-major
+ * B operand of the PV product, no transposed copy); out [B, Sq, H*64] (strides out_sb, out_ss). All strides multiples
+ * of 8 elements.
  * Replaces MONAI SABlock einsum/softmax/einsum (reference vit.py:100-105,120-122). */
 typedef struct u2_fa_desc {
   int32_t B, H, Sq, Sk, dh;
   float scale;
   int64_t q_sb, q_ss, q_sh;
   int64_t k_sb, k_ss, k_sh;
-  int64_t vt_sb, vt_sh, vt_sd;
+  int64_t v_sb, v_ss, v_sh;
   int64_t out_sb, out_ss;
   float* lse; /* optional fp32 [B, H, Sq]: log-sum-exp of the scaled score rows (training: the backward rebuilds the
                  probabilities as exp(scale * q.k - lse) in the score GEMM's epilogue); NULL at inference */
 } u2_fa_desc;
-U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* vt, void* out, const u2_fa_desc* desc,
+U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* v, void* out, const u2_fa_desc* desc,
                                        void* stream);
 
 /* Sampled decoding head: ids[b] ~ multinomial(top_p(top_k(softmax(logits[b] / temperature)))) - the HF warper chain

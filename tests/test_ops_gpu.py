@@ -478,13 +478,9 @@ def test_flash_attention_d64(Sq, Sk):
     Sp = (max(Sq, Sk) + 7) // 8 * 8
     qkv = torch.randn(B, Sp, 3, H, dh, device=DEV, generator=g).bfloat16()   # fused layout like the ViT qkv Linear
     q, k, v = qkv[:, :Sq, 0], qkv[:, :Sk, 1], qkv[:, :Sk, 2]
-    Skp = (Sk + 7) // 8 * 8
-    vt = torch.empty(B, H, dh, Skp, device=DEV, dtype=torch.bfloat16)
-    ops.transpose_heads(v, vt, B=B, S=Sk, H=H, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
-                        out_strides=(H * dh * Skp, dh * Skp), ld_out=Skp)
     out = torch.zeros(B, Sp, H * dh, device=DEV, dtype=torch.bfloat16)
     scale = dh ** -0.5
-    ops.flash_attention_d64(q, k, vt, out[:, :Sq], scale)
+    ops.flash_attention_d64(q, k, v, out[:, :Sq], scale)  # V consumed in place (MN-major operand of the PV product)
     ref = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale, -1)
     ref = torch.einsum("bhqk,bkhd->bqhd", ref, v.float()).reshape(B, Sq, H * dh)
     close(out[:, :Sq], ref, 1e-2)

@@ -134,7 +134,7 @@ class FaDesc(C.Structure):
         ("scale", C.c_float),
         ("q_sb", C.c_int64), ("q_ss", C.c_int64), ("q_sh", C.c_int64),
         ("k_sb", C.c_int64), ("k_ss", C.c_int64), ("k_sh", C.c_int64),
-        ("vt_sb", C.c_int64), ("vt_sh", C.c_int64), ("vt_sd", C.c_int64),
+        ("v_sb", C.c_int64), ("v_ss", C.c_int64), ("v_sh", C.c_int64),
         ("out_sb", C.c_int64), ("out_ss", C.c_int64),
         ("lse", C.c_void_p),
     ]

@@ -2,7 +2,7 @@
 // (12 heads, S = 2049 tokens per frame): O = softmax(Q K^T * scale) V without materialising the S x S scores.
 //
 // One CTA owns a 128-row query tile of one (frame, head) and walks the keys in tiles of 128:
-//   warp 0   : TMA producer   Q once, then (K_j, V^T_j) into a 2-deep ring
+//   warp 0   : TMA producer   Q once, then (K_j, V_j) into a 2-deep ring
 //   warp 1   : MMA issuer     S_j = Q K_j^T  (128 x 128 x 64, fp32 in TMEM, double buffered) and
 //                             PV_j = P_j V_j (128 x 64 x 128); S_{j+1} is issued BEFORE waiting for P_j, so the
 //                             tensor pipe works on the next scores while the CUDA cores do the softmax of tile j
@@ -10,8 +10,10 @@
 //   warps 4-7: softmax        thread == query row: tcgen05.ld the S row, online max/sum in the log2 domain,
 //                             P (bf16) written to shared memory in the swizzled K-major UMMA layout, running O kept
 //                             in registers and rescaled there (no TMEM read-modify-write)
-// Q / K are 4-D TMA views of the fused QKV activation ([frame, token, 3, head, d]); V comes pre-transposed
-// ([frame, head, d, token], tokens padded to a multiple of 8) because the PV product needs a K-major B operand.
+// Q / K / V are 4-D TMA views of the fused QKV activation ([frame, token, 3, head, d]). V is consumed AS STORED: a
+// {64 d, 128 keys} box with the 128-byte swizzle is the canonical MN-major UMMA operand layout (one 64-wide N chunk,
+// groups of 8 key rows 1024 B apart), so the PV product takes it through an MN-major B descriptor - no transposed
+// copy of V (round 1 ran a transpose kernel per block: 86 us x 12 at the bench configuration).
 //
 // Replaces MONAI SABlock's einsum / softmax / einsum (reference call site src/model/multimodal_encoder/vit.py:
 // 100-105,120-122), which materialises a [frames*12, 2049, 2049] fp32 score tensor per block.
@@ -31,7 +33,7 @@ constexpr int kFaBN = 128;   // keys per tile
 constexpr int kFaThreads = 256;
 constexpr int kFaQBytes = kFaBM * kFaDh * 2;          // 16 KB
 constexpr int kFaKBytes = kFaBN * kFaDh * 2;          // 16 KB
-constexpr int kFaVBytes = kFaDh * kFaBN * 2;          // 16 KB (two 64-key slabs of 8 KB)
+constexpr int kFaVBytes = kFaBN * kFaDh * 2;          // 16 KB (128 key rows of 128 B)
 constexpr int kFaPBytes = kFaBM * kFaBN * 2;          // 32 KB (two 64-key slabs of 16 KB)
 constexpr int kFaSmem = kFaQBytes + 2 * kFaKBytes + 2 * kFaVBytes + 2 * kFaPBytes + 1024 + 256;
 constexpr int kFaTmemCols = 512;
@@ -53,7 +55,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(kFaThreads, 1)
 fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                      const __grid_constant__ CUtensorMap tmap_vt, const FaArgs p) {
+                      const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
@@ -81,7 +83,7 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_vt);
+    tma_prefetch_desc(&tmap_v);
   }
   if (warp_idx == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -115,15 +117,14 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         mbar_wait(&kv_empty[buf], (n & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[buf], kFaKBytes + kFaVBytes);
         tma_load_4d(sK + buf * kFaKBytes, &tmap_k, &kv_full[buf], 0, j * kFaBN, h, b);
-        tma_load_4d(sV + buf * kFaVBytes, &tmap_vt, &kv_full[buf], j * kFaBN, 0, h, b);
-        tma_load_4d(sV + buf * kFaVBytes + kFaVBytes / 2, &tmap_vt, &kv_full[buf], j * kFaBN + 64, 0, h, b);
+        tma_load_4d(sV + buf * kFaVBytes, &tmap_v, &kv_full[buf], 0, j * kFaBN, h, b);
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kFaBM, kFaBN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kFaBM, kFaDh);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kFaBM, kFaDh) | (1u << 16);  // B (= V) is MN-major
       const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(sQ));
       auto issue_qk = [&](int j) {
         const int buf = j & 1, n = j >> 1;
@@ -148,7 +149,8 @@ fa_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int k = 0; k < kFaBN / 16; ++k) {
           const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (kFaPBytes / 2)) + 2 * (k & 3);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(v_addr + (k >> 2) * (kFaVBytes / 2)) + 2 * (k & 3);
+          // 16 keys per UMMA_K step = two 1024-byte groups of 8 key rows (descriptor start address in 16-byte units)
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr, kFaVBytes) + 128 * k;
           umma_f16(tO + buf * kFaDh, a_desc, b_desc, idesc_pv, k != 0);
         }
         umma_commit(&o_full[buf]);
@@ -288,7 +290,7 @@ constexpr int kFa2Smem = 2 * kFaQBytes + 2 * kFaKBytes + 2 * kFaVBytes + 2 * kFa
 
 __global__ void __launch_bounds__(kFa2Threads, 1)
 fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                       const __grid_constant__ CUtensorMap tmap_vt, const FaArgs p) {
+                       const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                       // [2 tiles]
@@ -317,7 +319,7 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_vt);
+    tma_prefetch_desc(&tmap_v);
   }
   if (warp_idx == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -351,14 +353,13 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         mbar_wait(&kv_empty[st], (n & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[st], kFaKBytes + kFaVBytes);
         tma_load_4d(sK + st * kFaKBytes, &tmap_k, &kv_full[st], 0, j * kFaBN, h, b);
-        tma_load_4d(sV + st * kFaVBytes, &tmap_vt, &kv_full[st], j * kFaBN, 0, h, b);
-        tma_load_4d(sV + st * kFaVBytes + kFaVBytes / 2, &tmap_vt, &kv_full[st], j * kFaBN + 64, 0, h, b);
+        tma_load_4d(sV + st * kFaVBytes, &tmap_v, &kv_full[st], 0, j * kFaBN, h, b);
       }
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kFaBM, kFaBN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kFaBM, kFaDh);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kFaBM, kFaDh) | (1u << 16);  // B (= V) is MN-major
       const int ntile = has_b ? 2 : 1;
       auto issue_qk = [&](int t, int j) {
         const int st = j & 1;
@@ -380,7 +381,8 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 #pragma unroll
         for (int k = 0; k < kFaBN / 16; ++k) {
           const uint64_t a_desc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (kFaPBytes / 2)) + 2 * (k & 3);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(v_addr + (k >> 2) * (kFaVBytes / 2)) + 2 * (k & 3);
+          // 16 keys per UMMA_K step = two 1024-byte groups of 8 key rows (descriptor start address in 16-byte units)
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(v_addr, kFaVBytes) + 128 * k;
           umma_f16(tO + t * kFaDh, a_desc, b_desc, idesc_pv, k != 0);
         }
         umma_commit(&o_full[t]);
@@ -515,15 +517,15 @@ fa_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
 }  // namespace u2
 
-extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* vt, void* out,
+extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, const void* v, void* out,
                                                   const u2_fa_desc* d, void* stream) {
   using namespace u2;
-  if (!q || !k || !vt || !out || !d) return set_error(U2_ERR_ARG, "flash_attention: null pointer");
+  if (!q || !k || !v || !out || !d) return set_error(U2_ERR_ARG, "flash_attention: null pointer");
   if (d->dh != kFaDh) return set_error(U2_ERR_UNSUPPORTED, "flash_attention: head_dim %d (this kernel: 64)", d->dh);
   if (d->B <= 0 || d->H <= 0 || d->Sq <= 0 || d->Sk <= 0) return set_error(U2_ERR_ARG, "flash_attention: bad extents");
   if (d->B > 65535 || d->H > 65535) return set_error(U2_ERR_ARG, "flash_attention: B, H must be <= 65535");
-  if ((d->q_ss & 7) || (d->q_sh & 7) || (d->q_sb & 7) || (d->k_ss & 7) || (d->k_sh & 7) || (d->k_sb & 7) || (d->vt_sd & 7) ||
-      (d->vt_sh & 7) || (d->vt_sb & 7) || (d->out_ss & 7))
+  if ((d->q_ss & 7) || (d->q_sh & 7) || (d->q_sb & 7) || (d->k_ss & 7) || (d->k_sh & 7) || (d->k_sb & 7) || (d->v_ss & 7) ||
+      (d->v_sh & 7) || (d->v_sb & 7) || (d->out_ss & 7))
     return set_error(U2_ERR_ARG, "flash_attention: strides must be multiples of 8 elements");
   static bool configured = false;
   if (!configured) {
@@ -536,8 +538,8 @@ extern "C" U2_API int u2_flash_attention_d64_bf16(const void* q, const void* k, 
   if (rc) return rc;
   rc = make_tmap_bf16_4d(&tk, k, kFaDh, d->Sk, d->H, d->B, d->k_ss, d->k_sh, d->k_sb, kFaDh, kFaBN);
   if (rc) return rc;
-  // V^T: dims {token, d, head, batch}; token axis contiguous
-  rc = make_tmap_bf16_4d(&tv, vt, d->Sk, kFaDh, d->H, d->B, d->vt_sd, d->vt_sh, d->vt_sb, 64, kFaDh);
+  // V as stored: dims {d, token, head, batch}, box {64 d, 128 keys} = the MN-major B operand of the PV product
+  rc = make_tmap_bf16_4d(&tv, v, kFaDh, d->Sk, d->H, d->B, d->v_ss, d->v_sh, d->v_sb, kFaDh, kFaBN);
   if (rc) return rc;
   FaArgs a;
   a.Sq = d->Sq; a.Sk = d->Sk;

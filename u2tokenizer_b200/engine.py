@@ -255,31 +255,26 @@ class U2Engine:
         Sk, hk = k.shape[1], k.shape[2]
         Skp = _pad8(Sk)
         if dh == 64 and h == hk and rel_bias is None and not causal and self.use_flash:
-            # fused tcgen05 attention: scores never leave the SM (the ViT tower, S = 2049)
-            vt = torch.empty(b, hk, dh, Skp, device=q.device, dtype=BF16)
-            ops.transpose_heads(v, vt, B=b, S=Sk, H=hk, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
-                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
-            return ops.flash_attention_d64(q, k, vt, out, scale)
-        per_b = h * Sq * Skp * 6 + hk * dh * Skp * 2
+            # fused tcgen05 attention: scores never leave the SM (the ViT tower, S = 2049); V is consumed as stored
+            return ops.flash_attention_d64(q, k, v, out, scale)
+        per_b = h * Sq * Skp * 6
         chunk = max(1, min(b, self.attn_ws // max(per_b, 1)))
         dev = q.device
         sc = torch.empty(chunk, h, Sq, Skp, device=dev, dtype=F32)
         pr = torch.empty(chunk, h, Sq, Skp, device=dev, dtype=BF16)
-        vt = torch.empty(chunk, hk, dh, Skp, device=dev, dtype=BF16)
         for b0 in range(0, b, chunk):
             nb = min(chunk, b - b0)
             qq, kk, vv, oo = q[b0:b0 + nb], k[b0:b0 + nb], v[b0:b0 + nb], out[b0:b0 + nb]
-            ops.transpose_heads(vv, vt, B=nb, S=Sk, H=hk, Dh=dh, in_strides=(vv.stride(0), vv.stride(1), vv.stride(2)),
-                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
             ops.gemm(qq, kk, sc, M=Sq, N=Sk, K=dh, lda=qq.stride(1), ldb=kk.stride(1), ldc=Skp, zi=h, zo=nb,
                      b_zi_div=h // hk, a_strides=(qq.stride(2), qq.stride(0)), b_strides=(kk.stride(2), kk.stride(0)),
                      c_strides=(Sq * Skp, h * Sq * Skp), alpha=scale)
             ops.softmax(sc, pr, n0=nb, H=h, S=Sq, n=Sk, in_strides=(h * Sq * Skp, Sq * Skp, Skp),
                         out_strides=(h * Sq * Skp, Sq * Skp, Skp), rel_bias=rel_bias, rel_max=REL_MAX, causal=causal,
                         causal_off=Sk - Sq)
-            ops.gemm(pr, vt, oo, M=Sq, N=dh, K=Sk, lda=Skp, ldb=Skp, ldc=oo.stride(1), zi=h, zo=nb, b_zi_div=h // hk,
-                     a_strides=(Sq * Skp, h * Sq * Skp), b_strides=(dh * Skp, hk * dh * Skp),
-                     c_strides=(dh, oo.stride(0)))
+            # P @ V with V [Sk, dh] as stored (MN-major B operand): no transposed copy of V
+            ops.gemm(pr, vv, oo, M=Sq, N=dh, K=Sk, lda=Skp, ldb=vv.stride(1), ldc=oo.stride(1), zi=h, zo=nb,
+                     b_zi_div=h // hk, a_strides=(Sq * Skp, h * Sq * Skp), b_strides=(vv.stride(2), vv.stride(0)),
+                     c_strides=(dh, oo.stride(0)), b_mn=True)
         return out
 
     # =========================================================================================
@@ -416,11 +411,10 @@ class U2Engine:
         ops.gemm(self.score_w, x2, scT, M=K, N=B * T, K=E, lda=E, ldb=E, ldc=B * T)
         pT = torch.empty(B, K, Tp, device=self.dev, dtype=BF16)
         ops.softmax(scT, pT, n0=B, H=1, S=K, n=T, in_strides=(T, 0, B * T), out_strides=(K * Tp, 0, Tp))
-        xT = torch.empty(B, E, Tp, device=self.dev, dtype=BF16)
-        ops.transpose_heads(x2, xT, B=B, S=T, H=1, Dh=E, in_strides=(T * E, E, 0), out_strides=(E * Tp, 0), ld_out=Tp)
         sel = torch.empty(B, K, E, device=self.dev, dtype=BF16)
-        ops.gemm(pT, xT, sel, M=K, N=E, K=T, lda=Tp, ldb=Tp, ldc=E, zo=B, a_strides=(0, K * Tp), b_strides=(0, E * Tp),
-                 c_strides=(0, K * E))
+        # weights [K, T] @ X [T, E] with X as stored (MN-major B operand): no transposed copy of the tokens
+        ops.gemm(pT, x2, sel, M=K, N=E, K=T, lda=Tp, ldb=E, ldc=E, zo=B, a_strides=(0, K * Tp), b_strides=(0, T * E),
+                 c_strides=(0, K * E), b_mn=True)
         return sel
 
     def _token_selection_hard(self, x2: torch.Tensor, B: int, T: int) -> torch.Tensor:

@@ -494,26 +494,26 @@ def topk_rows(scores: torch.Tensor, k: int, idx_offset_per_row: int = 0) -> torc
     return out
 
 
-def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, scale: float,
+def flash_attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
                         lse: Optional[torch.Tensor] = None):
-    """Fused non-causal attention for head_dim 64: q [B,Sq,H,64], k [B,Sk,H,64] (strided views, d contiguous),
-    vt [B,H,64,Sk_pad] (token axis contiguous), out [B,Sq,H*64] view."""
-    _need_cuda(q, k, vt, out)
+    """Fused non-causal attention for head_dim 64: q [B,Sq,H,64], k / v [B,Sk,H,64] (strided views, d contiguous: the
+    slices of a fused QKV activation are consumed in place), out [B,Sq,H*64] view."""
+    _need_cuda(q, k, v, out)
     B, Sq, H, dh = q.shape
     Sk = k.shape[1]
-    if dh != 64 or q.stride(3) != 1 or k.stride(3) != 1 or vt.stride(3) != 1 or out.stride(2) != 1:
-        raise ValueError("flash_attention_d64: head_dim must be 64 with a contiguous last dim")
+    if dh != 64 or q.stride(3) != 1 or k.stride(3) != 1 or v.stride(3) != 1 or out.stride(2) != 1 or v.shape != k.shape:
+        raise ValueError("flash_attention_d64: head_dim must be 64 with a contiguous last dim, v shaped like k")
     d = _lib.FaDesc()
     d.B, d.H, d.Sq, d.Sk, d.dh, d.scale = B, H, Sq, Sk, dh, scale
     d.q_sb, d.q_ss, d.q_sh = q.stride(0), q.stride(1), q.stride(2)
     d.k_sb, d.k_ss, d.k_sh = k.stride(0), k.stride(1), k.stride(2)
-    d.vt_sb, d.vt_sh, d.vt_sd = vt.stride(0), vt.stride(1), vt.stride(2)
+    d.v_sb, d.v_ss, d.v_sh = v.stride(0), v.stride(1), v.stride(2)
     d.out_sb, d.out_ss = out.stride(0), out.stride(1)
     _need_cuda(lse)
     if lse is not None and (lse.dtype != F32 or not lse.is_contiguous() or lse.numel() != B * H * Sq):
         raise ValueError("flash_attention_d64: lse must be contiguous fp32 [B, H, Sq]")
     d.lse = _ptr(lse)
-    _lib.check(_lib.load().u2_flash_attention_d64_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(),
+    _lib.check(_lib.load().u2_flash_attention_d64_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                                        C.byref(d), _stream()), "u2_flash_attention_d64_bf16")
     return out
 

@@ -468,13 +468,9 @@ class TrainEngine:
         saved = {}
         if recompute and dh == 64 and h == hk and rel is None and not causal:
             # fused tcgen05 attention forward (scores never leave the SM); the probabilities are recomputed in the backward
-            vt = torch.empty(b, hk, dh, Skp, device=dev, dtype=BF16)
-            ops.transpose_heads(v, vt, B=b, S=Sk, H=hk, Dh=dh, in_strides=(v.stride(0), v.stride(1), v.stride(2)),
-                                out_strides=(hk * dh * Skp, dh * Skp), ld_out=Skp)
             lse = torch.empty(b, h, Sq, device=dev, dtype=F32)
-            ops.flash_attention_d64(q, k, vt, ctx, scale, lse=lse)
+            ops.flash_attention_d64(q, k, v, ctx, scale, lse=lse)
             saved["lse"] = lse
-            del vt
         else:
             pr0 = probs()
             # ctx = P @ V: V [Sk, dh] is consumed as stored (MN-major B operand: no transposed copy)
