@@ -33,6 +33,9 @@ constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 352;   // 3 control warps + 8 epilogue warps (352 threads -> 186 registers per thread)
 constexpr int kEpiWarp0 = 3;
 constexpr int kEpiThreads = 256;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+#ifndef U2_GEMM_TMA_STORE_DEFAULT
+#define U2_GEMM_TMA_STORE_DEFAULT 1
+#endif
 
 template <int kBlockN>
 struct GemmCfg {
@@ -59,6 +62,7 @@ struct GemmDev {
   int row_div, row_stride, row_off;
   void* C;
   int m_major;                // tile order inside a batch (see tile_coords)
+  int tma_store;              // C goes out through TMA bulk stores of the staged 32 x 32 blocks (tmap_c valid)
   int epi_op;                 // U2_EPI_*
   const float* rowvec;
   long long rv_zi, rv_zo;
@@ -115,7 +119,8 @@ __device__ __forceinline__ void tile_coords(int t, int num_m_blocks, int num_n_b
 template <int kBlockN, int kMode = 0, int kMajor = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmDev p) {
   using Cfg = GemmCfg<kBlockN>;
   constexpr int kStages = Cfg::kStages;
 
@@ -125,13 +130,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  // 8 x 4 KB staging tiles, one per epilogue warp, 1024-byte aligned: sources of swizzled TMA stores
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiStageBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes + 256;  // 8 x 4 KB staging tiles, one per epilogue warp
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -145,6 +151,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_c);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -251,6 +258,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int half = (warp_idx - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains (warps 3-6 / 7-10)
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t n_st = 0;  // TMA stores issued by this warp (bf16: two 2 KB staging buffers used alternately)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_batch;
       const int t = tile - z * tiles_per_batch;
@@ -449,7 +457,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // replaces touched 32 half-used sectors per request, which bounded every short-K GEMM by its epilogue.
             const bool fast = full &&
                               (p.c_dtype == U2_DT_BF16 ? (((p.ldc | zoff) & 7) == 0) : (((p.ldc | zoff) & 3) == 0));
-            if (fast) {
+            if (p.tma_store) {
+              // ---- TMA path: the same swizzled 32 x 32 image (it IS the 64-byte / 128-byte TMA swizzle of a box of 32
+              // rows) leaves through ONE bulk tensor store issued by lane 0: no read-back, no per-row address arithmetic,
+              // rows >= M and columns >= N are clipped by the tensor map. bf16 blocks are 2 KB, so the warp's 4 KB
+              // staging area double-buffers them: block c is filled while the copy engine still reads block c - 1.
+              if (p.c_dtype == U2_DT_BF16) {
+                const uint32_t sb = st + (n_st & 1) * 2048;
+                if (lane == 0) bulk_wait_group_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  uint4 o;
+                  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[8 * cc + 2 * e], f[8 * cc + 2 * e + 1]);
+                  sts128(sb + lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4), o);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&tmap_c, sb, col0, row0, zi_i, zo_i);
+                  bulk_commit_group();
+                }
+              } else {
+                if (lane == 0) bulk_wait_group_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                  sts128(st + lane * 128 + ((cc ^ (lane & 7)) << 4),
+                         make_uint4(__float_as_uint(f[4 * cc]), __float_as_uint(f[4 * cc + 1]), __float_as_uint(f[4 * cc + 2]),
+                                    __float_as_uint(f[4 * cc + 3])));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&tmap_c, st, col0, row0, zi_i, zo_i);
+                  bulk_commit_group();
+                }
+              }
+              ++n_st;
+            } else if (fast) {
               __syncwarp();  // the previous chunk's read-back is complete
               if (p.c_dtype == U2_DT_BF16) {
 #pragma unroll
@@ -517,6 +564,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         acc_phase ^= 1;
       }
     }
+    // outstanding bulk stores read this CTA's shared memory: they must be complete before the CTA retires
+    if (p.tma_store && lane == 0) bulk_wait_group<0>();
   }
 
   tc_fence_before();
@@ -531,7 +580,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int kBlockN, int kMode = 0, int kMajor = 0>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int num_sms,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& p, int num_sms,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
   static bool configured = false;
@@ -545,7 +594,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   const int num_n = (p.N + kBlockN - 1) / kBlockN;
   const long long tiles = (long long)num_m * num_n * p.zi * p.zo;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<kBlockN, kMode, kMajor><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_kernel<kBlockN, kMode, kMajor><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(U2_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return U2_OK;
@@ -635,7 +684,7 @@ extern "C" U2_API int u2_lmhead_logprob_bf16(const void* hidden, const void* W, 
   p.lab_logit = reinterpret_cast<float*>(reinterpret_cast<char*>(d->ws) + (long long)P * r_pad * 16);
   p.part_ld = r_pad;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  rc = launch_gemm<kBn, 1>(ta, tb, p, num_sms(), s);
+  rc = launch_gemm<kBn, 1>(ta, tb, ta /* no C tensor map: nothing of the logits is stored */, p, num_sms(), s);
   if (rc) return rc;
   logprob_merge_kernel<<<(unsigned)((d->R + 31) / 32), 256, 0, s>>>(p.part, p.lab_logit, p.labels, d->R, P, r_pad, logp, d->lse,
                                                                     d->logit_sum, d->nll_acc);
@@ -713,12 +762,32 @@ extern "C" U2_API int u2_gemm_bf16(const void* A, const void* B, void* C, const 
     if (p.epi_op == U2_EPI_DS_ROW && (!p.mul || d->c_dtype != U2_DT_BF16)) return set_error(U2_ERR_ARG, "gemm: U2_EPI_DS_ROW needs mul and a bf16 C");
     if (p.row_div > 0) return set_error(U2_ERR_ARG, "gemm: the fused attention epilogue does not combine with row remapping");
   }
+  // C through TMA bulk stores (staged 32 x 32 blocks, clipped at the matrix edges) when its layout allows a tensor map:
+  // 16-byte aligned base / row pitch / batch strides and no row remapping. U2_GEMM_TMA_STORE=0 keeps the ld.shared +
+  // st.global read-back path. Measured on B200 (profiles/r2_gemm_tma_store.txt): S x S x 64 attention products
+  // 701 -> 653 us (bf16 C), 933 -> 670 us (fp32 C); ViT fc1 + GELU 65792 x 3072 x 768: 606 -> 549 us; qkv 220 -> 198 us.
+  // The dS epilogue, which reads P from the buffer it overwrites, got SLOWER (1322 -> 1542 us) and keeps the old path.
+  CUtensorMap tc = ta;
+  {
+    static const int want = [] {
+      const char* e = getenv("U2_GEMM_TMA_STORE");
+      return e ? atoi(e) : U2_GEMM_TMA_STORE_DEFAULT;
+    }();
+    const long long es = (d->c_dtype == U2_DT_BF16) ? 2 : 4;
+    const bool ok = want && p.row_div <= 0 && p.epi_op != U2_EPI_DS_ROW && (d->c_dtype == U2_DT_BF16 || d->c_dtype == U2_DT_F32) &&
+                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ((d->ldc * es) & 15) == 0 &&
+                    (zi == 1 || ((d->c_stride_zi * es) & 15) == 0) && (zo == 1 || ((d->c_stride_zo * es) & 15) == 0) &&
+                    d->ldc >= d->N;
+    // a layout the driver refuses to encode simply keeps the read-back path
+    if (ok && make_tmap_store_4d(&tc, C, (int)es, d->N, d->M, zi, zo, d->ldc, d->c_stride_zi, d->c_stride_zo, 32, 32) == U2_OK)
+      p.tma_store = 1;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define U2_GEMM_BN(MAJ)                                                    \
-  switch (block_n) {                                                      \
-    case 64: return launch_gemm<64, 0, MAJ>(ta, tb, p, num_sms(), s);     \
-    case 128: return launch_gemm<128, 0, MAJ>(ta, tb, p, num_sms(), s);   \
-    default: return launch_gemm<256, 0, MAJ>(ta, tb, p, num_sms(), s);    \
+#define U2_GEMM_BN(MAJ)                                                        \
+  switch (block_n) {                                                          \
+    case 64: return launch_gemm<64, 0, MAJ>(ta, tb, tc, p, num_sms(), s);     \
+    case 128: return launch_gemm<128, 0, MAJ>(ta, tb, tc, p, num_sms(), s);   \
+    default: return launch_gemm<256, 0, MAJ>(ta, tb, tc, p, num_sms(), s);    \
   }
   switch (major) {
     case 0: U2_GEMM_BN(0)

@@ -80,6 +80,36 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, int64_t k, int64_t row
   return U2_OK;
 }
 
+int make_tmap_store_4d(CUtensorMap* out, void* base, int elem_bytes, int64_t n, int64_t rows, int64_t zi, int64_t zo,
+                       int64_t ld, int64_t stride_zi, int64_t stride_zo, int box_n, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(U2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (elem_bytes != 2 && elem_bytes != 4) return set_error(U2_ERR_ARG, "store tensor map: bf16 or fp32 elements");
+  cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)rows, (cuuint64_t)(zi > 0 ? zi : 1), (cuuint64_t)(zo > 0 ? zo : 1)};
+  int64_t s1 = ld * elem_bytes;
+  int64_t s2 = (dims[2] > 1 ? stride_zi * elem_bytes : s1 * (int64_t)rows);
+  int64_t s3 = (dims[3] > 1 ? stride_zo * elem_bytes : s2 * (int64_t)dims[2]);
+  if (dims[2] == 1) s2 = (s2 + 15) / 16 * 16;
+  if (dims[3] == 1) s3 = (s3 + 15) / 16 * 16;
+  if (s2 <= 0) s2 = 16;
+  if (s3 <= 0) s3 = 16;
+  cuuint64_t strides[3] = {(cuuint64_t)s1, (cuuint64_t)s2, (cuuint64_t)s3};
+  cuuint32_t box[4] = {(cuuint32_t)box_n, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // the inner box extent is 64 B (32 bf16) or 128 B (32 fp32): the swizzle span equals the box row
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(U2_ERR_CUDA,
+                     "cuTensorMapEncodeTiled(store 4d) failed: %d (n=%lld rows=%lld zi=%lld zo=%lld ld=%lld szi=%lld szo=%lld "
+                     "box=%dx%d base=%p)",
+                     (int)r, (long long)n, (long long)rows, (long long)zi, (long long)zo, (long long)ld, (long long)stride_zi,
+                     (long long)stride_zo, box_n, box_rows, base);
+  return U2_OK;
+}
+
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2,
                      int64_t stride1_elems, int64_t stride2_elems, int box0, int box1, int box2) {
   EncodeTiledFn enc = get_encode();

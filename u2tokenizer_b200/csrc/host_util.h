@@ -18,6 +18,11 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* base, int64_t k, int64_t row
                       int64_t zo, int64_t ld, int64_t stride_zi, int64_t stride_zo, int box_k,
                       int box_rows);
 
+// 4-D tensor map of a GEMM OUTPUT (bf16: 64-byte swizzle, fp32: 128-byte swizzle; the box row is 32 elements): dims
+// (inner -> outer) {n, rows, zi, zo}, strides in ELEMENTS; box elements outside the extents are not written by a store.
+int make_tmap_store_4d(CUtensorMap* out, void* base, int elem_bytes, int64_t n, int64_t rows, int64_t zi, int64_t zo,
+                       int64_t ld, int64_t stride_zi, int64_t stride_zo, int box_n, int box_rows);
+
 // 3-D fp32 tensor map (no swizzle) used by the patch-embed brick gather.
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2,
                      int64_t stride1_elems, int64_t stride2_elems, int box0, int box1, int box2);

@@ -77,6 +77,28 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 4-D tiled STORE: shared (a box laid out with the tensor map's swizzle) -> global, tracked by the issuing thread's bulk
+// async-group. Elements of the box that fall outside the tensor's extents are not written. The shared-memory writes that
+// filled the box must be made visible to the async proxy first (fence_proxy_async_smem by every writing thread, then a
+// warp / CTA sync, then ONE thread issues the store).
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most kPending of this thread's bulk groups still have to READ their shared-memory source
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+// wait until at most kPending of this thread's bulk groups are incomplete (source read AND destination written)
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // L2 prefetch of a 4-D tile (no shared-memory destination, no completion tracking): warms L2 for a later load.
 __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
