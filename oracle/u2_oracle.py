@@ -14,7 +14,9 @@ Pinning (see DESIGN.md "Oracle"):
     restated from MONAI 1.3.0's published PatchEmbeddingBlock("perceptron") / SABlock / MLPBlock /
     TransformerBlock definitions; the reference holds no test or golden vector for it ->
     "parity unpinned" for that stage (anchored on the call sites
-    src/model/multimodal_encoder/vit.py:90-105,114-126,143-158).
+    src/model/multimodal_encoder/vit.py:90-105,114-126,143-158). Cross-checks that do exist (tests/test_oracle_pin.py):
+    the block against the installed HF transformers ViTLayer, an independent implementation of the same pre-LN ViT
+    block, and the brick gather against einops running MONAI's published pattern string.
   * The decoder is checked against the installed HuggingFace transformers Qwen3/Llama
     implementation (the reference calls it through super().forward, u2llama.py:76-87).
 
