@@ -133,7 +133,9 @@ typedef struct u2_softmax_desc {
 U2_API int u2_softmax_f32_bf16(const float* in, void* out, const u2_softmax_desc* desc, void* stream);
 
 /* out[r, i] = silu(g) * u with (g, u) = gate_up[r, i], gate_up[r, I + i]  (interleaved == 0) or
- * gate_up[r, 2i], gate_up[r, 2i + 1] (interleaved != 0)   (HF Qwen3MLP / LlamaMLP act_fn(gate) * up) */
+ * gate_up[r, 2i], gate_up[r, 2i + 1] (interleaved != 0). Replaces `act_fn(gate_proj(x)) * up_proj(x)` of the HF decoder MLP
+ * (transformers models/qwen3/modeling_qwen3.py:81-83, reached from the reference through super().forward,
+ * src/model/language_model/u2llama.py:76-87). */
 U2_API int u2_silu_mul_bf16(const void* gate_up, void* out, int64_t rows, int32_t I, int64_t ldg,
                             int64_t ldo, int32_t interleaved, void* stream);
 
@@ -162,7 +164,9 @@ U2_API int u2_set_rows_bf16(void* dst, const void* vec, int64_t n_rows, int64_t 
 U2_API int u2_vit_frame_rows_bf16(void* dst, const void* cls, int64_t frames, int32_t Sp, int32_t S, int32_t E,
                                   void* stream);
 /* in[b][s][h][d] (element strides in_sb, in_ss, in_sh; d contiguous) -> out[b][h][d][s] with the s axis
- * padded to ld_out (zeros): the K-major V^T operand of the PV contraction. */
+ * padded to ld_out (zeros): a K-major V^T / X^T operand. Replaces the `split_heads` + `transpose(-2, -1)` copies of
+ * src/model/u2tokenizer/rma.py:41-44,60 and tta.py:24-26,52. The path itself no longer calls it: V and the DiffTS token
+ * matrix are consumed in place as MN-major operands (u2_gemm_desc.b_mn, u2_flash_attention_d64_bf16). */
 U2_API int u2_transpose_heads_bf16(const void* in, void* out, int32_t B, int32_t S, int32_t H, int32_t Dh,
                                    int64_t in_sb, int64_t in_ss, int64_t in_sh, int64_t out_sb,
                                    int64_t out_sh, int64_t ld_out, void* stream);
@@ -210,12 +214,16 @@ typedef struct u2_rope_desc {
 U2_API int u2_rope_bf16(void* x, const u2_rope_desc* desc, void* stream);
 
 /* One query token per sequence against the KV cache (GQA). q [B, Hq*dh] (row stride ldq), caches
- * [B, Hkv, Tmax, dh]; T valid keys (or *T_dev when T_dev != NULL). */
+ * [B, Hkv, Tmax, dh]; T valid keys (or *T_dev when T_dev != NULL). Replaces the HF eager attention at q_len == 1
+ * (transformers models/qwen3/modeling_qwen3.py:252-291) inside generate() (src/model/language_model/u2llama.py:123-126);
+ * unfused variant used by the CUDA-core decode path. */
 U2_API int u2_decode_attention_bf16(const void* q, const void* k_cache, const void* v_cache, void* out,
                                     int32_t B, int32_t Hq, int32_t Hkv, int32_t dh, int32_t Tmax, int32_t T,
                                     const int32_t* T_dev, int64_t ldq, int64_t ldo, float scale, void* stream);
 
 /* Decode-step linear (weight streaming, HBM-bound): y[b, n] = sum_k norm(x)[b, k] * w[n, k] (+ residual).
+ * CUDA-core variant of the HF decoder Linears (+ Qwen3RMSNorm, modeling_qwen3.py:50-67) at q_len == 1 inside generate()
+ * (src/model/language_model/u2llama.py:123-126) for shapes the tcgen05 path does not take (K % 64 != 0).
  * B <= 8. norm_gamma != NULL fuses the input RMSNorm; silu_pair != 0 treats rows (2j, 2j+1) of w as
  * (gate_j, up_j) and writes silu(gate) * up (N/2 outputs). */
 typedef struct u2_gemv_desc {
@@ -228,7 +236,9 @@ typedef struct u2_gemv_desc {
   int32_t silu_pair;
 } u2_gemv_desc;
 U2_API int u2_gemv_bf16(const void* x, const void* w, void* y, const u2_gemv_desc* desc, void* stream);
-/* ids[b] = argmax_v logits[b, v] (first index on ties). scratch: uint64 [B], zero on entry and zero again on exit. */
+/* ids[b] = argmax_v logits[b, v] (first index on ties). scratch: uint64 [B], zero on entry and zero again on exit.
+ * Replaces `torch.argmax(next_token_scores, dim=-1)` of HF GenerationMixin._sample with do_sample=False
+ * (transformers generation/utils.py:2793; reference call src/model/language_model/u2llama.py:123-126). */
 U2_API int u2_argmax_f32(const float* logits, int64_t* out, uint64_t* scratch, int32_t B, int32_t V, int64_t ld,
                          void* stream);
 
@@ -274,7 +284,8 @@ typedef struct u2_dlinear_desc {
 } u2_dlinear_desc;
 U2_API int u2_dlinear_bf16(const void* x, const void* w, void* y, const u2_dlinear_desc* desc, void* stream);
 U2_API int64_t u2_dlinear_ws_elems(int32_t N, int32_t K); /* fp32 elements of workspace for an N x K linear */
-/* Up to four DEPENDENT decode linears in one launch (o_proj -> gate|up -> down -> next qkv): software grid
+/* Up to four DEPENDENT decode linears in one launch (o_proj -> gate|up -> down -> next qkv; the Linears of
+ * Qwen3DecoderLayer.forward, transformers models/qwen3/modeling_qwen3.py:305-336, at q_len == 1): software grid
  * barriers between them (gridbar: uint32[4], monotonically increasing; target = *step_dev * #SMs, step_dev is
  * the per-step counter u2_decode_embed_bf16 bumps), the weight stream of op i+1 is prefetched while op i
  * drains. x[i], w[i], y[i], descs[i] as for u2_dlinear_bf16. */
@@ -295,7 +306,8 @@ U2_API int u2_dlinear_multi_bf16(const void* const* x, const void* const* w, voi
                                  const u2_dlinear_desc* descs, int32_t n_ops, uint32_t* gridbar,
                                  const int32_t* step_dev, int32_t pdl, const u2_dlinear_next* next, void* stream);
 /* x[b] = table[ids[b]]; xg[b] = bf16(x * gamma); ssq[b] = sum x^2; ssq_zero[b] = 0; *step_counter += 1
- * (start of a decode step; step_counter may be NULL) */
+ * (start of a decode step; step_counter may be NULL). Replaces `embed_tokens(input_ids)` of the cached decode step
+ * (transformers models/qwen3/modeling_qwen3.py:392) + the first half of the first layer's input RMSNorm. */
 U2_API int u2_decode_embed_bf16(const int64_t* ids, const void* table, const float* gamma, void* x, void* xg,
                                 float* ssq, float* ssq_zero, int32_t* step_counter, int32_t B, int32_t E,
                                 int64_t vocab, void* stream);
@@ -354,7 +366,8 @@ U2_API int u2_sample_f32(const float* logits, int64_t* out, int32_t B, int32_t V
                          int32_t top_k, float top_p, uint64_t seed, const int32_t* step_dev, int32_t step,
                          void* stream);
 
-/* Same head with its parameters in DEVICE memory (24 bytes): a decode step captured in a CUDA graph reads them at
+/* Same head (HF _sample with do_sample=True, generation/utils.py:2791; reference eval/mrg.py:74-75,
+ * src/train/dpo_u2trainer.py:71-79) with its parameters in DEVICE memory (24 bytes): a captured decode step reads them at
  * replay time, so a new seed / temperature / top-k / top-p per request (HF generate kwargs) needs one small
  * host-to-device copy, not a new capture. The caller validates temperature > 0 and 0 < top_p <= 1. */
 typedef struct u2_sample_params {
